@@ -1,0 +1,167 @@
+// common.cuh -- shared declarations of libgsr (sm_100a).  Product code: never includes anything from oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gsr.h"
+
+namespace gsr {
+
+constexpr int TILE = 16;            // rasterizer.gd:4 TILE_SIZE
+constexpr int NUM_PLANES = 15;      // 60-float Splat = 15 float4 planes in SoA
+constexpr int PROJ_THREADS = 256;   // gsplat_projection.glsl:31 local_size_x
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_last_error(const char *fmt, ...);
+
+#define GSR_CUDA_TRY(expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::gsr::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? GSR_ERR_OOM : GSR_ERR_CUDA;                 \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// "gsr deterministic math" (DESIGN.md section 4).  One IEEE binary32 op per operator, no implicit
+// contraction (the library is compiled with -fmad=false), explicit __fmaf_rn where the spec says so.
+// GLSL min/max/clamp semantics written out (gsplat_projection.glsl uses clamp/max).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float g_max(float x, float y) { return (x < y) ? y : x; }
+__device__ __forceinline__ float g_min(float x, float y) { return (y < x) ? y : x; }
+__device__ __forceinline__ float g_clamp(float x, float lo, float hi) { return g_min(g_max(x, lo), hi); }
+
+// 2^t: clamp to [-127,128], round-half-even via the 1.5*2^23 magic constant, degree-6 polynomial on
+// [-0.5,0.5] (Horner, fma), scale 2^n assembled in the exponent field (n=-127 -> 0, n=128 -> +inf).
+__device__ __forceinline__ float det_exp2(float t) {
+    const float MAGIC = 12582912.0f;
+    float tc = g_min(g_max(t, -127.0f), 128.0f);
+    float tm = __fadd_rn(tc, MAGIC);
+    float nf = __fsub_rn(tm, MAGIC);
+    float f = __fsub_rn(tc, nf);
+    float p = 0x1.446c7ep-13f;
+    p = __fmaf_rn(p, f, 0x1.5f48c8p-10f);
+    p = __fmaf_rn(p, f, 0x1.3b29d8p-7f);
+    p = __fmaf_rn(p, f, 0x1.c6aeccp-5f);
+    p = __fmaf_rn(p, f, 0x1.ebfbe0p-3f);
+    p = __fmaf_rn(p, f, 0x1.62e430p-1f);
+    p = __fmaf_rn(p, f, 1.0f);
+    uint32_t sbits = (__float_as_uint(tm) << 23) + 0x3F800000u;
+    return __fmul_rn(p, __uint_as_float(sbits));
+}
+
+// GLSL exp(x) := 2^(x*log2e), log2e rounded to binary32.
+__device__ __forceinline__ float det_exp(float x) { return det_exp2(__fmul_rn(x, 0x1.715476p+0f)); }
+
+__device__ __forceinline__ float det_log2(float x) {
+    int eadj = 0;
+    if (x < 0x1p-126f) { x = __fmul_rn(x, 0x1p+32f); eadj = -32; }
+    uint32_t u = __float_as_uint(x);
+    int e = (int)(u >> 23) - 127;
+    float m = __uint_as_float((u & 0x007FFFFFu) | 0x3F800000u);
+    if (m >= 0x1.6a09e6p+0f) { m = __fmul_rn(m, 0.5f); e += 1; }
+    float s = __fdiv_rn(__fsub_rn(m, 1.0f), __fadd_rn(m, 1.0f));
+    float z = __fmul_rn(s, s);
+    float g = 0x1.ba18b8p-2f;
+    g = __fmaf_rn(g, z, 0x1.27471ep-1f);
+    g = __fmaf_rn(g, z, 0x1.ec70e6p-1f);
+    g = __fmaf_rn(g, z, 0x1.715476p+1f);
+    return __fadd_rn((float)(e + eadj), __fmul_rn(s, g));
+}
+
+// GLSL pow(x,y) := exp2(y*log2(x)), pow(x<=0, y>0) := 0.
+__device__ __forceinline__ float det_pow(float x, float y) {
+    if (!(x > 0.0f)) return 0.0f;
+    return det_exp2(__fmul_rn(y, det_log2(x)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-frame device state (one cudaMemsetAsync clears it; rasterizer.gd:127 clears histogram[0..1024])
+// ---------------------------------------------------------------------------------------------
+struct FrameState {
+    unsigned long long dup_total;  // M, true count (histogram[0] of the reference)
+    uint32_t dup_sorted;           // min(M, capacity): what the sort / ranges / compositor see
+    uint32_t visible;              // V
+    int32_t last_tile_plus1;       // 1 + largest tile id touched (0 = none); atomicMax target
+    uint32_t overflow;
+    uint32_t proj_ticket;          // dynamic block id for the projection look-back
+    uint32_t pad[9];
+};
+
+// Uniform block exactly as the reference uploads it (rasterizer.gd:126; gsplat_projection.glsl:75-80)
+struct Uniforms {
+    float camera_pos[3];
+    float model_scale;
+    int32_t dims[2];
+    float time;
+    float pad;
+};
+static_assert(sizeof(Uniforms) == 32, "uniform block must be 32 bytes");
+
+// ---------------------------------------------------------------------------------------------
+// radix sorter (radix_sort.cu)
+// ---------------------------------------------------------------------------------------------
+struct SortWorkspace {
+    uint32_t *hist = nullptr;       // [4][256] global digit histograms
+    uint32_t *status = nullptr;     // [4][max_tiles][256] decoupled look-back words
+    uint32_t *tickets = nullptr;    // [4] dynamic tile counters (same allocation as hist)
+    uint32_t *alt_keys = nullptr;   // ping-pong halves
+    uint32_t *alt_vals = nullptr;
+    uint32_t *n_dev = nullptr;      // device copy of n for the stand-alone sorter
+    uint64_t max_n = 0;
+    uint32_t max_tiles = 0;
+    int grid_hist = 0, grid_sweep_pairs = 0, grid_sweep_keys = 0;
+    size_t bytes() const;
+};
+int sort_workspace_create(SortWorkspace &ws, uint64_t max_n, bool need_alt_buffers);
+void sort_workspace_destroy(SortWorkspace &ws);
+// Sorts n (read on the device from *n_ptr, clamped to ws.max_n) pairs; 4 passes ping-pong between
+// keys/vals and alt_keys/alt_vals (the reference's two buffer halves, rasterizer.gd:145), result back in
+// keys/vals.  vals/alt_vals may be null (keys only).  *launches += kernels launched.
+int sort_pairs_device(SortWorkspace &ws, uint32_t *keys, uint32_t *vals, const uint32_t *n_ptr, uint32_t *alt_keys,
+                      uint32_t *alt_vals, cudaStream_t stream, int *launches);
+uint32_t sort_tile_keys();
+
+// ---------------------------------------------------------------------------------------------
+// stage launchers (projection.cu, ranges.cu, compositor.cu, ingest.cu)
+// ---------------------------------------------------------------------------------------------
+struct ProjectionArgs {
+    const float4 *soa;       // 15 planes of `plane_stride` float4 each
+    uint64_t plane_stride;
+    uint32_t num_splats;
+    float vp[32];            // view_matrix, projection_matrix (GLSL column-major)
+    Uniforms u;
+    int32_t band_y0, band_y1;
+    float4 *records;         // 3 float4 per splat id (RasterizeData layout)
+    uint32_t *keys, *values;
+    uint32_t capacity;
+    unsigned long long *lookback;  // one word per projection block
+    FrameState *frame;
+};
+int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
+uint32_t projection_num_blocks(uint32_t num_splats);
+
+int launch_tile_ranges(const uint32_t *sorted_keys, const FrameState *frame, uint2 *bounds, uint32_t num_tiles,
+                       int quirks, int sharded, int grid, cudaStream_t stream);
+
+struct CompositeArgs {
+    const float4 *records;
+    const uint32_t *values;
+    const uint2 *bounds;
+    float4 *out;             // W*H RGBA32F
+    int32_t width, height, tiles_x;
+    int32_t tile_begin;      // first tile id rendered (band_y0 * tiles_x)
+    int32_t num_tiles;       // tiles rendered
+    float heatmap_factor;
+    uint32_t target_tile_id; // 0xFFFFFFFF = none (rasterizer.gd:158)
+    float4 *pick;            // tile_splat_pos buffer (gsplat_render.glsl:33-36)
+};
+int launch_composite(const CompositeArgs &a, cudaStream_t stream);
+
+int launch_aos_to_soa(const float4 *aos, uint64_t count, float4 *soa, uint64_t plane_stride, uint64_t first, cudaStream_t stream);
+
+}  // namespace gsr

@@ -1,0 +1,503 @@
+// gsr_api.cu -- the C-ABI of libgsr.so (include/gsr.h): context, buffers, per-frame sequencing.
+//
+// Host-side counterpart of GaussianSplattingRasterizer.init_gpu / rasterize / get_splat_position /
+// cleanup_gpu (util/gaussian_splatting_rasterizer.gd:65-171) and of RenderingContext
+// (util/render_context.gd).  Fifteen compute dispatches with full barriers per frame in the reference
+// become 1 + 5 + 1 + 1 kernel launches on one CUDA stream, with no host synchronisation on the frame path.
+#include <stdarg.h>
+#include <stddef.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace gsr {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+struct gsr_ctx {
+    int device = 0;
+    uint32_t flags = 0;
+    uint64_t max_splats = 0, capacity = 0, plane_stride = 0, num_splats = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    float4 *soa = nullptr;       // 15 planes x plane_stride
+    float4 *records = nullptr;   // 3 float4 per splat id
+    uint32_t *keys = nullptr;    // 2 * capacity (ping-pong halves, rasterizer.gd:88)
+    uint32_t *vals = nullptr;    // 2 * capacity
+    SortWorkspace sort;
+    char *frame_blob = nullptr;  // FrameState followed by the projection look-back words (one memset)
+    size_t frame_blob_bytes = 0;
+    FrameState *frame = nullptr;
+    unsigned long long *lookback = nullptr;
+    uint2 *bounds = nullptr;
+    float4 *fb = nullptr, *fb_ext = nullptr;
+    float4 *pick = nullptr;
+    float4 *staging = nullptr;
+    uint64_t staging_splats = 0;
+    uint32_t *unsorted_keys = nullptr, *unsorted_vals = nullptr;
+    bool keep_unsorted = false;
+    int width = 0, height = 0, tiles_x = 0, tiles_y = 0, band_y0 = 0, band_y1 = 0;
+    bool band_set = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    uint32_t last_launches = 0;
+    int sm_count = 0;
+};
+
+struct gsr_sorter {
+    int device = 0;
+    SortWorkspace ws;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+
+int use_device(int device) {
+    GSR_CUDA_TRY(cudaSetDevice(device));
+    return GSR_OK;
+}
+
+int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_last_error("no CUDA device available (%s); libgsr has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+        return GSR_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_last_error("device ordinal %d out of range [0,%d)", device, count);
+        return GSR_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    GSR_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_last_error("device %d is sm_%d%d; libgsr is built for sm_100a only", device, prop.major, prop.minor);
+        return GSR_ERR_CUDA;
+    }
+    return GSR_OK;
+}
+
+float4 *framebuffer(gsr_ctx *c) { return c->fb_ext ? c->fb_ext : c->fb; }
+
+void free_ctx(gsr_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
+    sort_workspace_destroy(c->sort);
+    cudaFree(c->frame_blob); cudaFree(c->bounds); cudaFree(c->fb); cudaFree(c->pick); cudaFree(c->staging);
+    cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+}  // namespace
+
+extern "C" {
+
+GSR_API const char *gsr_error_string(int code) {
+    switch (code) {
+        case GSR_OK: return "ok";
+        case GSR_ERR_INVALID: return "invalid argument";
+        case GSR_ERR_CUDA: return "CUDA failure or no usable sm_100 device (no CPU fallback exists)";
+        case GSR_ERR_OOM: return "device out of memory";
+        case GSR_ERR_STATE: return "call order violated";
+        case GSR_ERR_OVERFLOW: return "duplicate list exceeded capacity";
+        default: return "unknown error";
+    }
+}
+GSR_API const char *gsr_last_error(void) { return g_last_error; }
+GSR_API const char *gsr_version(void) { return "gsr 0.1.0 (sm_100a)"; }
+GSR_API int gsr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
+    if (!cfg || !out || cfg->max_splats == 0) { set_last_error("gsr_create: null config/out or max_splats == 0"); return GSR_ERR_INVALID; }
+    *out = nullptr;
+    int rc = check_device(cfg->device);
+    if (rc) return rc;
+    if ((rc = use_device(cfg->device))) return rc;
+    if (cfg->max_splats >= (1ull << 32) - 256ull) { set_last_error("max_splats must be < 2^32-256"); return GSR_ERR_INVALID; }
+    gsr_ctx *c = new (std::nothrow) gsr_ctx();
+    if (!c) return GSR_ERR_OOM;
+    c->device = cfg->device;
+    c->flags = cfg->flags ? cfg->flags : GSR_FLAG_REFERENCE_QUIRKS;
+    c->max_splats = cfg->max_splats;
+    const uint64_t factor = cfg->dup_capacity_factor ? cfg->dup_capacity_factor : 10;  // rasterizer.gd:79
+    c->capacity = c->max_splats * factor;
+    if (c->capacity >= (1ull << 30)) c->capacity = (1ull << 30) - 1;  // look-back words carry 30-bit counts
+    c->plane_stride = (c->max_splats + 255ull) & ~255ull;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+
+#define TRY_ALLOC(ptr, bytes)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = cudaMalloc((void **)&(ptr), (bytes));                                     \
+        if (_e != cudaSuccess) {                                                                   \
+            set_last_error("cudaMalloc(%s, %llu B) -> %s", #ptr, (unsigned long long)(bytes), cudaGetErrorString(_e)); \
+            free_ctx(c);                                                                           \
+            return _e == cudaErrorMemoryAllocation ? GSR_ERR_OOM : GSR_ERR_CUDA;                   \
+        }                                                                                          \
+    } while (0)
+
+    cudaError_t se = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(se)); free_ctx(c); return GSR_ERR_CUDA; }
+    c->stream = c->own_stream;
+    TRY_ALLOC(c->soa, sizeof(float4) * NUM_PLANES * c->plane_stride);
+    TRY_ALLOC(c->records, sizeof(float4) * 3ull * c->max_splats);
+    TRY_ALLOC(c->keys, sizeof(uint32_t) * 2ull * c->capacity);
+    TRY_ALLOC(c->vals, sizeof(uint32_t) * 2ull * c->capacity);
+    const uint32_t lb_blocks = projection_num_blocks((uint32_t)c->max_splats);
+    c->frame_blob_bytes = sizeof(FrameState) + sizeof(unsigned long long) * (size_t)lb_blocks;
+    TRY_ALLOC(c->frame_blob, c->frame_blob_bytes);
+    c->frame = reinterpret_cast<FrameState *>(c->frame_blob);
+    c->lookback = reinterpret_cast<unsigned long long *>(c->frame_blob + sizeof(FrameState));
+    TRY_ALLOC(c->pick, sizeof(float4));
+    c->staging_splats = c->max_splats < (1ull << 18) ? c->max_splats : (1ull << 18);
+    TRY_ALLOC(c->staging, sizeof(float4) * NUM_PLANES * c->staging_splats);
+#undef TRY_ALLOC
+    rc = sort_workspace_create(c->sort, c->capacity, /*need_alt_buffers=*/false);
+    if (rc) { free_ctx(c); return rc; }
+    for (auto &e : c->ev) {
+        if (cudaEventCreate(&e) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
+    }
+    cudaMemsetAsync(c->soa, 0, sizeof(float4) * NUM_PLANES * c->plane_stride, c->stream);
+    cudaMemsetAsync(c->records, 0, sizeof(float4) * 3ull * c->max_splats, c->stream);
+    cudaMemsetAsync(c->pick, 0, sizeof(float4), c->stream);
+    cudaMemsetAsync(c->frame_blob, 0, c->frame_blob_bytes, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_last_error("init sync -> %s", cudaGetErrorString(e)); free_ctx(c); return GSR_ERR_CUDA; }
+    *out = c;
+    return GSR_OK;
+}
+
+GSR_API int gsr_destroy(gsr_ctx *ctx) {
+    free_ctx(ctx);
+    return GSR_OK;
+}
+
+GSR_API int gsr_set_stream(gsr_ctx *c, void *cuda_stream) {
+    if (!c) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    c->ev_valid = false;
+    return GSR_OK;
+}
+
+GSR_API int gsr_upload_splats_aos(gsr_ctx *c, const float *splat60, uint64_t first, uint64_t count) {
+    if (!c || (!splat60 && count)) return GSR_ERR_INVALID;
+    if (first + count > c->max_splats) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    uint64_t done = 0;
+    while (done < count) {
+        const uint64_t m = (count - done) < c->staging_splats ? (count - done) : c->staging_splats;
+        GSR_CUDA_TRY(cudaMemcpyAsync(c->staging, splat60 + (done * 60ull), m * 240ull, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = launch_aos_to_soa(c->staging, m, c->soa, c->plane_stride, first + done, c->stream))) return rc;
+        done += m;
+    }
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the caller may free/reuse splat60 (buffer_update semantics)
+    if (first + count > c->num_splats) c->num_splats = first + count;
+    return GSR_OK;
+}
+
+GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
+    if (!c || width < 1 || height < 1) { set_last_error("gsr_resize: bad size %dx%d", width, height); return GSR_ERR_INVALID; }
+    const int tx = (width + TILE - 1) / TILE, ty = (height + TILE - 1) / TILE;
+    if ((int64_t)tx * ty > 65536) {  // tile id must fit the 16 key bits above the depth code (gsplat_projection.glsl:222)
+        set_last_error("gsr_resize: %d tiles exceed the 16-bit tile id of the sort key", tx * ty);
+        return GSR_ERR_INVALID;
+    }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->bounds); c->bounds = nullptr;
+    cudaFree(c->fb); c->fb = nullptr;
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, sizeof(uint2) * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->fb, sizeof(float4) * (size_t)width * height));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->fb, 0, sizeof(float4) * (size_t)width * height, c->stream));
+    c->width = width; c->height = height; c->tiles_x = tx; c->tiles_y = ty;
+    if (!c->band_set) { c->band_y0 = 0; c->band_y1 = ty; }
+    if (c->band_y1 > ty) c->band_y1 = ty;
+    if (c->band_y0 > c->band_y1) c->band_y0 = c->band_y1;
+    return GSR_OK;
+}
+
+GSR_API int gsr_set_band(gsr_ctx *c, int32_t row_begin, int32_t row_end) {
+    if (!c || c->tiles_y == 0) { set_last_error("gsr_set_band before gsr_resize"); return GSR_ERR_STATE; }
+    if (row_begin < 0 || row_end > c->tiles_y || row_begin > row_end) { set_last_error("band [%d,%d) outside [0,%d]", row_begin, row_end, c->tiles_y); return GSR_ERR_INVALID; }
+    c->band_y0 = row_begin; c->band_y1 = row_end;
+    c->band_set = !(row_begin == 0 && row_end == c->tiles_y);
+    return GSR_OK;
+}
+
+static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor) {
+    if (!c || !view_proj || !uniforms32) return GSR_ERR_INVALID;
+    if (c->width == 0) { set_last_error("gsr_render before gsr_resize"); return GSR_ERR_STATE; }
+    Uniforms u;
+    memcpy(&u, uniforms32, sizeof u);
+    if (u.dims[0] != c->width || u.dims[1] != c->height) {
+        set_last_error("uniform dims %dx%d differ from gsr_resize %dx%d", u.dims[0], u.dims[1], c->width, c->height);
+        return GSR_ERR_INVALID;
+    }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    int launches = 0;
+    // rasterizer.gd:127-128: clear M + histograms, clear tile bounds
+    GSR_CUDA_TRY(cudaMemsetAsync(c->frame_blob, 0, sizeof(FrameState) + sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
+    GSR_CUDA_TRY(cudaEventRecord(c->ev[0], s));  // 'Start'
+
+    ProjectionArgs pa;
+    pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
+    memcpy(pa.vp, view_proj, sizeof pa.vp);
+    pa.u = u;
+    pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
+    pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
+    pa.lookback = c->lookback; pa.frame = c->frame;
+    if ((rc = launch_projection(pa, s))) return rc;
+    launches += pa.num_splats ? 1 : 0;
+    GSR_CUDA_TRY(cudaEventRecord(c->ev[1], s));  // 'Projection'
+
+    if (c->keep_unsorted) {
+        GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_keys, c->keys, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
+        GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_vals, c->vals, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
+    }
+    const uint32_t *m_ptr = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(c->frame) + offsetof(FrameState, dup_sorted));
+    if ((rc = sort_pairs_device(c->sort, c->keys, c->vals, m_ptr, c->keys + c->capacity, c->vals + c->capacity, s, &launches))) return rc;
+    GSR_CUDA_TRY(cudaEventRecord(c->ev[2], s));  // 'Sort'
+
+    const int sharded = !(c->band_y0 == 0 && c->band_y1 == c->tiles_y);
+    const int quirks = (c->flags & GSR_FLAG_FIXED_RANGES) ? 0 : 1;
+    if ((rc = launch_tile_ranges(c->keys, c->frame, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), quirks, sharded, c->sm_count * 8, s))) return rc;
+    launches += 1;
+    GSR_CUDA_TRY(cudaEventRecord(c->ev[3], s));  // 'Boundaries'
+
+    CompositeArgs ca;
+    ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
+    ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
+    ca.tile_begin = c->band_y0 * c->tiles_x;
+    ca.num_tiles = (c->band_y1 - c->band_y0) * c->tiles_x;
+    ca.heatmap_factor = heatmap_factor;
+    ca.target_tile_id = 0xFFFFFFFFu;  // rasterizer.gd:158
+    ca.pick = c->pick;
+    if ((rc = launch_composite(ca, s))) return rc;
+    launches += ca.num_tiles > 0 ? 1 : 0;
+    GSR_CUDA_TRY(cudaEventRecord(c->ev[4], s));  // 'Render'
+    c->ev_valid = true;
+    c->last_launches = (uint32_t)launches;
+    return GSR_OK;
+}
+
+GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *out_host) {
+    int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
+    if (rc) return rc;
+    if (out_host) {
+        GSR_CUDA_TRY(cudaMemcpyAsync(out_host, framebuffer(c), sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+        GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return GSR_OK;
+}
+
+GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host) {
+    int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
+    if (rc) return rc;
+    if (pinned_host)
+        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, framebuffer(c), sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+    return GSR_OK;
+}
+
+GSR_API int gsr_sync(gsr_ctx *c) {
+    if (!c) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return GSR_OK;
+}
+
+GSR_API void *gsr_framebuffer_device_ptr(gsr_ctx *c) { return c ? (void *)framebuffer(c) : nullptr; }
+
+GSR_API int gsr_set_framebuffer_external(gsr_ctx *c, void *device_ptr) {
+    if (!c) return GSR_ERR_INVALID;
+    c->fb_ext = (float4 *)device_ptr;
+    return GSR_OK;
+}
+
+GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float out_xyzn[4]) {
+    if (!c || !out_xyzn) return GSR_ERR_INVALID;
+    if (c->width == 0) { set_last_error("gsr_pick before gsr_resize"); return GSR_ERR_STATE; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const uint32_t T = (uint32_t)(c->tiles_x * c->tiles_y);
+    const uint32_t t0 = (uint32_t)(c->band_y0 * c->tiles_x), t1 = (uint32_t)(c->band_y1 * c->tiles_x);
+    if (tile_id < T && tile_id >= t0 && tile_id < t1) {
+        CompositeArgs ca;
+        ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
+        ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
+        ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1;
+        ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
+        if ((rc = launch_composite(ca, c->stream))) return rc;
+    }
+    GSR_CUDA_TRY(cudaMemcpyAsync(out_xyzn, c->pick, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return GSR_OK;
+}
+
+GSR_API int gsr_get_stats(gsr_ctx *c, gsr_stats *out) {
+    if (!c || !out) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    FrameState fs;
+    GSR_CUDA_TRY(cudaMemcpyAsync(&fs, c->frame, sizeof fs, cudaMemcpyDeviceToHost, c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out->num_splats = c->num_splats;
+    out->duplicates = fs.dup_total;
+    out->visible = fs.visible;
+    out->capacity = c->capacity;
+    out->last_tile = (int64_t)fs.last_tile_plus1 - 1;
+    out->overflow = fs.overflow;
+    out->width = (uint32_t)c->width; out->height = (uint32_t)c->height;
+    out->tiles_x = (uint32_t)c->tiles_x; out->tiles_y = (uint32_t)c->tiles_y;
+    out->band_y0 = (uint32_t)c->band_y0; out->band_y1 = (uint32_t)c->band_y1;
+    out->kernel_launches = c->last_launches;
+    if (c->ev_valid) {
+        for (int i = 0; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[i], c->ev[i], c->ev[i + 1]));
+        GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[4], c->ev[0], c->ev[4]));
+    }
+    return GSR_OK;
+}
+
+GSR_API int gsr_debug_keep_unsorted(gsr_ctx *c, int enable) {
+    if (!c) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    if (enable && !c->unsorted_keys) {
+        GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_keys, sizeof(uint32_t) * c->capacity));
+        GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_vals, sizeof(uint32_t) * c->capacity));
+    }
+    c->keep_unsorted = enable != 0;
+    return GSR_OK;
+}
+
+GSR_API int gsr_debug_copy(gsr_ctx *c, int which, void *dst, size_t bytes) {
+    if (!c || !dst) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const void *src = nullptr;
+    size_t avail = 0;
+    switch (which) {
+        case GSR_BUF_RECORDS: src = c->records; avail = sizeof(float4) * 3ull * c->max_splats; break;
+        case GSR_BUF_KEYS: src = c->keys; avail = sizeof(uint32_t) * c->capacity; break;
+        case GSR_BUF_VALUES: src = c->vals; avail = sizeof(uint32_t) * c->capacity; break;
+        case GSR_BUF_BOUNDS: src = c->bounds; avail = sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y; break;
+        case GSR_BUF_KEYS_UNSORTED: src = c->unsorted_keys; avail = c->unsorted_keys ? sizeof(uint32_t) * c->capacity : 0; break;
+        case GSR_BUF_VALUES_UNSORTED: src = c->unsorted_vals; avail = c->unsorted_vals ? sizeof(uint32_t) * c->capacity : 0; break;
+        case GSR_BUF_FRAMEBUFFER: src = framebuffer(c); avail = sizeof(float4) * (size_t)c->width * c->height; break;
+        default: set_last_error("gsr_debug_copy: unknown buffer %d", which); return GSR_ERR_INVALID;
+    }
+    if (!src || bytes > avail) { set_last_error("gsr_debug_copy(%d): %zu bytes requested, %zu available", which, bytes, avail); return GSR_ERR_INVALID; }
+    GSR_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return GSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone sorter
+// ---------------------------------------------------------------------------------------------------
+GSR_API int gsr_sorter_create(int32_t device, uint64_t max_n, gsr_sorter **out) {
+    if (!out || max_n == 0) return GSR_ERR_INVALID;
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = use_device(device))) return rc;
+    gsr_sorter *s = new (std::nothrow) gsr_sorter();
+    if (!s) return GSR_ERR_OOM;
+    s->device = device;
+    rc = sort_workspace_create(s->ws, max_n, /*need_alt_buffers=*/true);
+    if (rc == GSR_OK && (cudaEventCreate(&s->e0) != cudaSuccess || cudaEventCreate(&s->e1) != cudaSuccess)) rc = GSR_ERR_CUDA;
+    if (rc) { sort_workspace_destroy(s->ws); delete s; return rc; }
+    *out = s;
+    return GSR_OK;
+}
+
+GSR_API int gsr_sorter_destroy(gsr_sorter *s) {
+    if (!s) return GSR_OK;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    sort_workspace_destroy(s->ws);
+    if (s->e0) cudaEventDestroy(s->e0);
+    if (s->e1) cudaEventDestroy(s->e1);
+    delete s;
+    return GSR_OK;
+}
+
+GSR_API int gsr_sorter_sort_device(gsr_sorter *s, void *d_keys, void *d_values, uint64_t n, void *cuda_stream) {
+    if (!s || (!d_keys && n)) return GSR_ERR_INVALID;
+    if (n > s->ws.max_n) { set_last_error("sort of %llu exceeds sorter capacity %llu", (unsigned long long)n, (unsigned long long)s->ws.max_n); return GSR_ERR_INVALID; }
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint32_t n32 = (uint32_t)n;
+    GSR_CUDA_TRY(cudaMemcpyAsync(s->ws.n_dev, &n32, sizeof n32, cudaMemcpyHostToDevice, st));
+    GSR_CUDA_TRY(cudaEventRecord(s->e0, st));
+    int launches = 0;
+    rc = sort_pairs_device(s->ws, (uint32_t *)d_keys, (uint32_t *)d_values, s->ws.n_dev, s->ws.alt_keys, d_values ? s->ws.alt_vals : nullptr, st, &launches);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaEventRecord(s->e1, st));
+    s->timed = true;
+    return GSR_OK;
+}
+
+GSR_API int gsr_sorter_last_ms(gsr_sorter *s, float *ms) {
+    if (!s || !ms || !s->timed) return GSR_ERR_STATE;
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaEventSynchronize(s->e1));
+    GSR_CUDA_TRY(cudaEventElapsedTime(ms, s->e0, s->e1));
+    return GSR_OK;
+}
+
+GSR_API int gsr_sort_pairs_host(int32_t device, uint32_t *keys, uint32_t *values, uint64_t n) {
+    if (n == 0) return GSR_OK;
+    if (!keys) return GSR_ERR_INVALID;
+    gsr_sorter *s = nullptr;
+    int rc = gsr_sorter_create(device, n, &s);
+    if (rc) return rc;
+    uint32_t *dk = nullptr, *dv = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dk, 4 * n);
+    if (e == cudaSuccess && values) e = cudaMalloc((void **)&dv, 4 * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dk, keys, 4 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && values) e = cudaMemcpy(dv, values, 4 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = gsr_sorter_sort_device(s, dk, dv, n, nullptr);
+        if (rc == GSR_OK) e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess && rc == GSR_OK) e = cudaMemcpy(keys, dk, 4 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == GSR_OK && values) e = cudaMemcpy(values, dv, 4 * n, cudaMemcpyDeviceToHost);
+    cudaFree(dk); cudaFree(dv);
+    gsr_sorter_destroy(s);
+    if (e != cudaSuccess) { set_last_error("gsr_sort_pairs_host: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GSR_ERR_OOM : GSR_ERR_CUDA; }
+    return rc;
+}
+
+}  // extern "C"

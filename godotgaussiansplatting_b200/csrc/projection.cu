@@ -1,0 +1,320 @@
+// projection.cu -- stage 1: projection + frustum cull + EWA 2-D covariance + SH colour + tile-key duplication.
+//
+// Replaces gsplat_projection.glsl:150-227 (one thread per splat).  Differences in *how*, not *what*:
+//   * splat attributes are read from 15 SoA float4 planes (culled splats touch 16 B, not the 240-B AoS
+//     struct; SH planes are only read for splats that actually emit keys);
+//   * the single contended atomicAdd (:196) is replaced by a block scan + decoupled look-back over the
+//     projection blocks, so duplicate offsets are an exclusive prefix sum in splat-id order -- the
+//     deterministic refinement of the reference's arbitrary atomic order (Q13);
+//   * the per-thread serial emit loop (:219-226, up to hundreds of keys from one lane) is replaced by a
+//     block-cooperative emit: every output slot of the block is produced by some thread (binary search
+//     over the block's offsets), so writes are perfectly coalesced and load-balanced;
+//   * M never leaves the GPU (the last block stores it in FrameState) -- same as the reference, which
+//     feeds it to indirect dispatches (:210-214).
+// The arithmetic follows the "gsr deterministic math" contract (common.cuh): this file is compiled with
+// -fmad=false, every operator below is one IEEE binary32 operation in GLSL parse order.
+#include "common.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+constexpr float SH_C2_0 = 1.0925484305920792f;
+constexpr float SH_C2_1 = 1.0925484305920792f;
+constexpr float SH_C2_2 = 0.31539156525252005f;
+constexpr float SH_C2_3 = 1.0925484305920792f;
+constexpr float SH_C2_4 = 0.5462742152960396f;
+constexpr float SH_C3_0 = 0.5900435899266435f;
+constexpr float SH_C3_1 = 2.890611442640554f;
+constexpr float SH_C3_2 = 0.4570457994644658f;
+constexpr float SH_C3_3 = 0.3731763325901154f;
+constexpr float SH_C3_4 = 0.4570457994644658f;
+constexpr float SH_C3_5 = 1.445305721320277f;
+constexpr float SH_C3_6 = 0.5900435899266435f;
+
+#define LB_AGG (1ull << 62)
+#define LB_PREFIX (2ull << 62)
+#define LB_VAL ((1ull << 62) - 1ull)
+
+struct Mat3 { float m[3][3]; };  // m[c][r], GLSL column-major
+
+// GLSL a*b: out[c][r] = (a[0][r]*b[c][0] + a[1][r]*b[c][1]) + a[2][r]*b[c][2]
+__device__ __forceinline__ Mat3 mat3_mul(const Mat3 &a, const Mat3 &b) {
+    Mat3 o;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) o.m[c][r] = (a.m[0][r] * b.m[c][0] + a.m[1][r] * b.m[c][1]) + a.m[2][r] * b.m[c][2];
+    return o;
+}
+__device__ __forceinline__ Mat3 mat3_transpose(const Mat3 &a) {
+    Mat3 o;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) o.m[c][r] = a.m[r][c];
+    return o;
+}
+
+__device__ __forceinline__ float ease_out_cubic(float x) {  // gsplat_projection.glsl:87-90
+    float a = 1.0f - x;
+    return 1.0f - a * a * a;
+}
+
+// gsplat_projection.glsl:94-121, one colour channel
+__device__ __forceinline__ float sh_channel(const float *sh, int ch, float x, float y, float z) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#define SHC(k) (sh[3 * (k) + ch])
+    float r = 0.5f + SHC(0) * SH_C0;
+    r = r - SHC(1) * SH_C1 * y;
+    r = r + SHC(2) * SH_C1 * z;
+    r = r - SHC(3) * SH_C1 * x;
+    r = r + SHC(4) * SH_C2_0 * xy;
+    r = r - SHC(5) * SH_C2_1 * yz;
+    r = r + SHC(6) * SH_C2_2 * (2.0f * zz - xx - yy);
+    r = r - SHC(7) * SH_C2_3 * xz;
+    r = r + SHC(8) * SH_C2_4 * (xx - yy);
+    r = r - SHC(9) * SH_C3_0 * y * (3.0f * xx - yy);
+    r = r + SHC(10) * SH_C3_1 * x * yz;
+    r = r - SHC(11) * SH_C3_2 * y * (4.0f * zz - xx - yy);
+    r = r + SHC(12) * SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    r = r - SHC(13) * SH_C3_4 * x * (4.0f * zz - xx - yy);
+    r = r + SHC(14) * SH_C3_5 * z * (xx - yy);
+    r = r - SHC(15) * SH_C3_6 * x * (xx - 3.0f * yy);
+#undef SHC
+    return g_max(0.0f, r);
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+// Warp-parallel decoupled look-back over one 64-bit word per block.  Returns the exclusive prefix.
+__device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsigned long long *status, uint32_t bid,
+                                                                 unsigned long long total, uint32_t lane) {
+    if (lane == 0) status[bid] = (bid == 0 ? LB_PREFIX : LB_AGG) | total;
+    if (bid == 0) return 0ull;
+    unsigned long long excl = 0ull;
+    int64_t start = (int64_t)bid - 1;
+    while (true) {
+        const int64_t t = start - (int64_t)lane;
+        unsigned long long v = (t >= 0) ? status[t] : LB_PREFIX;
+        while (__any_sync(0xffffffffu, (v >> 62) == 0ull)) {
+            if ((v >> 62) == 0ull) v = status[t];
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        unsigned long long c = (lane <= first) ? (v & LB_VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        excl += c;
+        if (pmask) break;
+        start -= 32;
+    }
+    if (lane == 0) status[bid] = LB_PREFIX | ((excl + total) & LB_VAL);
+    return excl;
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS) projection_kernel(const __grid_constant__ ProjectionArgs a) {
+    __shared__ uint32_t s_bid;
+    __shared__ uint32_t s_off[PROJ_THREADS];  // exclusive duplicate offsets inside the block
+    __shared__ uint32_t s_xy[PROJ_THREADS];   // x0 | y0 << 16
+    __shared__ uint32_t s_wd[PROJ_THREADS];   // rect width | depth16 << 16
+    __shared__ uint32_t s_wsum[PROJ_THREADS / 32];
+    __shared__ int32_t s_wlast[PROJ_THREADS / 32];
+    __shared__ unsigned long long s_base;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const uint32_t id = bid * PROJ_THREADS + tid;
+
+    const float *V = a.vp, *P = a.vp + 16;  // X[c][r] = X[4*c + r]
+    const int W = a.u.dims[0], H = a.u.dims[1];
+    const uint32_t gx = (uint32_t)((W + TILE - 1) / TILE), gy = (uint32_t)((H + TILE - 1) / TILE);
+    const float ms = a.u.model_scale;
+
+    uint32_t n = 0, x0u = 0, y0u = 0, wu = 0, depth = 0;
+    int32_t last_tile = -1;
+
+    if (id < a.num_splats) {
+        do {
+            const float4 pt = __ldg(a.soa + id);  // plane 0: position.xyz, time
+            // :158-166 frustum cull
+            const float sp0 = pt.x * ms, sp1 = pt.y * ms, sp2 = pt.z * ms;
+            float view[4], clip[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) view[r] = ((V[0 + r] * sp0 + V[4 + r] * sp1) + V[8 + r] * sp2) + V[12 + r] * 1.0f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) clip[r] = ((P[0 + r] * view[0] + P[4 + r] * view[1]) + P[8 + r] * view[2]) + P[12 + r] * view[3];
+            const float vb = clip[3] * 1.2f;
+            if (clip[0] < -vb || clip[1] < -vb || clip[2] < 0.0f || clip[0] > vb || clip[1] > vb || clip[2] > clip[3]) break;
+
+            const float4 ca = __ldg(a.soa + 1 * a.plane_stride + id);  // c00 c01 c02 c11
+            const float4 cb = __ldg(a.soa + 2 * a.plane_stride + id);  // c12 c22 opacity pad
+
+            // :169-174 load-in animation
+            const float splat_time = a.u.time - pt.w;
+            const float tf = ease_out_cubic(g_clamp(splat_time, 0.0f, 1.0f));
+            const float tfl = ease_out_cubic(g_clamp(splat_time - 0.35f, 0.0f, 1.0f));
+            const float splat_opacity = cb.z * tfl * tfl;
+            const float splat_scale = ms * (2.0f * (1.0f - tfl) + 1.0f * tfl);
+
+            // :124-142 project_covariance
+            Mat3 cov3 = {{{ca.x, ca.y, ca.z}, {ca.y, ca.w, cb.x}, {ca.z, cb.x, cb.y}}};
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) cov3.m[c][r] = cov3.m[c][r] * splat_scale * splat_scale;
+            const float tfi0 = P[0], tfi1 = P[5];
+            float focal0 = ((float)W * 0.5f) * tfi0, focal1 = ((float)H * 0.5f) * tfi1;
+            const float tanfov0 = 1.0f / tfi0, tanfov1 = 1.0f / tfi1;
+            const float z_inv = 1.0f / view[2];
+            focal0 = focal0 * z_inv;
+            focal1 = focal1 * z_inv;
+            const float mx = g_clamp(view[0] * z_inv, -tanfov0 * 1.3f, tanfov0 * 1.3f);
+            const float my = g_clamp(view[1] * z_inv, -tanfov1 * 1.3f, tanfov1 * 1.3f);
+            const Mat3 J = {{{focal0, 0.0f, -focal1 * mx}, {0.0f, focal1, -focal1 * my}, {0.0f, 0.0f, 0.0f}}};
+            const Mat3 V3 = {{{V[0], V[1], V[2]}, {V[4], V[5], V[6]}, {V[8], V[9], V[10]}}};
+            const Mat3 IV = mat3_transpose(V3);
+            const Mat3 b = mat3_mul(IV, J);
+            const Mat3 tb = mat3_transpose(b);
+            const Mat3 t1 = mat3_mul(tb, cov3);
+            const Mat3 c2 = mat3_mul(t1, b);
+            const float cx = c2.m[0][0] + 0.3f, cy = c2.m[0][1], cz = c2.m[1][1] + 0.3f;
+
+            // :177-182
+            const float det = cx * cz - cy * cy;
+            if (det == 0.0f) break;
+            const float mid = 0.5f * (cx + cz);
+            const float sq = sqrtf(g_max(0.1f, mid * mid - det));
+            const float e1 = mid + 1.0f * sq, e2 = mid + -1.0f * sq;
+            if (e1 < 0.0f || e2 < 0.0f) break;
+
+            // :184-185
+            const float ndc0 = clip[0] / clip[3], ndc1 = clip[1] / clip[3], ndc2 = clip[2] / clip[3];
+            const float ipx = ((ndc0 + 1.0f) * 0.5f - 1.0f * (1.0f - tf)) * (float)(W - 1);
+            const float ipy = ((ndc1 + 1.0f) * 0.5f - 0.75f * (1.0f - tf)) * (float)(H - 1);
+
+            // :190-194
+            const float radius = det_pow(splat_opacity, 0.2f) * 2.5f * sqrtf(g_max(e1, e2));
+            if (!(fabsf(ipx) <= 3.0e38f) || !(fabsf(ipy) <= 3.0e38f) || !(radius <= 3.0e38f)) break;  // gsr spec: non-finite => culled
+            const float fgx = (float)gx, fgy = (float)gy;
+            int32_t x0 = (int32_t)g_clamp((ipx - radius) / 16.0f, 0.0f, fgx);
+            int32_t y0 = (int32_t)g_clamp((ipy - radius) / 16.0f, 0.0f, fgy);
+            int32_t x1 = (int32_t)g_clamp(ceilf((ipx + radius) / 16.0f), 0.0f, fgx);
+            int32_t y1 = (int32_t)g_clamp(ceilf((ipy + radius) / 16.0f), 0.0f, fgy);
+            // largest tile of the un-banded rect (global Q10 bookkeeping for sharded runs)
+            if ((uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) != 0u) last_tile = (y1 - 1) * (int32_t)gx + (x1 - 1);
+            if (y0 < a.band_y0) y0 = a.band_y0;
+            if (y1 > a.band_y1) y1 = a.band_y1;
+            if (y1 < y0) y1 = y0;
+            const uint32_t nt = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+            if (nt == 0u) break;
+
+            // :198-206 record (SH planes are only touched here)
+            float sh[48];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const float4 v = __ldg(a.soa + (uint64_t)(3 + k) * a.plane_stride + id);
+                sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
+            }
+            const float d0 = sp0 - a.u.camera_pos[0], d1 = sp1 - a.u.camera_pos[1], d2 = sp2 - a.u.camera_pos[2];
+            const float inv_len = 1.0f / sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
+            const float dx = d0 * inv_len, dy = d1 * inv_len, dz = d2 * inv_len;
+            float4 r0, r1, r2;
+            r0.x = ipx; r0.y = ipy; r0.z = sp0; r0.w = sp1;                        // image_pos, pos_xy
+            r1.x = cz / det; r1.y = -cy / det; r1.z = cx / det; r1.w = sp2;        // conic, pos_z
+            r2.x = sh_channel(sh, 0, dx, dy, dz);
+            r2.y = sh_channel(sh, 1, dx, dy, dz);
+            r2.z = sh_channel(sh, 2, dx, dy, dz);
+            r2.w = splat_opacity;
+            float4 *rec = a.records + (uint64_t)id * 3u;
+            rec[0] = r0; rec[1] = r1; rec[2] = r2;
+
+            // :218
+            depth = ((uint32_t)(ndc2 * ndc2 * ndc2 * 65535.0f)) & 0xFFFFu;
+            n = nt; x0u = (uint32_t)x0; y0u = (uint32_t)y0; wu = (uint32_t)(x1 - x0);
+        } while (false);
+    }
+
+    // ---- block-exclusive scan of the duplicate counts ----
+    const uint32_t incl = warp_incl_scan_u32(n, lane);
+    if (lane == 31) s_wsum[warp] = incl;
+    const int32_t wl = __reduce_max_sync(0xffffffffu, last_tile);
+    if (lane == 0) s_wlast[warp] = wl;
+    const uint32_t nvis = (uint32_t)__syncthreads_count(n != 0u);
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < PROJ_THREADS / 32; ++w) {
+        const uint32_t s = s_wsum[w];
+        if (w < warp) woff += s;
+        total += s;
+    }
+    s_off[tid] = woff + incl - n;
+    s_xy[tid] = x0u | (y0u << 16);
+    s_wd[tid] = wu | (depth << 16);
+
+    // ---- chained scan across blocks (warp 0) + per-block counters ----
+    if (warp == 0) {
+        const unsigned long long base = lookback_exclusive(a.lookback, bid, (unsigned long long)total, lane);
+        if (lane == 0) {
+            s_base = base;
+            if (nvis) atomicAdd(&a.frame->visible, nvis);
+            int32_t bl = -1;
+#pragma unroll
+            for (int w = 0; w < PROJ_THREADS / 32; ++w) bl = bl > s_wlast[w] ? bl : s_wlast[w];
+            if (bl >= 0) atomicMax(&a.frame->last_tile_plus1, bl + 1);
+            if (bid == gridDim.x - 1) {  // tickets are dense: this block closes the scan => M is known
+                const unsigned long long m = base + total;
+                a.frame->dup_total = m;
+                a.frame->dup_sorted = m < (unsigned long long)a.capacity ? (uint32_t)m : a.capacity;
+                a.frame->overflow = m > (unsigned long long)a.capacity ? 1u : 0u;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+
+    // ---- block-cooperative emit (:219-226): slot j of the block -> owner splat by binary search ----
+    for (uint32_t j = tid; j < total; j += PROJ_THREADS) {
+        uint32_t lo = 0, hi = PROJ_THREADS - 1;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= j) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t r = j - s_off[lo];
+        const uint32_t xy = s_xy[lo], wd = s_wd[lo];
+        const uint32_t w = wd & 0xFFFFu;
+        const uint32_t ry = r / w, rx = r - ry * w;
+        const uint32_t tile_id = ((xy >> 16) + ry) * gx + (xy & 0xFFFFu) + rx;
+        const unsigned long long g = base + j;
+        if (g < (unsigned long long)a.capacity) {
+            a.keys[g] = (tile_id << 16) | (wd >> 16);
+            a.values[g] = bid * PROJ_THREADS + lo;
+        }
+    }
+}
+
+}  // namespace
+
+uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_THREADS - 1) / PROJ_THREADS; }
+
+int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
+    const uint32_t blocks = projection_num_blocks(a.num_splats);
+    if (blocks == 0) return GSR_OK;
+    projection_kernel<<<blocks, PROJ_THREADS, 0, stream>>>(a);
+    GSR_CUDA_TRY(cudaGetLastError());
+    return GSR_OK;
+}
+
+}  // namespace gsr

@@ -1,0 +1,159 @@
+/*
+ * gsr.h -- C-ABI of libgsr.so: the B200-native (sm_100a) forward 3D-Gaussian-splatting rasterizer that
+ * replaces the body of 2Retr0/GodotGaussianSplatting's `GaussianSplattingRasterizer`
+ * (util/gaussian_splatting_rasterizer.gd) plus the six compute shaders it dispatches
+ * (resources/shaders/compute/*.glsl) and the RenderingDevice wrapper (util/render_context.gd).
+ *
+ * The reference has no native/FFI boundary of its own: its "plugin API" is the GDScript class.  Each
+ * entry point below cites the reference interface it replaces (paths relative to the reference root).
+ * A Godot host binds these through a GDExtension shim or C# P/Invoke; this repo's
+ * tests and bench bind them with Python ctypes (godotgaussiansplatting_b200/_lib.py).
+ *
+ * Conventions: plain C, opaque handle, `int` status returns (0 = GSR_OK), no exceptions cross the
+ * boundary, no torch/CUDA types in signatures (device pointers and streams travel as void*).
+ * All calls on one handle must be serialised by the caller (the reference calls everything from the
+ * render thread: main.gd:122,152,156).  There is NO CPU fallback: every entry point fails with
+ * GSR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GSR_H_
+#define GSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_API __attribute__((visibility("default")))
+
+/* ---- status codes ---- */
+enum {
+    GSR_OK = 0,
+    GSR_ERR_INVALID = 1,  /* bad argument / out-of-range size */
+    GSR_ERR_CUDA = 2,     /* CUDA runtime failure, or no usable device (see gsr_last_error) */
+    GSR_ERR_OOM = 3,      /* device allocation failed */
+    GSR_ERR_STATE = 4,    /* call order violated (e.g. render before resize) */
+    GSR_ERR_OVERFLOW = 5  /* duplicate list exceeded capacity (main.gd:100 "(buffer overflow!)") */
+};
+
+/* ---- gsr_config.flags ---- */
+#define GSR_FLAG_REFERENCE_QUIRKS 0x1u /* reproduce gsplat_boundaries.glsl:47-49 tile-range quirks (Q10); default */
+#define GSR_FLAG_FIXED_RANGES     0x2u /* corrected tile ranges instead (every occupied tile gets [start,end)) */
+
+/* ---- gsr_debug_copy selectors (parity taps; not on the frame path) ---- */
+enum {
+    GSR_BUF_RECORDS = 0, /* 48 B RasterizeData per splat id (gsplat_projection.glsl:42-48), max_splats entries */
+    GSR_BUF_KEYS = 1,    /* sorted keys, M entries (descriptors['sort_keys'] half 0) */
+    GSR_BUF_VALUES = 2,  /* sorted values, M entries (descriptors['sort_values'] half 0) */
+    GSR_BUF_BOUNDS = 3,  /* uvec2 per tile (descriptors['tile_bounds']) */
+    GSR_BUF_KEYS_UNSORTED = 4,  /* keys in emission order (only valid if flags keep them; see gsr_debug_keep_unsorted) */
+    GSR_BUF_VALUES_UNSORTED = 5,
+    GSR_BUF_FRAMEBUFFER = 6  /* RGBA32F W*H (descriptors['render_texture']) */
+};
+
+typedef struct gsr_ctx gsr_ctx;       /* one rasterizer = one GaussianSplattingRasterizer instance */
+typedef struct gsr_sorter gsr_sorter; /* stand-alone radix sorter (config c5 microbench) */
+
+typedef struct gsr_config {
+    int32_t device;               /* CUDA ordinal (RenderingServer.get_rendering_device(), rasterizer.gd:70) */
+    uint32_t flags;               /* GSR_FLAG_*; 0 = GSR_FLAG_REFERENCE_QUIRKS */
+    uint64_t max_splats;          /* point_cloud.size (rasterizer.gd:79,83) */
+    uint32_t dup_capacity_factor; /* sort capacity = factor * max_splats; 0 -> 10 (rasterizer.gd:79) */
+    uint32_t reserved;
+} gsr_config;
+
+typedef struct gsr_stats {
+    uint64_t num_splats;  /* highest uploaded splat index + 1 */
+    uint64_t duplicates;  /* M = histogram[0] of the reference (main.gd:98) -- true count, may exceed capacity */
+    uint64_t visible;     /* V: splats that passed the cull and touch >= 1 tile */
+    uint64_t capacity;    /* sort capacity in pairs */
+    int64_t last_tile;    /* largest tile id touched by any visible splat (-1 if none) */
+    uint32_t overflow;    /* 1 if duplicates > capacity in the last frame */
+    uint32_t width, height, tiles_x, tiles_y;
+    uint32_t band_y0, band_y1;  /* tile-row band rendered by this context */
+    uint32_t kernel_launches;   /* kernels launched by the last gsr_render */
+    float stage_ms[5];    /* 'Projection','Sort','Boundaries','Render' (rasterizer.gd:139,150,155,160) + total */
+} gsr_stats;
+
+/* ---- lifecycle: replaces _init/init_gpu/cleanup_gpu (rasterizer.gd:59-120) and RenderingContext
+ *      (render_context.gd:35-51).  Allocates every buffer of rasterizer.gd:83-92 (SoA instead of AoS). ---- */
+GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out);
+GSR_API int gsr_destroy(gsr_ctx *ctx);
+
+/* Use an existing CUDA stream (cudaStream_t as void*; NULL = the context's own stream).  The host that
+ * owns the GPU work queue (Godot's render thread; torch's current stream in bench.py) passes its stream. */
+GSR_API int gsr_set_stream(gsr_ctx *ctx, void *cuda_stream);
+
+/* ---- splat upload: replaces device.buffer_update(buffer, i*STRUCT_SIZE*stride*4, ...) of
+ *      PlyFile.load_gaussian_splats (util/ply_file.gd:71).  `splat60` = `count` std430 Splat structs of
+ *      60 floats (gsplat_projection.glsl:33-40) in host memory; converted to SoA planes on the device.
+ *      May be called repeatedly with disjoint or overlapping ranges (chunked async load). ---- */
+GSR_API int gsr_upload_splats_aos(gsr_ctx *ctx, const float *splat60, uint64_t first, uint64_t count);
+
+/* ---- texture_size setter (rasterizer.gd:26-48): reallocates tile_bounds + render_texture ---- */
+GSR_API int gsr_resize(gsr_ctx *ctx, int32_t width, int32_t height);
+
+/* Multi-GPU tile-row sharding (no counterpart in the single-device reference): this context renders tile
+ * rows [row_begin, row_end) only; keys keep the global tile id.  (0, tiles_y) restores the full frame. */
+GSR_API int gsr_set_band(gsr_ctx *ctx, int32_t row_begin, int32_t row_end);
+
+/* ---- rasterize() (rasterizer.gd:122-160).
+ *      view_proj: the 128-byte push constant of update_camera_matrices (rasterizer.gd:181-193):
+ *                 view_matrix then projection_matrix, GLSL column-major.
+ *      uniforms:  the 32-byte uniform block of rasterizer.gd:126, byte-identical:
+ *                 float camera_pos[3], float model_scale, int32 width, int32 height, float time, pad.
+ *                 (width/height must equal the gsr_resize values.)
+ *      heatmap_factor: float(should_enable_heatmap) (rasterizer.gd:158).
+ *      out_rgba32f_host: NULL (frame stays on the device, like the reference's Texture2DRD) or a host
+ *                 buffer of width*height*4 floats that receives the frame (synchronous).
+ *      Enqueues on the context's stream and returns without a host sync when out_rgba32f_host is NULL. */
+GSR_API int gsr_render(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
+                       float *out_rgba32f_host);
+
+/* Pipelined host read-back: enqueue the frame and an async copy into `pinned_host` (may be pageable, then the
+ * copy is synchronous); gsr_sync waits for everything enqueued so far. */
+GSR_API int gsr_render_async(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
+                             float *pinned_host);
+GSR_API int gsr_sync(gsr_ctx *ctx);
+
+/* Device pointer of the RGBA32F frame (render_texture.texture_rd_rid, rasterizer.gd:48,101); row-major W*H. */
+GSR_API void *gsr_framebuffer_device_ptr(gsr_ctx *ctx);
+/* Render into caller-owned device memory instead (>= width*height*16 bytes; NULL restores the internal one). */
+GSR_API int gsr_set_framebuffer_external(gsr_ctx *ctx, void *device_ptr);
+
+/* ---- get_splat_position() (rasterizer.gd:162-171): re-dispatches the compositor for `tile_id` and reads the
+ *      16-byte tile_splat_pos buffer (gsplat_render.glsl:33-36,105-110).  out_xyzn = splat_pos.xyz,
+ *      num_tile_splats -- persistent across calls exactly like the reference's storage buffer. ---- */
+GSR_API int gsr_pick(gsr_ctx *ctx, uint32_t tile_id, float heatmap_factor, float out_xyzn[4]);
+
+/* ---- update_debug_info() (main.gd:93-119): M, overflow, per-stage GPU ms.  Synchronises the stream. ---- */
+GSR_API int gsr_get_stats(gsr_ctx *ctx, gsr_stats *out);
+
+/* ---- parity taps: copy an internal buffer to host (synchronises).  bytes = size of dst. ---- */
+GSR_API int gsr_debug_copy(gsr_ctx *ctx, int which, void *dst, size_t bytes);
+/* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
+GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);
+
+/* ---- stand-alone radix sort (config c5; replaces radix_sort_{upsweep,spine,downsweep}.glsl x 4 passes,
+ *      rasterizer.gd:143-149).  Stable LSD sort of 32-bit keys (+ optional 32-bit values), 4 x 8-bit digits. ---- */
+GSR_API int gsr_sorter_create(int32_t device, uint64_t max_n, gsr_sorter **out);
+GSR_API int gsr_sorter_destroy(gsr_sorter *s);
+/* Device-resident sort: keys/values are device pointers (values may be NULL); result in place.
+ * cuda_stream: cudaStream_t as void* (NULL = default stream).  No host sync. */
+GSR_API int gsr_sorter_sort_device(gsr_sorter *s, void *d_keys, void *d_values, uint64_t n, void *cuda_stream);
+/* Host convenience: copies in, sorts on the GPU, copies out (values may be NULL). */
+GSR_API int gsr_sort_pairs_host(int32_t device, uint32_t *keys, uint32_t *values, uint64_t n);
+/* ms of the last gsr_sorter_sort_device call measured with CUDA events on its stream (synchronises). */
+GSR_API int gsr_sorter_last_ms(gsr_sorter *s, float *ms);
+
+/* ---- misc ---- */
+GSR_API const char *gsr_error_string(int code);
+GSR_API const char *gsr_last_error(void); /* thread-local detail of the last failure */
+GSR_API int gsr_device_count(void);
+GSR_API const char *gsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_H_ */

@@ -1,0 +1,78 @@
+"""Thin test helper that drives the C-ABI directly (no Python mirror in between)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from godotgaussiansplatting_b200 import _lib
+
+REC_DTYPE = np.dtype([("image_pos", "<f4", 2), ("pos_xy", "<f4", 2), ("conic", "<f4", 3), ("pos_z", "<f4"), ("color", "<f4", 4)])
+
+
+class Ctx:
+    def __init__(self, max_splats, width, height, flags=0, factor=10, device=0):
+        self.L = _lib.lib()
+        self.h = C.c_void_p()
+        cfg = _lib.GsrConfig(device, flags, max_splats, factor, 0)
+        _lib.check(self.L.gsr_create(C.byref(cfg), C.byref(self.h)), "gsr_create")
+        self.max_splats, self.w, self.hgt = max_splats, width, height
+        _lib.check(self.L.gsr_resize(self.h, width, height), "gsr_resize")
+
+    def close(self):
+        if self.h:
+            self.L.gsr_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload(self, splat60, first=0):
+        s = np.ascontiguousarray(splat60, dtype=np.float32)
+        _lib.check(self.L.gsr_upload_splats_aos(self.h, s.ctypes.data_as(C.POINTER(C.c_float)), first, s.shape[0]), "upload")
+
+    def resize(self, w, h):
+        _lib.check(self.L.gsr_resize(self.h, w, h), "gsr_resize")
+        self.w, self.hgt = w, h
+
+    def set_band(self, y0, y1):
+        _lib.check(self.L.gsr_set_band(self.h, y0, y1), "gsr_set_band")
+
+    def keep_unsorted(self):
+        _lib.check(self.L.gsr_debug_keep_unsorted(self.h, 1), "keep_unsorted")
+
+    def render(self, vp, uniforms, heatmap=0.0, readback=True):
+        vp = np.ascontiguousarray(vp, dtype=np.float32)
+        out = np.empty((self.hgt, self.w, 4), dtype=np.float32) if readback else None
+        _lib.check(self.L.gsr_render(self.h, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms, float(heatmap),
+                                     None if out is None else C.c_void_p(out.ctypes.data)), "gsr_render")
+        return out
+
+    def stats(self):
+        st = _lib.GsrStats()
+        _lib.check(self.L.gsr_get_stats(self.h, C.byref(st)), "gsr_get_stats")
+        return st
+
+    def copy(self, which, count, dtype):
+        out = np.empty(count, dtype=dtype)
+        if out.nbytes:
+            _lib.check(self.L.gsr_debug_copy(self.h, which, C.c_void_p(out.ctypes.data), out.nbytes), "gsr_debug_copy")
+        return out
+
+    def pick(self, tile_id, heatmap=0.0):
+        out = (C.c_float * 4)()
+        _lib.check(self.L.gsr_pick(self.h, tile_id, float(heatmap), out), "gsr_pick")
+        return np.array(list(out), dtype=np.float32)
+
+    def taps(self):
+        """All stage outputs of the last frame."""
+        st = self.stats()
+        m = int(min(st.duplicates, st.capacity))
+        T = st.tiles_x * st.tiles_y
+        return dict(stats=st, m=m,
+                    records=self.copy(_lib.GSR_BUF_RECORDS, self.max_splats, REC_DTYPE),
+                    keys=self.copy(_lib.GSR_BUF_KEYS, m, np.uint32), values=self.copy(_lib.GSR_BUF_VALUES, m, np.uint32),
+                    bounds=self.copy(_lib.GSR_BUF_BOUNDS, T * 2, np.uint32).reshape(T, 2))
