@@ -20,7 +20,7 @@ GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES = 0x1, 0x2
 EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_resize", "gsr_set_band", "gsr_render",
     "gsr_render_async", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
-    "gsr_get_stats", "gsr_debug_copy", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
+    "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
     "gsr_device_count", "gsr_version",
 ]
@@ -35,7 +35,15 @@ class GsrStats(C.Structure):
     _fields_ = [("num_splats", C.c_uint64), ("duplicates", C.c_uint64), ("visible", C.c_uint64), ("capacity", C.c_uint64),
                 ("last_tile", C.c_int64), ("overflow", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
                 ("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32), ("band_y0", C.c_uint32), ("band_y1", C.c_uint32),
-                ("kernel_launches", C.c_uint32), ("stage_ms", C.c_float * 5)]
+                ("kernel_launches", C.c_uint32), ("stage_ms", C.c_float * 5), ("staged", C.c_uint64)]
+
+
+GSR_HISTORY_FRAMES = 512
+
+
+class GsrFrameRecord(C.Structure):
+    _fields_ = [("frame_index", C.c_uint64), ("duplicates", C.c_uint64), ("visible", C.c_uint64), ("staged", C.c_uint64),
+                ("overflow", C.c_uint32), ("reserved", C.c_uint32), ("stage_ms", C.c_float * 5), ("reserved2", C.c_float)]
 
 
 class GsrError(RuntimeError):
@@ -70,6 +78,7 @@ def lib():
         L.gsr_set_framebuffer_external.argtypes = [vp, vp]
         L.gsr_pick.argtypes = [vp, u32, C.c_float, fp]
         L.gsr_get_stats.argtypes = [vp, C.POINTER(GsrStats)]
+        L.gsr_get_frame_history.argtypes = [vp, u32, C.POINTER(GsrFrameRecord), C.POINTER(u32)]
         L.gsr_debug_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.gsr_debug_keep_unsorted.argtypes = [vp, C.c_int]
         L.gsr_sorter_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp)]

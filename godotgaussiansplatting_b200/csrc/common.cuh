@@ -89,8 +89,11 @@ struct FrameState {
     int32_t last_tile_plus1;       // 1 + largest tile id touched (0 = none); atomicMax target
     uint32_t overflow;
     uint32_t proj_ticket;          // dynamic block id for the projection look-back
-    uint32_t pad[9];
+    uint32_t pad0;
+    unsigned long long staged;     // C: instances staged by the compositor (sum of consumed chunk sizes)
+    uint32_t pad[6];
 };
+static_assert(sizeof(FrameState) == 64, "FrameState is one 64-byte slot of the history ring");
 
 // Uniform block exactly as the reference uploads it (rasterizer.gd:126; gsplat_projection.glsl:75-80)
 struct Uniforms {
@@ -159,6 +162,7 @@ struct CompositeArgs {
     float heatmap_factor;
     uint32_t target_tile_id; // 0xFFFFFFFF = none (rasterizer.gd:158)
     float4 *pick;            // tile_splat_pos buffer (gsplat_render.glsl:33-36)
+    FrameState *frame;       // staged-instance counter (null: do not count, e.g. pick re-dispatch)
 };
 int launch_composite(const CompositeArgs &a, cudaStream_t stream);
 

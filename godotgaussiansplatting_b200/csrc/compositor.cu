@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(CHUNK) composite_kernel(const __grid_constant_
     const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);  // :62
 
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, t = 1.0f;
+    uint32_t staged = 0;  // SURVEY 8 symbol C: sum of consumed chunk sizes (uniform across the CTA)
 
     Staged nxt;
     nxt.a = make_float4(0.f, 0.f, 0.f, 0.f); nxt.b = nxt.a; nxt.o = 0.f;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(CHUNK) composite_kernel(const __grid_constant_
         const int buf = i & 1;
         const int sort_offset = CHUNK * i;
         const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
+        staged += (uint32_t)chunk;
         s_a[buf][tid] = nxt.a;
         s_b[buf][tid] = nxt.b;
         s_o[buf][tid] = nxt.o;
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(CHUNK) composite_kernel(const __grid_constant_
         for (int w = 0; w < CHUNK / 32; ++w) shared_t += s_vote[w];
         if (!(shared_t > 255u)) break;
     }
+
+    if (tid == 0 && staged && p.frame) atomicAdd(&p.frame->staged, (unsigned long long)staged);
 
     // :100-101
     const float hx = (float)num_splats * 5e-4f;

@@ -37,10 +37,11 @@ struct gsr_ctx {
     uint32_t *keys = nullptr;    // 2 * capacity (ping-pong halves, rasterizer.gd:88)
     uint32_t *vals = nullptr;    // 2 * capacity
     SortWorkspace sort;
-    char *frame_blob = nullptr;  // FrameState followed by the projection look-back words (one memset)
-    size_t frame_blob_bytes = 0;
-    FrameState *frame = nullptr;
-    unsigned long long *lookback = nullptr;
+    FrameState *ring = nullptr;  // GSR_HISTORY_FRAMES slots; slot = frame_counter % GSR_HISTORY_FRAMES
+    FrameState *frame = nullptr; // slot of the most recent frame
+    unsigned long long *lookback = nullptr;  // one word per projection block, cleared every frame
+    uint32_t lookback_blocks = 0;
+    uint64_t frame_counter = 0;
     uint2 *bounds = nullptr;
     float4 *fb = nullptr, *fb_ext = nullptr;
     float4 *pick = nullptr;
@@ -50,7 +51,7 @@ struct gsr_ctx {
     bool keep_unsorted = false;
     int width = 0, height = 0, tiles_x = 0, tiles_y = 0, band_y0 = 0, band_y1 = 0;
     bool band_set = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
     bool ev_valid = false;
     uint32_t last_launches = 0;
     int sm_count = 0;
@@ -98,9 +99,12 @@ void free_ctx(gsr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
     sort_workspace_destroy(c->sort);
-    cudaFree(c->frame_blob); cudaFree(c->bounds); cudaFree(c->fb); cudaFree(c->pick); cudaFree(c->staging);
+    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->fb); cudaFree(c->pick); cudaFree(c->staging);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
-    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->ev) {
+        for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        delete[] c->ev;
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -163,24 +167,25 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     TRY_ALLOC(c->records, sizeof(float4) * 3ull * c->max_splats);
     TRY_ALLOC(c->keys, sizeof(uint32_t) * 2ull * c->capacity);
     TRY_ALLOC(c->vals, sizeof(uint32_t) * 2ull * c->capacity);
-    const uint32_t lb_blocks = projection_num_blocks((uint32_t)c->max_splats);
-    c->frame_blob_bytes = sizeof(FrameState) + sizeof(unsigned long long) * (size_t)lb_blocks;
-    TRY_ALLOC(c->frame_blob, c->frame_blob_bytes);
-    c->frame = reinterpret_cast<FrameState *>(c->frame_blob);
-    c->lookback = reinterpret_cast<unsigned long long *>(c->frame_blob + sizeof(FrameState));
+    c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats);
+    TRY_ALLOC(c->ring, sizeof(FrameState) * GSR_HISTORY_FRAMES);
+    TRY_ALLOC(c->lookback, sizeof(unsigned long long) * (size_t)c->lookback_blocks);
+    c->frame = c->ring;
     TRY_ALLOC(c->pick, sizeof(float4));
     c->staging_splats = c->max_splats < (1ull << 18) ? c->max_splats : (1ull << 18);
     TRY_ALLOC(c->staging, sizeof(float4) * NUM_PLANES * c->staging_splats);
 #undef TRY_ALLOC
     rc = sort_workspace_create(c->sort, c->capacity, /*need_alt_buffers=*/false);
     if (rc) { free_ctx(c); return rc; }
-    for (auto &e : c->ev) {
-        if (cudaEventCreate(&e) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
+    c->ev = new (std::nothrow) cudaEvent_t[GSR_HISTORY_FRAMES * 5]();
+    if (!c->ev) { free_ctx(c); return GSR_ERR_OOM; }
+    for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) {
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
     }
     cudaMemsetAsync(c->soa, 0, sizeof(float4) * NUM_PLANES * c->plane_stride, c->stream);
     cudaMemsetAsync(c->records, 0, sizeof(float4) * 3ull * c->max_splats, c->stream);
     cudaMemsetAsync(c->pick, 0, sizeof(float4), c->stream);
-    cudaMemsetAsync(c->frame_blob, 0, c->frame_blob_bytes, c->stream);
+    cudaMemsetAsync(c->ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { set_last_error("init sync -> %s", cudaGetErrorString(e)); free_ctx(c); return GSR_ERR_CUDA; }
     *out = c;
@@ -262,10 +267,14 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     if (rc) return rc;
     cudaStream_t s = c->stream;
     int launches = 0;
-    // rasterizer.gd:127-128: clear M + histograms, clear tile bounds
-    GSR_CUDA_TRY(cudaMemsetAsync(c->frame_blob, 0, sizeof(FrameState) + sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
+    // rasterizer.gd:127-128: clear M (this frame's history slot) + look-back words, clear tile bounds
+    const uint32_t slot = (uint32_t)(c->frame_counter % GSR_HISTORY_FRAMES);
+    c->frame = c->ring + slot;
+    cudaEvent_t *ev = c->ev + 5 * slot;
+    GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
     GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
-    GSR_CUDA_TRY(cudaEventRecord(c->ev[0], s));  // 'Start'
+    GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 
     ProjectionArgs pa;
     pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
@@ -276,7 +285,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.lookback = c->lookback; pa.frame = c->frame;
     if ((rc = launch_projection(pa, s))) return rc;
     launches += pa.num_splats ? 1 : 0;
-    GSR_CUDA_TRY(cudaEventRecord(c->ev[1], s));  // 'Projection'
+    GSR_CUDA_TRY(cudaEventRecord(ev[1], s));  // 'Projection'
 
     if (c->keep_unsorted) {
         GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_keys, c->keys, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
@@ -284,13 +293,13 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     }
     const uint32_t *m_ptr = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(c->frame) + offsetof(FrameState, dup_sorted));
     if ((rc = sort_pairs_device(c->sort, c->keys, c->vals, m_ptr, c->keys + c->capacity, c->vals + c->capacity, s, &launches))) return rc;
-    GSR_CUDA_TRY(cudaEventRecord(c->ev[2], s));  // 'Sort'
+    GSR_CUDA_TRY(cudaEventRecord(ev[2], s));  // 'Sort'
 
     const int sharded = !(c->band_y0 == 0 && c->band_y1 == c->tiles_y);
     const int quirks = (c->flags & GSR_FLAG_FIXED_RANGES) ? 0 : 1;
     if ((rc = launch_tile_ranges(c->keys, c->frame, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), quirks, sharded, c->sm_count * 8, s))) return rc;
     launches += 1;
-    GSR_CUDA_TRY(cudaEventRecord(c->ev[3], s));  // 'Boundaries'
+    GSR_CUDA_TRY(cudaEventRecord(ev[3], s));  // 'Boundaries'
 
     CompositeArgs ca;
     ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
@@ -300,10 +309,12 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     ca.heatmap_factor = heatmap_factor;
     ca.target_tile_id = 0xFFFFFFFFu;  // rasterizer.gd:158
     ca.pick = c->pick;
+    ca.frame = c->frame;
     if ((rc = launch_composite(ca, s))) return rc;
     launches += ca.num_tiles > 0 ? 1 : 0;
-    GSR_CUDA_TRY(cudaEventRecord(c->ev[4], s));  // 'Render'
+    GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Render'
     c->ev_valid = true;
+    c->frame_counter += 1;
     c->last_launches = (uint32_t)launches;
     return GSR_OK;
 }
@@ -354,7 +365,7 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
         ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
         ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
         ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1;
-        ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
+        ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick; ca.frame = nullptr;
         if ((rc = launch_composite(ca, c->stream))) return rc;
     }
     GSR_CUDA_TRY(cudaMemcpyAsync(out_xyzn, c->pick, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -380,10 +391,38 @@ GSR_API int gsr_get_stats(gsr_ctx *c, gsr_stats *out) {
     out->tiles_x = (uint32_t)c->tiles_x; out->tiles_y = (uint32_t)c->tiles_y;
     out->band_y0 = (uint32_t)c->band_y0; out->band_y1 = (uint32_t)c->band_y1;
     out->kernel_launches = c->last_launches;
-    if (c->ev_valid) {
-        for (int i = 0; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[i], c->ev[i], c->ev[i + 1]));
-        GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[4], c->ev[0], c->ev[4]));
+    out->staged = fs.staged;
+    if (c->ev_valid && c->frame_counter > 0) {
+        cudaEvent_t *ev = c->ev + 5 * ((c->frame_counter - 1) % GSR_HISTORY_FRAMES);
+        for (int i = 0; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[i], ev[i], ev[i + 1]));
+        GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[4], ev[0], ev[4]));
     }
+    return GSR_OK;
+}
+
+GSR_API int gsr_get_frame_history(gsr_ctx *c, uint32_t max_frames, gsr_frame_record *out, uint32_t *n_out) {
+    if (!c || !out || !n_out) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    *n_out = 0;
+    if (!c->ev_valid || c->frame_counter == 0) return GSR_OK;
+    uint64_t n = c->frame_counter < GSR_HISTORY_FRAMES ? c->frame_counter : GSR_HISTORY_FRAMES;
+    if (n > max_frames) n = max_frames;
+    static thread_local FrameState host_ring[GSR_HISTORY_FRAMES];
+    GSR_CUDA_TRY(cudaMemcpyAsync(host_ring, c->ring, sizeof(FrameState) * GSR_HISTORY_FRAMES, cudaMemcpyDeviceToHost, c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint64_t fi = c->frame_counter - n + k;
+        const uint32_t slot = (uint32_t)(fi % GSR_HISTORY_FRAMES);
+        const FrameState &fs = host_ring[slot];
+        gsr_frame_record &r = out[k];
+        memset(&r, 0, sizeof r);
+        r.frame_index = fi; r.duplicates = fs.dup_total; r.visible = fs.visible; r.staged = fs.staged; r.overflow = fs.overflow;
+        cudaEvent_t *ev = c->ev + 5 * slot;
+        for (int i = 0; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&r.stage_ms[i], ev[i], ev[i + 1]));
+        GSR_CUDA_TRY(cudaEventElapsedTime(&r.stage_ms[4], ev[0], ev[4]));
+    }
+    *n_out = (uint32_t)n;
     return GSR_OK;
 }
 

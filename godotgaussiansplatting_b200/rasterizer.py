@@ -95,7 +95,8 @@ class GaussianSplattingRasterizer:
         return self._clock() - self._t0
 
     # ---- init_gpu (rasterizer.gd:65-114) ----
-    def init_gpu(self) -> None:
+    def init_gpu(self, load: bool = True) -> None:
+        """load=False creates the context only; the caller then streams splats in with `upload_splats`."""
         assert self.render_texture is not None, "An output Texture2DRD must be set!"
         L = _lib.lib()
         cfg = _lib.GsrConfig(self._device, self._flags, max(1, self.point_cloud.size), self._factor, 0)
@@ -105,6 +106,8 @@ class GaussianSplattingRasterizer:
         self._bind_texture()
         self.should_terminate_thread[0] = False
         self.num_splats_loaded[0] = 0
+        if not load:
+            return
         # the reference starts a loader thread (:114); here the load runs inline, chunk by chunk
         stride = max(1, self.point_cloud.size // 1000)
         load_gaussian_splats(self.point_cloud, stride, self._upload, self.should_terminate_thread, self.num_splats_loaded,
@@ -126,6 +129,17 @@ class GaussianSplattingRasterizer:
         self.is_loaded = True
         for cb in self.loaded_callbacks:
             cb()
+
+    def set_framebuffer_external(self, device_ptr: int) -> None:
+        _lib.check(_lib.lib().gsr_set_framebuffer_external(self._ctx, C.c_void_p(device_ptr)), "gsr_set_framebuffer_external")
+        self._bind_texture()
+
+    def render_raw(self, vp32: np.ndarray, uniforms32: bytes, heatmap: float = 0.0, host_ptr: int | None = None,
+                   asynchronous: bool = True) -> None:
+        """rasterize() with pre-packed push constants / uniform block (bench hot loop)."""
+        fn = _lib.lib().gsr_render_async if asynchronous else _lib.lib().gsr_render
+        _lib.check(fn(self._ctx, vp32.ctypes.data_as(C.POINTER(C.c_float)), uniforms32, float(heatmap),
+                      None if host_ptr is None else C.c_void_p(host_ptr)), "gsr_render")
 
     def set_stream(self, cuda_stream: int) -> None:
         _lib.check(_lib.lib().gsr_set_stream(self._ctx, C.c_void_p(cuda_stream)), "gsr_set_stream")
@@ -204,6 +218,14 @@ class GaussianSplattingRasterizer:
         st = _lib.GsrStats()
         _lib.check(_lib.lib().gsr_get_stats(self._ctx, C.byref(st)), "gsr_get_stats")
         return st
+
+    def frame_history(self, max_frames: int = _lib.GSR_HISTORY_FRAMES) -> list:
+        """Per-frame GPU timestamps + counters of the most recent frames (main.gd:106-119)."""
+        n = min(max_frames, _lib.GSR_HISTORY_FRAMES)
+        buf = (_lib.GsrFrameRecord * n)()
+        got = C.c_uint32(0)
+        _lib.check(_lib.lib().gsr_get_frame_history(self._ctx, n, buf, C.byref(got)), "gsr_get_frame_history")
+        return [buf[i] for i in range(got.value)]
 
     def read_framebuffer(self) -> np.ndarray:
         w, h = self._texture_size

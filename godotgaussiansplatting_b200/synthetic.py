@@ -19,8 +19,17 @@ CENTER = (0.0, 0.0, 2.5)
 
 def synthetic_ply_table(n: int, seed: int, sh_degree: int = 3, clusters: int = 64, ball_radius: float = 1.0,
                         chunk: int = 1 << 20) -> np.ndarray:
-    rng = np.random.default_rng(seed)
     out = np.empty((n, 62), dtype=np.float32)
+    for lo, blk in synthetic_ply_chunks(n, seed, sh_degree, clusters, ball_radius, chunk):
+        out[lo:lo + blk.shape[0]] = blk
+    return out
+
+
+def synthetic_ply_chunks(n: int, seed: int, sh_degree: int = 3, clusters: int = 64, ball_radius: float = 1.0,
+                         chunk: int = 1 << 20):
+    """Generator form of `synthetic_ply_table`: yields (first_index, (m, 62) float32 block) so that multi-million
+    splat scenes can be swizzled and uploaded chunk by chunk without holding the whole table."""
+    rng = np.random.default_rng(seed)
     # cluster parameters
     dirs = rng.standard_normal((clusters, 3))
     dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
@@ -45,7 +54,7 @@ def synthetic_ply_table(n: int, seed: int, sh_degree: int = 3, clusters: int = 6
         far = r > ball_radius
         pos[far] *= (ball_radius * (0.9 + 0.1 * rng.random(far.sum())) / r[far])[:, None]
         pos += np.asarray(CENTER)
-        blk = out[lo:hi]
+        blk = np.empty((m, 62), dtype=np.float32)
         blk[:, 0:3] = pos
         blk[:, 3:6] = 0.0
         blk[:, 6:9] = rng.normal(-0.4, 0.8, size=(m, 3))
@@ -59,7 +68,7 @@ def synthetic_ply_table(n: int, seed: int, sh_degree: int = 3, clusters: int = 6
         rot = rng.standard_normal((m, 4))
         rot /= np.linalg.norm(rot, axis=1, keepdims=True)
         blk[:, 58:62] = rot
-    return out
+        yield lo, blk
 
 
 def synthetic_ply(n: int, seed: int, **kw) -> PlyFile:

@@ -74,7 +74,21 @@ typedef struct gsr_stats {
     uint32_t band_y0, band_y1;  /* tile-row band rendered by this context */
     uint32_t kernel_launches;   /* kernels launched by the last gsr_render */
     float stage_ms[5];    /* 'Projection','Sort','Boundaries','Render' (rasterizer.gd:139,150,155,160) + total */
+    uint64_t staged;      /* C: instances actually staged by the compositor (sum of consumed chunk sizes) */
 } gsr_stats;
+
+/* One entry of the per-frame history ring (the last GSR_HISTORY_FRAMES frames rendered by a context). */
+#define GSR_HISTORY_FRAMES 512
+typedef struct gsr_frame_record {
+    uint64_t frame_index; /* 0-based count of gsr_render calls on this context */
+    uint64_t duplicates;  /* M */
+    uint64_t visible;     /* V */
+    uint64_t staged;      /* C */
+    uint32_t overflow;
+    uint32_t reserved;
+    float stage_ms[5];    /* Projection, Sort, Boundaries, Render, total -- CUDA events on the render stream */
+    float reserved2;
+} gsr_frame_record;
 
 /* ---- lifecycle: replaces _init/init_gpu/cleanup_gpu (rasterizer.gd:59-120) and RenderingContext
  *      (render_context.gd:35-51).  Allocates every buffer of rasterizer.gd:83-92 (SoA instead of AoS). ---- */
@@ -129,6 +143,10 @@ GSR_API int gsr_pick(gsr_ctx *ctx, uint32_t tile_id, float heatmap_factor, float
 
 /* ---- update_debug_info() (main.gd:93-119): M, overflow, per-stage GPU ms.  Synchronises the stream. ---- */
 GSR_API int gsr_get_stats(gsr_ctx *ctx, gsr_stats *out);
+
+/* Per-frame GPU timestamps + counters of the most recent frames, oldest first (capture_timestamp/
+ * get_captured_timestamp_gpu_time, rasterizer.gd:135-160, main.gd:106-119).  Synchronises the stream once. */
+GSR_API int gsr_get_frame_history(gsr_ctx *ctx, uint32_t max_frames, gsr_frame_record *out, uint32_t *n_out);
 
 /* ---- parity taps: copy an internal buffer to host (synchronises).  bytes = size of dst. ---- */
 GSR_API int gsr_debug_copy(gsr_ctx *ctx, int which, void *dst, size_t bytes);
