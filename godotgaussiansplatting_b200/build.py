@@ -42,10 +42,10 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None, out: str | None = None) -> str:
+    if not force and not needs_build() and out is None:
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (extra or []) + ["-o", OUT] + sources()
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (extra or []) + ["-o", out or OUT] + sources()
     env = dict(os.environ)
     # the image exports CC/CXX wrappers that nvcc must not pick up as host compiler
     res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], env=env, capture_output=True, text=True)
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":

@@ -1,107 +1,170 @@
 // compositor.cu -- stage 4: per-tile front-to-back alpha blend.  Replaces gsplat_render.glsl:50-111.
 //
-// One CTA per 16x16 tile, one thread per pixel (the reference's workgroup shape), 256-splat chunks staged
-// in shared memory.  What changes is the data movement, not the arithmetic:
-//   * the gather `culled_buffer[sort_buffer[...]]` (:72) for chunk i+1 is issued into registers BEFORE the
-//     blend loop of chunk i runs (software double buffering), so the random 48-B record gathers overlap
-//     the ~256*35 FP32 instructions of the blend instead of sitting between two barriers;
-//   * only the 9 floats the blend needs (image_pos, conic, colour+opacity) are staged (36 B, not 48 B);
-//   * the tile-stop vote `atomicAdd(shared_t, uint(t*255))` (:97) becomes a warp reduction + 8 shared
-//     words (same sum, one barrier less per chunk);
-//   * the per-pixel early-out `t > 1/255` (:79) additionally breaks the warp's chunk loop when no lane is
-//     live, which is a pure skip of no-op iterations.
-// Arithmetic: "gsr deterministic math" (common.cuh; compiled -fmad=false): the two GLSL-legal contractions
-// of :84 and the three of :89 are explicit __fmaf_rn, exp() is det_exp().  Bit-identical to the oracle.
+// One CTA per 16x16 tile like the reference's workgroup, 256-splat chunks staged in shared memory, the
+// same per-pixel arithmetic and the same tile-stop vote.  What is Blackwell-specific is how the blend is
+// issued: the kernel is instruction-issue bound (ncu: 82 % issue-active, 2 % DRAM), so
+//   * every thread owns TWO horizontally adjacent pixels and the blend runs on packed fp32x2
+//     instructions (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2/FMUL2/FFMA2, sm_100+).  Each lane of a
+//     packed op is an ordinary IEEE binary32 operation, so results stay bit-identical to the oracle while
+//     the FP32 work of two pixels costs one issue slot (measured on B200: FFMA2 sustains the full
+//     128 lane-FMA/clk/SM at 2 warp-instructions/clk/SM, ubench/f32x2.cu);
+//   * per-splat control flow is gone: dead pixels (t <= 1/255, gsplat_render.glsl:79) are masked by
+//     selecting alpha = 0 (an exact no-op on colour and transmittance), the warp-level "all dead" test
+//     runs once per 4 splats, and the last chunk is padded with null splats (opacity 0);
+//   * the conic is pre-scaled at staging time (-0.5*cx, -0.5*cz, -cy: exact power-of-two/sign changes) so
+//     the `-0.5 * (...)` multiply of :84 disappears from the inner loop without changing any rounding;
+//   * the gather `culled_buffer[sort_buffer[...]]` (:72) for chunk i+1 is issued into registers before the
+//     blend loop of chunk i (software prefetch); one shared buffer suffices because the vote barrier
+//     already separates blend(i) from store(i+1);
+//   * the tile-stop vote `atomicAdd(shared_t, uint(t*255))` (:97) is a warp reduction + 4 shared words.
+// Arithmetic contract: "gsr deterministic math" (common.cuh): the GLSL-legal contractions of :84 and :89 are
+// explicit fma, exp() is the det_exp() polynomial (evaluated here two lanes at a time).
 #include "common.cuh"
 
 namespace gsr {
 
 namespace {
 
-constexpr int CHUNK = 256;  // gsplat_render.glsl:9 WORKGROUP_SIZE
+constexpr int CHUNK = 256;    // gsplat_render.glsl:9 WORKGROUP_SIZE: splats per staged chunk / pixels per tile
+constexpr int THREADS = 128;  // 2 pixels per thread
 constexpr float MIN_ALPHA = 1.0f / 255.0f;
 
-struct Staged {  // registers holding one gathered record
-    float4 a;    // image_pos.xy, conic.x, conic.y
-    float4 b;    // conic.z, color.rgb
-    float o;     // opacity
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 bc(float x) { return pk(x, x); }
+
+struct Staged {  // one gathered record, pre-scaled for the inner loop
+    float4 a;    // image_pos.x, image_pos.y, -0.5*conic.x, -0.5*conic.z
+    float4 b;    // -conic.y, opacity, color.r, color.g
+    float c;     // color.b
 };
+
+__device__ __forceinline__ Staged null_splat() {
+    Staged s;
+    s.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.c = 0.f;
+    return s;
+}
 
 __device__ __forceinline__ Staged gather(const float4 *__restrict__ records, const uint32_t *__restrict__ values, uint32_t idx) {
     const uint32_t v = __ldg(values + idx);
     const float4 *r = records + (uint64_t)v * 3u;
     const float4 r0 = __ldg(r + 0), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
     Staged s;
-    s.a = make_float4(r0.x, r0.y, r1.x, r1.y);
-    s.b = make_float4(r1.z, r2.x, r2.y, r2.z);
-    s.o = r2.w;
+    s.a = make_float4(r0.x, r0.y, -0.5f * r1.x, -0.5f * r1.z);
+    s.b = make_float4(-r1.y, r2.w, r2.x, r2.y);
+    s.c = r2.z;
     return s;
 }
 
-__global__ void __launch_bounds__(CHUNK) composite_kernel(const __grid_constant__ CompositeArgs p) {
-    __shared__ float4 s_a[2][CHUNK];
-    __shared__ float4 s_b[2][CHUNK];
-    __shared__ float s_o[2][CHUNK];
-    __shared__ uint32_t s_vote[CHUNK / 32];
+__global__ void __launch_bounds__(THREADS) composite_kernel(const __grid_constant__ CompositeArgs p) {
+    __shared__ float4 s_a[CHUNK];
+    __shared__ float4 s_b[CHUNK];
+    __shared__ float s_c[CHUNK];
+    __shared__ uint32_t s_vote[THREADS / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile_id = (uint32_t)p.tile_begin + blockIdx.x;
     const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
-    const int px = (int)(tx * TILE + (tid & 15u)), py = (int)(ty * TILE + (tid >> 4));
-    const float fpx = (float)px, fpy = (float)py;
+    const int px0 = (int)(tx * TILE + 2u * (tid & 7u)), py = (int)(ty * TILE + (tid >> 3));
+    const u64 npx2 = pk(-(float)px0, -(float)(px0 + 1));  // ox = image_pos.x - pixel.x  ==  image_pos.x + (-pixel.x)
+    const float fpy = (float)py;
 
     const uint2 bounds = p.bounds[tile_id];
     const int32_t diff = (int32_t)(bounds.y - bounds.x);
-    const int num_splats = diff > 0 ? diff : 0;                             // :61
+    const int num_splats = diff > 0 ? diff : 0;                              // :61
     const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);  // :62
 
-    float cr = 0.0f, cg = 0.0f, cb = 0.0f, t = 1.0f;
-    uint32_t staged = 0;  // SURVEY 8 symbol C: sum of consumed chunk sizes (uniform across the CTA)
+    u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;  // blended colour of the two pixels
+    float t0 = 1.0f, t1 = 1.0f;                    // transmittance of the two pixels
+    uint32_t staged = 0;                           // SURVEY 8 symbol C (uniform across the CTA)
 
-    Staged nxt;
-    nxt.a = make_float4(0.f, 0.f, 0.f, 0.f); nxt.b = nxt.a; nxt.o = 0.f;
-    if (num_iterations > 0 && (int)tid < num_splats) nxt = gather(p.records, p.values, bounds.x + tid);
+    Staged n0 = null_splat(), n1 = null_splat();
+    if (num_iterations > 0) {
+        if ((int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + tid);
+        if ((int)tid + THREADS < num_splats) n1 = gather(p.records, p.values, bounds.x + tid + THREADS);
+    }
+
+    const u64 L2E2 = bc(0x1.715476p+0f), MAGIC2 = bc(12582912.0f), ONE2 = bc(1.0f);
+    const u64 C6 = bc(0x1.446c7ep-13f), C5 = bc(0x1.5f48c8p-10f), C4 = bc(0x1.3b29d8p-7f), C3 = bc(0x1.c6aeccp-5f),
+              C2 = bc(0x1.ebfbe0p-3f), C1 = bc(0x1.62e430p-1f);
 
     for (int i = 0; i < num_iterations; ++i) {
-        const int buf = i & 1;
         const int sort_offset = CHUNK * i;
         const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
         staged += (uint32_t)chunk;
-        s_a[buf][tid] = nxt.a;
-        s_b[buf][tid] = nxt.b;
-        s_o[buf][tid] = nxt.o;
+        s_a[tid] = n0.a; s_b[tid] = n0.b; s_c[tid] = n0.c;
+        s_a[tid + THREADS] = n1.a; s_b[tid + THREADS] = n1.b; s_c[tid + THREADS] = n1.c;
         __syncthreads();
-        // prefetch the next chunk's record while this one is blended
-        if (i + 1 < num_iterations && sort_offset + CHUNK + (int)tid < num_splats)
-            nxt = gather(p.records, p.values, bounds.x + (uint32_t)(sort_offset + CHUNK) + tid);
+        // prefetch the next chunk's records while this one is blended (slots past the list end become null splats)
+        n0 = null_splat(); n1 = null_splat();
+        if (i + 1 < num_iterations) {
+            const int nb = sort_offset + CHUNK;
+            if (nb + (int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + (uint32_t)nb + tid);
+            if (nb + (int)tid + THREADS < num_splats) n1 = gather(p.records, p.values, bounds.x + (uint32_t)nb + tid + THREADS);
+        }
 
-        // :79-91
-        for (int j = 0; j < chunk; ++j) {
-            const bool live = t > MIN_ALPHA;
-            if (!__any_sync(0xffffffffu, live)) break;
-            if (live) {
-                const float4 a = s_a[buf][j];
-                const float4 b = s_b[buf][j];
-                const float op = s_o[buf][j];
-                const float ox = a.x - fpx, oy = a.y - fpy;
-                // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy
-                const float q = __fmaf_rn(b.x * oy, oy, a.z * ox * ox);
-                const float power = __fmaf_rn(-(a.w * ox), oy, -0.5f * q);
-                const float alpha = op * det_exp(power);
-                cr = __fmaf_rn(b.y * alpha, t, cr);
-                cg = __fmaf_rn(b.z * alpha, t, cg);
-                cb = __fmaf_rn(b.w * alpha, t, cb);
-                t = t * (1.0f - alpha);
+        // :79-91, four splats per liveness test; `chunk` rounded up to 4 reads null splats (opacity 0 => exact no-op)
+        const int chunk4 = (chunk + 3) & ~3;
+        for (int j = 0; j < chunk4; j += 4) {
+            if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 a = s_a[j + u];
+                const float4 b = s_b[j + u];
+                const float cbl = s_c[j + u];
+                const u64 ox2 = add2(bc(a.x), npx2);
+                const float oy = a.y - fpy;
+                // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy  with q = fma(cz*oy, oy, cx*ox*ox), power = fma(-(cy*ox), oy, -0.5*q)
+                const u64 a2 = mul2(mul2(bc(a.z), ox2), ox2);
+                const u64 h2 = fma2(bc(a.w * oy), bc(oy), a2);
+                const u64 pw2 = fma2(mul2(bc(b.x), ox2), bc(oy), h2);
+                // exp(power): det_exp(), two lanes at a time
+                float tl, th;
+                upk(mul2(pw2, L2E2), tl, th);
+                tl = g_min(g_max(tl, -127.0f), 128.0f);
+                th = g_min(g_max(th, -127.0f), 128.0f);
+                const u64 tc2 = pk(tl, th);
+                const u64 tm2 = add2(tc2, MAGIC2);
+                const u64 f2 = sub2(tc2, sub2(tm2, MAGIC2));
+                u64 e2 = fma2(C6, f2, C5);
+                e2 = fma2(e2, f2, C4);
+                e2 = fma2(e2, f2, C3);
+                e2 = fma2(e2, f2, C2);
+                e2 = fma2(e2, f2, C1);
+                e2 = fma2(e2, f2, ONE2);
+                float ml, mh;
+                upk(tm2, ml, mh);
+                const u64 sc2 = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
+                                   __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
+                // alpha = opacity * exp(power); dead pixels take alpha = 0 (the reference's loop exit for that pixel)
+                float al, ah;
+                upk(mul2(bc(b.y), mul2(e2, sc2)), al, ah);
+                al = (t0 > MIN_ALPHA) ? al : 0.0f;
+                ah = (t1 > MIN_ALPHA) ? ah : 0.0f;
+                const u64 al2 = pk(al, ah);
+                const u64 t2 = pk(t0, t1);
+                cr2 = fma2(mul2(bc(b.z), al2), t2, cr2);
+                cg2 = fma2(mul2(bc(b.w), al2), t2, cg2);
+                cb2 = fma2(mul2(bc(cbl), al2), t2, cb2);
+                upk(mul2(t2, sub2(ONE2, al2)), t0, t1);
             }
         }
 
-        // :97 tile-stop vote: continue only if sum over the 256 threads of uint(t*255) > 255
-        const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t * 255.0f));
+        // :97 tile-stop vote: continue only if the sum over the tile's 256 pixels of uint(t*255) exceeds 255
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t0 * 255.0f) + (uint32_t)(t1 * 255.0f));
         if (lane == 0) s_vote[warp] = wsum;
         __syncthreads();
         uint32_t shared_t = 0;
 #pragma unroll
-        for (int w = 0; w < CHUNK / 32; ++w) shared_t += s_vote[w];
+        for (int w = 0; w < THREADS / 32; ++w) shared_t += s_vote[w];
         if (!(shared_t > 255u)) break;
     }
 
@@ -109,22 +172,24 @@ __global__ void __launch_bounds__(CHUNK) composite_kernel(const __grid_constant_
 
     // :100-101
     const float hx = (float)num_splats * 5e-4f;
-    const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2 = 1.0f * (1.0f - hx) + 0.2f * hx;
-    const float k = 1.0f - t;
-    if (px < p.width && py < p.height) {
-        float4 o;
-        o.x = cr + h0 * k * p.heatmap_factor;
-        o.y = cg + h1 * k * p.heatmap_factor;
-        o.z = cb + h2 * k * p.heatmap_factor;
-        o.w = 1.0f;
-        p.out[(uint64_t)py * (uint64_t)p.width + (uint64_t)px] = o;
+    const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
+    float r0, r1, g0, g1, b0, b1;
+    upk(cr2, r0, r1); upk(cg2, g0, g1); upk(cb2, b0, b1);
+    if (py < p.height) {
+        float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
+        const float k0 = 1.0f - t0, k1 = 1.0f - t1;
+        if (px0 < p.width)
+            row[px0] = make_float4(r0 + h0 * k0 * p.heatmap_factor, g0 + h1 * k0 * p.heatmap_factor, b0 + h2c * k0 * p.heatmap_factor, 1.0f);
+        if (px0 + 1 < p.width)
+            row[px0 + 1] = make_float4(r1 + h0 * k1 * p.heatmap_factor, g1 + h1 * k1 * p.heatmap_factor, b1 + h2c * k1 * p.heatmap_factor, 1.0f);
     }
 
-    // :105-110 pick: the elected (first) lane of each 32-wide subgroup of the target tile
-    if (lane == 0 && tile_id == p.target_tile_id && t != 1.0f) {
+    // :105-110 pick: the elected (first) lane of each 32-wide subgroup of the reference's 16x16 workgroup is local
+    // index 32*s = pixel (0, 2*s) of the tile = first pixel of thread 16*s here
+    if ((tid & 15u) == 0u && tile_id == p.target_tile_id && t0 != 1.0f) {
         const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
-        const float4 r0 = p.records[(uint64_t)v * 3u + 0], r1 = p.records[(uint64_t)v * 3u + 1];
-        *p.pick = make_float4(r0.z, r0.w, r1.w, (float)num_splats);
+        const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
+        *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
     }
 }
 
@@ -132,7 +197,7 @@ __global__ void __launch_bounds__(CHUNK) composite_kernel(const __grid_constant_
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    composite_kernel<<<a.num_tiles, CHUNK, 0, stream>>>(a);
+    composite_kernel<<<a.num_tiles, THREADS, 0, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

@@ -252,7 +252,7 @@ struct SweepConfig { int threads, items; };
 #define GSR_SORT_THREADS 512
 #endif
 #ifndef GSR_SORT_ITEMS
-#define GSR_SORT_ITEMS 8
+#define GSR_SORT_ITEMS 12
 #endif
 constexpr int SWEEP_THREADS = GSR_SORT_THREADS;
 constexpr int SWEEP_ITEMS = GSR_SORT_ITEMS;

@@ -597,7 +597,8 @@ void orc_boundaries(const uint32_t *keys, int64_t m, int64_t T, uint32_t *bounds
  * tile_y0/tile_y1: tile-row band to render (pixels outside the band are not touched).
  * staged_out (nullable): C = sum over tiles and consumed chunks of chunk_size (SURVEY 8 symbol C). */
 void orc_render(const orc_record *records, const uint32_t *values, const uint32_t *bounds, int W, int H, float heatmap_factor,
-                uint32_t target_tile_id, int tile_y0, int tile_y1, float *out, float *pick, int64_t *staged_out) {
+                uint32_t target_tile_id, int tile_y0, int tile_y1, float *out, float *pick, int64_t *staged_out,
+                uint32_t *tile_staged /* nullable: per-tile consumed instance count */) {
     const int gx = (W + ORC_TILE - 1) / ORC_TILE;
     const float MIN_ALPHA = 1.0f / 255.0f;
     int64_t staged_total = 0;
@@ -611,11 +612,12 @@ void orc_render(const orc_record *records, const uint32_t *values, const uint32_
             const int num_iterations = (int)ceilf((float)num_splats / 256.0f);
             float col[ORC_WG][3], t[ORC_WG];
             for (int l = 0; l < ORC_WG; ++l) { col[l][0] = col[l][1] = col[l][2] = 0.0f; t[l] = 1.0f; }
-            uint32_t shared_t = 0xFFFFFFFFu;
+            uint32_t shared_t = 0xFFFFFFFFu, tile_consumed = 0;
             for (int i = 0; i < num_iterations && shared_t > 255u; ++i) {
                 const int sort_offset = ORC_WG * i;
                 const int chunk = (num_splats - sort_offset) < ORC_WG ? (num_splats - sort_offset) : ORC_WG;
                 staged_total += chunk;
+                tile_consumed += (uint32_t)chunk;
                 shared_t = 0;
                 for (int l = 0; l < ORC_WG; ++l) {
                     const float px = (float)(tx * ORC_TILE + (l & 15)), py = (float)(ty * ORC_TILE + (l >> 4));
@@ -639,6 +641,7 @@ void orc_render(const orc_record *records, const uint32_t *values, const uint32_
                     shared_t += (uint32_t)(tt * 255.0f); /* :97 atomicAdd(shared_t, uint(t*MIN_FACTOR)) */
                 }
             }
+            if (tile_staged) tile_staged[tile_id] = tile_consumed;
             /* :100-101 */
             const float hx = (float)num_splats * 5e-4f;
             const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2 = 1.0f * (1.0f - hx) + 0.2f * hx;
@@ -701,7 +704,7 @@ int orc_frame(const float *splat60, int64_t n, const float *vp, const orc_unifor
     orc_boundaries(keys, m, (int64_t)gx * gy, bounds, quirks, sharded ? last : -1);
     double t3 = now_ms();
     int64_t staged = 0;
-    orc_render(records, values, bounds, u->dims[0], u->dims[1], heatmap_factor, 0xFFFFFFFFu, band_y0, band_y1, out, NULL, &staged);
+    orc_render(records, values, bounds, u->dims[0], u->dims[1], heatmap_factor, 0xFFFFFFFFu, band_y0, band_y1, out, NULL, &staged, NULL);
     double t4 = now_ms();
     if (st) { st->staged = staged; st->ms_sort = t2 - t1; st->ms_boundaries = t3 - t2; st->ms_render = t4 - t3; }
     return 0;

@@ -56,7 +56,7 @@ def lib():
         L.orc_sort_pairs_shader_emulation.argtypes = [u32p, u32p, i64, i64]
         L.orc_boundaries.argtypes = [u32p, i64, i64, u32p, C.c_int, i64]
         L.orc_render.argtypes = [C.c_void_p, u32p, u32p, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_int, C.c_int, fp, fp,
-                                 C.POINTER(i64)]
+                                 C.POINTER(i64), u32p]
         L.orc_frame.restype = C.c_int
         L.orc_frame.argtypes = [fp, i64, fp, C.POINTER(_Uniforms), C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, u32p,
                                 u32p, i64, u32p, fp, C.POINTER(_FrameStats)]
@@ -168,8 +168,10 @@ def boundaries(sorted_keys, num_tiles, quirks=True, global_last_tile=-1) -> np.n
     return b
 
 
-def render(records, sorted_values, bounds, width, height, heatmap=0.0, target_tile=0xFFFFFFFF, band=None, pick=None):
-    """Returns (rgba[H,W,4] float32, staged C, pick[4])."""
+def render(records, sorted_values, bounds, width, height, heatmap=0.0, target_tile=0xFFFFFFFF, band=None, pick=None,
+           tile_staged=None):
+    """Returns (rgba[H,W,4] float32, staged C, pick[4]).  tile_staged: optional uint32[T] filled with the
+    number of instances each tile consumed before its stop rule fired."""
     recs = np.ascontiguousarray(records)
     assert recs.dtype == RECORD_DTYPE
     v = np.ascontiguousarray(sorted_values, dtype=np.uint32)
@@ -182,7 +184,7 @@ def render(records, sorted_values, bounds, width, height, heatmap=0.0, target_ti
     pk = np.zeros(4, dtype=np.float32) if pick is None else np.array(pick, dtype=np.float32)
     staged = C.c_int64(0)
     lib().orc_render(recs.ctypes.data, _u(v), _u(b), int(width), int(height), float(heatmap), int(target_tile) & 0xFFFFFFFF,
-                     int(y0), int(y1), _f(out), _f(pk), C.byref(staged))
+                     int(y0), int(y1), _f(out), _f(pk), C.byref(staged), None if tile_staged is None else _u(tile_staged))
     return out, int(staged.value), pk
 
 
