@@ -142,7 +142,7 @@ struct ProjectionArgs {
     float4 *records;         // 3 float4 per splat id (RasterizeData layout)
     uint32_t *keys, *values;
     uint32_t capacity;
-    unsigned long long *lookback;  // one word per projection block
+    unsigned long long *lookback;  // one word per projection warp (32 splats)
     FrameState *frame;
 };
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);

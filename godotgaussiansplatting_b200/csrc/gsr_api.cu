@@ -167,7 +167,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     TRY_ALLOC(c->records, sizeof(float4) * 3ull * c->max_splats);
     TRY_ALLOC(c->keys, sizeof(uint32_t) * 2ull * c->capacity);
     TRY_ALLOC(c->vals, sizeof(uint32_t) * 2ull * c->capacity);
-    c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats);
+    c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats) * (PROJ_THREADS / 32);  // one scan link per warp
     TRY_ALLOC(c->ring, sizeof(FrameState) * GSR_HISTORY_FRAMES);
     TRY_ALLOC(c->lookback, sizeof(unsigned long long) * (size_t)c->lookback_blocks);
     c->frame = c->ring;
@@ -272,7 +272,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     c->frame = c->ring + slot;
     cudaEvent_t *ev = c->ev + 5 * slot;
     GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats) * (PROJ_THREADS / 32), s));
     GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
     GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 

@@ -3,13 +3,13 @@
 // Replaces gsplat_projection.glsl:150-227 (one thread per splat).  Differences in *how*, not *what*:
 //   * splat attributes are read from 15 SoA float4 planes (culled splats touch 16 B, not the 240-B AoS
 //     struct; SH planes are only read for splats that actually emit keys);
-//   * the single contended atomicAdd (:196) is replaced by a block scan + decoupled look-back over the
-//     projection blocks, so duplicate offsets are an exclusive prefix sum in splat-id order -- the
+//   * the single contended atomicAdd (:196) is replaced by a warp scan + decoupled look-back over the
+//     projection warps (32 splats per link, no CTA barriers), so duplicate offsets are an exclusive prefix sum in splat-id order -- the
 //     deterministic refinement of the reference's arbitrary atomic order (Q13);
 //   * the per-thread serial emit loop (:219-226, up to hundreds of keys from one lane) is replaced by a
-//     block-cooperative emit: every output slot of the block is produced by some thread (binary search
-//     over the block's offsets), so writes are perfectly coalesced and load-balanced;
-//   * M never leaves the GPU (the last block stores it in FrameState) -- same as the reference, which
+//     warp-cooperative emit: every output slot of the warp is produced by some lane (binary search
+//     over the warp's 32 offsets), so writes are perfectly coalesced and load-balanced;
+//   * M never leaves the GPU (the last warp of the scan stores it in FrameState) -- same as the reference, which
 //     feeds it to indirect dispatches (:210-214).
 // The arithmetic follows the "gsr deterministic math" contract (common.cuh): this file is compiled with
 // -fmad=false, every operator below is one IEEE binary32 operation in GLSL parse order.
@@ -63,30 +63,6 @@ __device__ __forceinline__ float ease_out_cubic(float x) {  // gsplat_projection
     return 1.0f - a * a * a;
 }
 
-// gsplat_projection.glsl:94-121, one colour channel
-__device__ __forceinline__ float sh_channel(const float *sh, int ch, float x, float y, float z) {
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-#define SHC(k) (sh[3 * (k) + ch])
-    float r = 0.5f + SHC(0) * SH_C0;
-    r = r - SHC(1) * SH_C1 * y;
-    r = r + SHC(2) * SH_C1 * z;
-    r = r - SHC(3) * SH_C1 * x;
-    r = r + SHC(4) * SH_C2_0 * xy;
-    r = r - SHC(5) * SH_C2_1 * yz;
-    r = r + SHC(6) * SH_C2_2 * (2.0f * zz - xx - yy);
-    r = r - SHC(7) * SH_C2_3 * xz;
-    r = r + SHC(8) * SH_C2_4 * (xx - yy);
-    r = r - SHC(9) * SH_C3_0 * y * (3.0f * xx - yy);
-    r = r + SHC(10) * SH_C3_1 * x * yz;
-    r = r - SHC(11) * SH_C3_2 * y * (4.0f * zz - xx - yy);
-    r = r + SHC(12) * SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-    r = r - SHC(13) * SH_C3_4 * x * (4.0f * zz - xx - yy);
-    r = r + SHC(14) * SH_C3_5 * z * (xx - yy);
-    r = r - SHC(15) * SH_C3_6 * x * (xx - 3.0f * yy);
-#undef SHC
-    return g_max(0.0f, r);
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -99,7 +75,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane
 // Warp-parallel decoupled look-back over one 64-bit word per block.  Returns the exclusive prefix.
 __device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsigned long long *status, uint32_t bid,
                                                                  unsigned long long total, uint32_t lane) {
-    if (lane == 0) status[bid] = (bid == 0 ? LB_PREFIX : LB_AGG) | total;
+    // the caller has already published (bid == 0 ? PREFIX : AGGREGATE) | total
     if (bid == 0) return 0ull;
     unsigned long long excl = 0ull;
     int64_t start = (int64_t)bid - 1;
@@ -122,20 +98,128 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsign
     return excl;
 }
 
-__global__ void __launch_bounds__(PROJ_THREADS) projection_kernel(const __grid_constant__ ProjectionArgs a) {
+// ---- TMA (bulk async copy) + mbarrier helpers: SASS UBLKCP / SYNCS ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// SH colour (gsplat_projection.glsl:94-121), streamed six planes (= 8 coefficients x RGB) at a time so that at
+// most 24 coefficient registers are live.  `src[k * stride]` is SH plane k of this splat (shared slab or global).
+template <bool FROM_SMEM>
+__device__ __forceinline__ void sh_color(const float4 *src, uint64_t stride, float x, float y, float z, float col[3]) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    {
+        float sh[24];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float4 v = FROM_SMEM ? src[(uint64_t)k * stride] : __ldg(src + (uint64_t)k * stride);
+            sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+#define SHC(k) (sh[3 * (k) + ch])
+            float r = 0.5f + SHC(0) * SH_C0;
+            r = r - SHC(1) * SH_C1 * y;
+            r = r + SHC(2) * SH_C1 * z;
+            r = r - SHC(3) * SH_C1 * x;
+            r = r + SHC(4) * SH_C2_0 * xy;
+            r = r - SHC(5) * SH_C2_1 * yz;
+            r = r + SHC(6) * SH_C2_2 * (2.0f * zz - xx - yy);
+            r = r - SHC(7) * SH_C2_3 * xz;
+#undef SHC
+            col[ch] = r;
+        }
+    }
+    {
+        float sh[24];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float4 v = FROM_SMEM ? src[(uint64_t)(6 + k) * stride] : __ldg(src + (uint64_t)(6 + k) * stride);
+            sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+#define SHC(k) (sh[3 * ((k) - 8) + ch])
+            float r = col[ch];
+            r = r + SHC(8) * SH_C2_4 * (xx - yy);
+            r = r - SHC(9) * SH_C3_0 * y * (3.0f * xx - yy);
+            r = r + SHC(10) * SH_C3_1 * x * yz;
+            r = r - SHC(11) * SH_C3_2 * y * (4.0f * zz - xx - yy);
+            r = r + SHC(12) * SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+            r = r - SHC(13) * SH_C3_4 * x * (4.0f * zz - xx - yy);
+            r = r + SHC(14) * SH_C3_5 * z * (xx - yy);
+            r = r - SHC(15) * SH_C3_6 * x * (xx - 3.0f * yy);
+#undef SHC
+            col[ch] = g_max(0.0f, r);
+        }
+    }
+}
+
+// One warp = 32 consecutive splats = one link of the chained scan.  Warps never wait for each other (the only
+// CTA barrier broadcasts the block ticket).  Data movement per warp:
+//   phase 1: lane 0 issues three 512-byte TMA bulk copies (planes 0-2: position/time, covariance, opacity of the
+//            warp's 32 splats) into the warp's shared slab and everybody waits on the warp's mbarrier;
+//            cull + EWA + rect => duplicate count; the warp's aggregate is PUBLISHED here, before phase 2, so
+//            that successors never wait on this warp's colour work;
+//   phase 2: if at least SH_BULK_MIN lanes emit keys, twelve more 512-byte bulk copies bring the SH planes
+//            (6 KB in flight per warp at zero register cost); otherwise the few live lanes gather their
+//            192 bytes with plain 128-bit loads (sparse view / out-of-band warps of a multi-GPU shard);
+//   then records are written, the look-back resolves the warp's base offset, and the warp emits its keys.
+constexpr int PROJ_WARPS = PROJ_THREADS / 32;
+constexpr int SH_BULK_MIN = 12;
+#ifndef GSR_PROJ_MIN_BLOCKS
+#define GSR_PROJ_MIN_BLOCKS 3
+#endif
+constexpr size_t PROJ_SLAB_BYTES = sizeof(float4) * NUM_PLANES * 32;             // 7680 B per warp
+constexpr size_t PROJ_SMEM_BYTES = PROJ_SLAB_BYTES * PROJ_WARPS;                // 61440 B per CTA
+
+__global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_kernel(const __grid_constant__ ProjectionArgs a) {
+    extern __shared__ __align__(128) unsigned char proj_smem[];
     __shared__ uint32_t s_bid;
-    __shared__ uint32_t s_off[PROJ_THREADS];  // exclusive duplicate offsets inside the block
-    __shared__ uint32_t s_xy[PROJ_THREADS];   // x0 | y0 << 16
-    __shared__ uint32_t s_wd[PROJ_THREADS];   // rect width | depth16 << 16
-    __shared__ uint32_t s_wsum[PROJ_THREADS / 32];
-    __shared__ int32_t s_wlast[PROJ_THREADS / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS][2];
+    __shared__ uint32_t s_off[PROJ_WARPS][32];  // exclusive duplicate offsets inside the warp
+    __shared__ uint32_t s_xy[PROJ_WARPS][32];   // x0 | y0 << 16
+    __shared__ uint32_t s_wd[PROJ_WARPS][32];   // rect width | depth16 << 16
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    float4 *slab = reinterpret_cast<float4 *>(proj_smem + (size_t)warp * PROJ_SLAB_BYTES);  // [15][32]
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_mbar_init();
+    }
     if (tid == 0) s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
     __syncthreads();
     const uint32_t bid = s_bid;
-    const uint32_t id = bid * PROJ_THREADS + tid;
+    const uint32_t vwarp = bid * PROJ_WARPS + warp;  // position of this warp in the chained scan
+    const uint32_t id0 = vwarp * 32u;
+    const uint32_t id = id0 + lane;
+
+    // ---- phase 1: TMA the warp's slices of planes 0..2 (planes are padded to a multiple of 256 splats) ----
+    if (lane == 0) {
+        mbar_expect_tx(&s_bar[warp][0], 3u * 512u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][0]);
+    }
 
     const float *V = a.vp, *P = a.vp + 16;  // X[c][r] = X[4*c + r]
     const int W = a.u.dims[0], H = a.u.dims[1];
@@ -144,10 +228,13 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_kernel(const __grid_c
 
     uint32_t n = 0, x0u = 0, y0u = 0, wu = 0, depth = 0;
     int32_t last_tile = -1;
+    float4 r0, r1;           // record words 0,1 (valid when n > 0)
+    float splat_opacity = 0.0f, vx = 0.0f, vy = 0.0f, vz = 0.0f;
 
+    mbar_wait(&s_bar[warp][0], 0);
     if (id < a.num_splats) {
         do {
-            const float4 pt = __ldg(a.soa + id);  // plane 0: position.xyz, time
+            const float4 pt = slab[lane];  // plane 0: position.xyz, time
             // :158-166 frustum cull
             const float sp0 = pt.x * ms, sp1 = pt.y * ms, sp2 = pt.z * ms;
             float view[4], clip[4];
@@ -158,14 +245,14 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_kernel(const __grid_c
             const float vb = clip[3] * 1.2f;
             if (clip[0] < -vb || clip[1] < -vb || clip[2] < 0.0f || clip[0] > vb || clip[1] > vb || clip[2] > clip[3]) break;
 
-            const float4 ca = __ldg(a.soa + 1 * a.plane_stride + id);  // c00 c01 c02 c11
-            const float4 cb = __ldg(a.soa + 2 * a.plane_stride + id);  // c12 c22 opacity pad
+            const float4 ca = slab[32 + lane];  // c00 c01 c02 c11
+            const float4 cb = slab[64 + lane];  // c12 c22 opacity pad
 
             // :169-174 load-in animation
             const float splat_time = a.u.time - pt.w;
             const float tf = ease_out_cubic(g_clamp(splat_time, 0.0f, 1.0f));
             const float tfl = ease_out_cubic(g_clamp(splat_time - 0.35f, 0.0f, 1.0f));
-            const float splat_opacity = cb.z * tfl * tfl;
+            splat_opacity = cb.z * tfl * tfl;
             const float splat_scale = ms * (2.0f * (1.0f - tfl) + 1.0f * tfl);
 
             // :124-142 project_covariance
@@ -220,87 +307,84 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_kernel(const __grid_c
             const uint32_t nt = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
             if (nt == 0u) break;
 
-            // :198-206 record (SH planes are only touched here)
-            float sh[48];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const float4 v = __ldg(a.soa + (uint64_t)(3 + k) * a.plane_stride + id);
-                sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
-            }
+            // :198-206 everything of the record except the colour
             const float d0 = sp0 - a.u.camera_pos[0], d1 = sp1 - a.u.camera_pos[1], d2 = sp2 - a.u.camera_pos[2];
             const float inv_len = 1.0f / sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
-            const float dx = d0 * inv_len, dy = d1 * inv_len, dz = d2 * inv_len;
-            float4 r0, r1, r2;
+            vx = d0 * inv_len; vy = d1 * inv_len; vz = d2 * inv_len;
             r0.x = ipx; r0.y = ipy; r0.z = sp0; r0.w = sp1;                        // image_pos, pos_xy
             r1.x = cz / det; r1.y = -cy / det; r1.z = cx / det; r1.w = sp2;        // conic, pos_z
-            r2.x = sh_channel(sh, 0, dx, dy, dz);
-            r2.y = sh_channel(sh, 1, dx, dy, dz);
-            r2.z = sh_channel(sh, 2, dx, dy, dz);
-            r2.w = splat_opacity;
-            float4 *rec = a.records + (uint64_t)id * 3u;
-            rec[0] = r0; rec[1] = r1; rec[2] = r2;
-
             // :218
             depth = ((uint32_t)(ndc2 * ndc2 * ndc2 * 65535.0f)) & 0xFFFFu;
             n = nt; x0u = (uint32_t)x0; y0u = (uint32_t)y0; wu = (uint32_t)(x1 - x0);
         } while (false);
     }
 
-    // ---- block-exclusive scan of the duplicate counts ----
+    // ---- warp scan of the duplicate counts; publish the warp aggregate NOW (before the colour phase) ----
     const uint32_t incl = warp_incl_scan_u32(n, lane);
-    if (lane == 31) s_wsum[warp] = incl;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t emit_mask = __ballot_sync(0xffffffffu, n != 0u);
+    const uint32_t nvis = __popc(emit_mask);
     const int32_t wl = __reduce_max_sync(0xffffffffu, last_tile);
-    if (lane == 0) s_wlast[warp] = wl;
-    const uint32_t nvis = (uint32_t)__syncthreads_count(n != 0u);
-    uint32_t woff = 0, total = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < PROJ_THREADS / 32; ++w) {
-        const uint32_t s = s_wsum[w];
-        if (w < warp) woff += s;
-        total += s;
+    if (lane == 0) {
+        volatile unsigned long long *st = a.lookback + vwarp;
+        *st = (vwarp == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)total;
     }
-    s_off[tid] = woff + incl - n;
-    s_xy[tid] = x0u | (y0u << 16);
-    s_wd[tid] = wu | (depth << 16);
+    s_off[warp][lane] = incl - n;
+    s_xy[warp][lane] = x0u | (y0u << 16);
+    s_wd[warp][lane] = wu | (depth << 16);
 
-    // ---- chained scan across blocks (warp 0) + per-block counters ----
-    if (warp == 0) {
-        const unsigned long long base = lookback_exclusive(a.lookback, bid, (unsigned long long)total, lane);
+    // ---- phase 2: SH planes -> colour -> record ----
+    if (nvis >= SH_BULK_MIN) {
         if (lane == 0) {
-            s_base = base;
-            if (nvis) atomicAdd(&a.frame->visible, nvis);
-            int32_t bl = -1;
+            mbar_expect_tx(&s_bar[warp][1], 12u * 512u);
 #pragma unroll
-            for (int w = 0; w < PROJ_THREADS / 32; ++w) bl = bl > s_wlast[w] ? bl : s_wlast[w];
-            if (bl >= 0) atomicMax(&a.frame->last_tile_plus1, bl + 1);
-            if (bid == gridDim.x - 1) {  // tickets are dense: this block closes the scan => M is known
-                const unsigned long long m = base + total;
-                a.frame->dup_total = m;
-                a.frame->dup_sorted = m < (unsigned long long)a.capacity ? (uint32_t)m : a.capacity;
-                a.frame->overflow = m > (unsigned long long)a.capacity ? 1u : 0u;
-            }
+            for (int k = 3; k < NUM_PLANES; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][1]);
+        }
+        mbar_wait(&s_bar[warp][1], 0);
+        if (n) {
+            float col[3];
+            sh_color<true>(slab + 3 * 32 + lane, 32, vx, vy, vz, col);
+            float4 *rec = a.records + (uint64_t)id * 3u;
+            rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
+        }
+    } else if (n) {
+        float col[3];
+        sh_color<false>(a.soa + 3ull * a.plane_stride + id, a.plane_stride, vx, vy, vz, col);
+        float4 *rec = a.records + (uint64_t)id * 3u;
+        rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
+    }
+
+    // ---- chained scan across warps (decoupled look-back; aggregate already published) + per-frame counters ----
+    const unsigned long long base = lookback_exclusive(a.lookback, vwarp, (unsigned long long)total, lane);
+    if (lane == 0) {
+        if (nvis) atomicAdd(&a.frame->visible, nvis);
+        if (wl >= 0) atomicMax(&a.frame->last_tile_plus1, wl + 1);
+        if (vwarp == gridDim.x * PROJ_WARPS - 1) {  // tickets are dense: this warp closes the scan => M is known
+            const unsigned long long m = base + total;
+            a.frame->dup_total = m;
+            a.frame->dup_sorted = m < (unsigned long long)a.capacity ? (uint32_t)m : a.capacity;
+            a.frame->overflow = m > (unsigned long long)a.capacity ? 1u : 0u;
         }
     }
-    __syncthreads();
-    const unsigned long long base = s_base;
+    __syncwarp();
 
-    // ---- block-cooperative emit (:219-226): slot j of the block -> owner splat by binary search ----
-    for (uint32_t j = tid; j < total; j += PROJ_THREADS) {
-        uint32_t lo = 0, hi = PROJ_THREADS - 1;
+    // ---- warp-cooperative emit (:219-226): output slot j of the warp -> owner splat by binary search ----
+    for (uint32_t j = lane; j < total; j += 32u) {
+        uint32_t lo = 0, hi = 31;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < 5; ++it) {
             const uint32_t mid = (lo + hi + 1) >> 1;
-            if (s_off[mid] <= j) lo = mid; else hi = mid - 1;
+            if (s_off[warp][mid] <= j) lo = mid; else hi = mid - 1;
         }
-        const uint32_t r = j - s_off[lo];
-        const uint32_t xy = s_xy[lo], wd = s_wd[lo];
+        const uint32_t r = j - s_off[warp][lo];
+        const uint32_t xy = s_xy[warp][lo], wd = s_wd[warp][lo];
         const uint32_t w = wd & 0xFFFFu;
         const uint32_t ry = r / w, rx = r - ry * w;
         const uint32_t tile_id = ((xy >> 16) + ry) * gx + (xy & 0xFFFFu) + rx;
         const unsigned long long g = base + j;
         if (g < (unsigned long long)a.capacity) {
             a.keys[g] = (tile_id << 16) | (wd >> 16);
-            a.values[g] = bid * PROJ_THREADS + lo;
+            a.values[g] = id0 + lo;
         }
     }
 }
@@ -312,7 +396,12 @@ uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     const uint32_t blocks = projection_num_blocks(a.num_splats);
     if (blocks == 0) return GSR_OK;
-    projection_kernel<<<blocks, PROJ_THREADS, 0, stream>>>(a);
+    static bool attr_set = false;  // per process; every context uses the same kernel
+    if (!attr_set) {
+        GSR_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROJ_SMEM_BYTES));
+        attr_set = true;
+    }
+    projection_kernel<<<blocks, PROJ_THREADS, PROJ_SMEM_BYTES, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
