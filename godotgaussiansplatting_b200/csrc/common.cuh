@@ -138,11 +138,13 @@ struct ProjectionArgs {
     uint32_t num_splats;
     float vp[32];            // view_matrix, projection_matrix (GLSL column-major)
     Uniforms u;
+    float focal_base[2];     // (dims*0.5) * (P00, P11)           gsplat_projection.glsl:127-128
+    float lim_lo[2], lim_hi[2];  // -+ (1/(P00,P11)) * 1.3          gsplat_projection.glsl:129,133
     int32_t band_y0, band_y1;
     float4 *records;         // 3 float4 per splat id (RasterizeData layout)
     uint32_t *keys, *values;
     uint32_t capacity;
-    unsigned long long *lookback;  // one word per projection warp (32 splats)
+    unsigned long long *lookback;  // one word per projection CTA (256 splats)
     FrameState *frame;
 };
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);

@@ -167,7 +167,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     TRY_ALLOC(c->records, sizeof(float4) * 3ull * c->max_splats);
     TRY_ALLOC(c->keys, sizeof(uint32_t) * 2ull * c->capacity);
     TRY_ALLOC(c->vals, sizeof(uint32_t) * 2ull * c->capacity);
-    c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats) * (PROJ_THREADS / 32);  // one scan link per warp
+    c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats);  // one scan link per CTA
     TRY_ALLOC(c->ring, sizeof(FrameState) * GSR_HISTORY_FRAMES);
     TRY_ALLOC(c->lookback, sizeof(unsigned long long) * (size_t)c->lookback_blocks);
     c->frame = c->ring;
@@ -272,7 +272,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     c->frame = c->ring + slot;
     cudaEvent_t *ev = c->ev + 5 * slot;
     GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats) * (PROJ_THREADS / 32), s));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
     GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
     GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 
@@ -280,6 +280,16 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
     memcpy(pa.vp, view_proj, sizeof pa.vp);
     pa.u = u;
+    {   // per-frame constants of project_covariance, same IEEE binary32 operations as gsplat_projection.glsl:127-133
+        const float tfi0 = view_proj[16 + 0], tfi1 = view_proj[16 + 5];
+        const volatile float hw = (float)u.dims[0] * 0.5f, hh = (float)u.dims[1] * 0.5f;
+        const volatile float f0 = hw * tfi0, f1 = hh * tfi1;
+        const volatile float t0 = 1.0f / tfi0, t1 = 1.0f / tfi1;
+        const volatile float n0 = -t0, n1 = -t1;
+        pa.focal_base[0] = f0; pa.focal_base[1] = f1;
+        pa.lim_lo[0] = n0 * 1.3f; pa.lim_lo[1] = n1 * 1.3f;
+        pa.lim_hi[0] = t0 * 1.3f; pa.lim_hi[1] = t1 * 1.3f;
+    }
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;

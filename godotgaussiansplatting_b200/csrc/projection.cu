@@ -40,24 +40,6 @@ constexpr float SH_C3_6 = 0.5900435899266435f;
 
 struct Mat3 { float m[3][3]; };  // m[c][r], GLSL column-major
 
-// GLSL a*b: out[c][r] = (a[0][r]*b[c][0] + a[1][r]*b[c][1]) + a[2][r]*b[c][2]
-__device__ __forceinline__ Mat3 mat3_mul(const Mat3 &a, const Mat3 &b) {
-    Mat3 o;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) o.m[c][r] = (a.m[0][r] * b.m[c][0] + a.m[1][r] * b.m[c][1]) + a.m[2][r] * b.m[c][2];
-    return o;
-}
-__device__ __forceinline__ Mat3 mat3_transpose(const Mat3 &a) {
-    Mat3 o;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) o.m[c][r] = a.m[r][c];
-    return o;
-}
-
 __device__ __forceinline__ float ease_out_cubic(float x) {  // gsplat_projection.glsl:87-90
     float a = 1.0f - x;
     return 1.0f - a * a * a;
@@ -174,16 +156,16 @@ __device__ __forceinline__ void sh_color(const float4 *src, uint64_t stride, flo
     }
 }
 
-// One warp = 32 consecutive splats = one link of the chained scan.  Warps never wait for each other (the only
-// CTA barrier broadcasts the block ticket).  Data movement per warp:
+// One warp = 32 consecutive splats; one CTA (8 warps, 256 splats) = one link of the chained scan.  There is no CTA
+// barrier after the ticket broadcast: warps meet only through shared-memory flags.  Data movement per warp:
 //   phase 1: lane 0 issues three 512-byte TMA bulk copies (planes 0-2: position/time, covariance, opacity of the
 //            warp's 32 splats) into the warp's shared slab and everybody waits on the warp's mbarrier;
-//            cull + EWA + rect => duplicate count; the warp's aggregate is PUBLISHED here, before phase 2, so
-//            that successors never wait on this warp's colour work;
+//            cull + EWA + rect => duplicate count; the last warp of the CTA to get here publishes the CTA
+//            aggregate, before phase 2, so that successor CTAs never wait on this CTA's colour work;
 //   phase 2: if at least SH_BULK_MIN lanes emit keys, twelve more 512-byte bulk copies bring the SH planes
 //            (6 KB in flight per warp at zero register cost); otherwise the few live lanes gather their
 //            192 bytes with plain 128-bit loads (sparse view / out-of-band warps of a multi-GPU shard);
-//   then records are written, the look-back resolves the warp's base offset, and the warp emits its keys.
+//   then records are written, the closer's look-back resolves the CTA's base offset, and every warp emits its keys.
 constexpr int PROJ_WARPS = PROJ_THREADS / 32;
 constexpr int SH_BULK_MIN = 12;
 #ifndef GSR_PROJ_MIN_BLOCKS
@@ -199,6 +181,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
     __shared__ uint32_t s_off[PROJ_WARPS][32];  // exclusive duplicate offsets inside the warp
     __shared__ uint32_t s_xy[PROJ_WARPS][32];   // x0 | y0 << 16
     __shared__ uint32_t s_wd[PROJ_WARPS][32];   // rect width | depth16 << 16
+    __shared__ uint32_t s_wtotal[PROJ_WARPS];   // duplicate count of each warp
+    __shared__ uint32_t s_count, s_ready, s_nvis;
+    __shared__ int32_t s_last;
+    __shared__ unsigned long long s_cta_base;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     float4 *slab = reinterpret_cast<float4 *>(proj_smem + (size_t)warp * PROJ_SLAB_BYTES);  // [15][32]
@@ -207,10 +193,13 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
         mbar_init(&s_bar[warp][1], 1);
         fence_mbar_init();
     }
-    if (tid == 0) s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
+    if (tid == 0) {
+        s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
+        s_count = 0u; s_ready = 0u; s_nvis = 0u; s_last = -1;
+    }
     __syncthreads();
-    const uint32_t bid = s_bid;
-    const uint32_t vwarp = bid * PROJ_WARPS + warp;  // position of this warp in the chained scan
+    const uint32_t bid = s_bid;                      // position of this CTA in the chained scan
+    const uint32_t vwarp = bid * PROJ_WARPS + warp;  // 32 consecutive splats
     const uint32_t id0 = vwarp * 32u;
     const uint32_t id = id0 + lane;
 
@@ -261,22 +250,34 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int r = 0; r < 3; ++r) cov3.m[c][r] = cov3.m[c][r] * splat_scale * splat_scale;
-            const float tfi0 = P[0], tfi1 = P[5];
-            float focal0 = ((float)W * 0.5f) * tfi0, focal1 = ((float)H * 0.5f) * tfi1;
-            const float tanfov0 = 1.0f / tfi0, tanfov1 = 1.0f / tfi1;
+            // per-frame constants (focal = dims*0.5*tan_fov_inv, +-tan_fov*1.3) are evaluated once on the host with
+            // the same IEEE operations (ProjectionArgs::focal_base, lim_lo, lim_hi)
             const float z_inv = 1.0f / view[2];
-            focal0 = focal0 * z_inv;
-            focal1 = focal1 * z_inv;
-            const float mx = g_clamp(view[0] * z_inv, -tanfov0 * 1.3f, tanfov0 * 1.3f);
-            const float my = g_clamp(view[1] * z_inv, -tanfov1 * 1.3f, tanfov1 * 1.3f);
-            const Mat3 J = {{{focal0, 0.0f, -focal1 * mx}, {0.0f, focal1, -focal1 * my}, {0.0f, 0.0f, 0.0f}}};
-            const Mat3 V3 = {{{V[0], V[1], V[2]}, {V[4], V[5], V[6]}, {V[8], V[9], V[10]}}};
-            const Mat3 IV = mat3_transpose(V3);
-            const Mat3 b = mat3_mul(IV, J);
-            const Mat3 tb = mat3_transpose(b);
-            const Mat3 t1 = mat3_mul(tb, cov3);
-            const Mat3 c2 = mat3_mul(t1, b);
-            const float cx = c2.m[0][0] + 0.3f, cy = c2.m[0][1], cz = c2.m[1][1] + 0.3f;
+            const float focal0 = a.focal_base[0] * z_inv, focal1 = a.focal_base[1] * z_inv;
+            const float mx = g_clamp(view[0] * z_inv, a.lim_lo[0], a.lim_hi[0]);
+            const float my = g_clamp(view[1] * z_inv, a.lim_lo[1], a.lim_hi[1]);
+            // jacobian columns (focal.x, 0, -focal.y*mean.x), (0, focal.y, -focal.y*mean.y), 0 (:134-137).  gsr spec: the
+            // structurally-zero terms of b = transpose(mat3(view)) * jacobian are skipped; only the three entries of
+            // cov_2d = transpose(b) * cov_3d * b that :141 reads are formed.  B0[r] = b[0][r], B1[r] = b[1][r].
+            const float j02 = -focal1 * mx, j12 = -focal1 * my;
+            float B0[3], B1[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                B0[r] = V[4 * r + 0] * focal0 + V[4 * r + 2] * j02;
+                B1[r] = V[4 * r + 1] * focal1 + V[4 * r + 2] * j12;
+            }
+            // t1 = transpose(b) * cov_3d: T0[c] = t1[c][0] = sum_k b[0][k]*cov3[c][k], T1[c] = t1[c][1]
+            float T0[3], T1[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T0[c] = (B0[0] * cov3.m[c][0] + B0[1] * cov3.m[c][1]) + B0[2] * cov3.m[c][2];
+                T1[c] = (B1[0] * cov3.m[c][0] + B1[1] * cov3.m[c][1]) + B1[2] * cov3.m[c][2];
+            }
+            // cov_2d[c][r] = sum_k t1[k][r] * b[c][k]
+            const float c2_00 = (T0[0] * B0[0] + T0[1] * B0[1]) + T0[2] * B0[2];
+            const float c2_01 = (T1[0] * B0[0] + T1[1] * B0[1]) + T1[2] * B0[2];
+            const float c2_11 = (T1[0] * B1[0] + T1[1] * B1[1]) + T1[2] * B1[2];
+            const float cx = c2_00 + 0.3f, cy = c2_01, cz = c2_11 + 0.3f;
 
             // :177-182
             const float det = cx * cz - cy * cy;
@@ -319,19 +320,34 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
         } while (false);
     }
 
-    // ---- warp scan of the duplicate counts; publish the warp aggregate NOW (before the colour phase) ----
+    // ---- warp scan of the duplicate counts; the warp that finishes phase 1 LAST in its CTA (the "closer") publishes
+    //      the CTA aggregate -- before anybody's colour phase -- and later resolves the CTA's base offset ----
     const uint32_t incl = warp_incl_scan_u32(n, lane);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t emit_mask = __ballot_sync(0xffffffffu, n != 0u);
     const uint32_t nvis = __popc(emit_mask);
     const int32_t wl = __reduce_max_sync(0xffffffffu, last_tile);
-    if (lane == 0) {
-        volatile unsigned long long *st = a.lookback + vwarp;
-        *st = (vwarp == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)total;
-    }
     s_off[warp][lane] = incl - n;
     s_xy[warp][lane] = x0u | (y0u << 16);
     s_wd[warp][lane] = wu | (depth << 16);
+    bool closer = false;
+    uint32_t cta_total = 0;
+    if (lane == 0) {
+        s_wtotal[warp] = total;
+        if (nvis) atomicAdd(&s_nvis, nvis);
+        if (wl >= 0) atomicMax(&s_last, wl);
+        __threadfence_block();
+        closer = atomicAdd(&s_count, 1u) == PROJ_WARPS - 1;
+        if (closer) {
+            __threadfence_block();
+#pragma unroll
+            for (int w = 0; w < PROJ_WARPS; ++w) cta_total += ((volatile uint32_t *)s_wtotal)[w];
+            volatile unsigned long long *st = a.lookback + bid;
+            *st = (bid == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)cta_total;
+        }
+    }
+    closer = __shfl_sync(0xffffffffu, (int)closer, 0) != 0;
+    cta_total = __shfl_sync(0xffffffffu, cta_total, 0);
 
     // ---- phase 2: SH planes -> colour -> record ----
     if (nvis >= SH_BULK_MIN) {
@@ -354,19 +370,33 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
         rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
     }
 
-    // ---- chained scan across warps (decoupled look-back; aggregate already published) + per-frame counters ----
-    const unsigned long long base = lookback_exclusive(a.lookback, vwarp, (unsigned long long)total, lane);
-    if (lane == 0) {
-        if (nvis) atomicAdd(&a.frame->visible, nvis);
-        if (wl >= 0) atomicMax(&a.frame->last_tile_plus1, wl + 1);
-        if (vwarp == gridDim.x * PROJ_WARPS - 1) {  // tickets are dense: this warp closes the scan => M is known
-            const unsigned long long m = base + total;
-            a.frame->dup_total = m;
-            a.frame->dup_sorted = m < (unsigned long long)a.capacity ? (uint32_t)m : a.capacity;
-            a.frame->overflow = m > (unsigned long long)a.capacity ? 1u : 0u;
+    // ---- chained scan across CTAs (decoupled look-back by the closer; aggregate already published) ----
+    if (closer) {
+        const unsigned long long cta_base = lookback_exclusive(a.lookback, bid, (unsigned long long)cta_total, lane);
+        if (lane == 0) {
+            s_cta_base = cta_base;
+            __threadfence_block();
+            *(volatile uint32_t *)&s_ready = 1u;
+            const uint32_t nv = *(volatile uint32_t *)&s_nvis;
+            const int32_t lt = *(volatile int32_t *)&s_last;
+            if (nv) atomicAdd(&a.frame->visible, nv);
+            if (lt >= 0) atomicMax(&a.frame->last_tile_plus1, lt + 1);
+            if (bid == gridDim.x - 1) {  // tickets are dense: this CTA closes the scan => M is known
+                const unsigned long long m = cta_base + cta_total;
+                a.frame->dup_total = m;
+                a.frame->dup_sorted = m < (unsigned long long)a.capacity ? (uint32_t)m : a.capacity;
+                a.frame->overflow = m > (unsigned long long)a.capacity ? 1u : 0u;
+            }
         }
     }
-    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) {
+        while (*(volatile uint32_t *)&s_ready == 0u) __nanosleep(32);
+        __threadfence_block();
+        base = *(volatile unsigned long long *)&s_cta_base;
+        for (uint32_t w = 0; w < warp; ++w) base += ((volatile uint32_t *)s_wtotal)[w];
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
 
     // ---- warp-cooperative emit (:219-226): output slot j of the warp -> owner splat by binary search ----
     for (uint32_t j = lane; j < total; j += 32u) {

@@ -300,14 +300,25 @@ static void project_one(const float *s, const float *vp, const orc_uniforms *u, 
     focal[0] *= z_inv; focal[1] *= z_inv;
     float mx = orc_clamp(view[0] * z_inv, -tanfov[0] * 1.3f, tanfov[0] * 1.3f);
     float my = orc_clamp(view[1] * z_inv, -tanfov[1] * 1.3f, tanfov[1] * 1.3f);
-    mat3 J = {{{focal[0], 0.0f, -focal[1] * mx}, {0.0f, focal[1], -focal[1] * my}, {0.0f, 0.0f, 0.0f}}};
-    mat3 V3 = {{{V[0], V[1], V[2]}, {V[4], V[5], V[6]}, {V[8], V[9], V[10]}}};
-    mat3 IV = mat3_transpose(&V3);
-    mat3 b = mat3_mul(&IV, &J);
-    mat3 tb = mat3_transpose(&b);
-    mat3 t1 = mat3_mul(&tb, &cov3);
-    mat3 c2 = mat3_mul(&t1, &b);
-    float cx = c2.m[0][0] + 0.3f, cy = c2.m[0][1], cz = c2.m[1][1] + 0.3f;
+    /* jacobian = mat3(focal.x, 0, -focal.y*mean.x,  0, focal.y, -focal.y*mean.y,  0, 0, 0)   (:134-137)
+     * b = transpose(mat3(view_matrix)) * jacobian;  cov_2d = transpose(b) * cov_3d * b              (:138-140)
+     * gsr spec: the structurally-zero terms of b are skipped (b[0][r] = V[r][0]*J00 + V[r][2]*J02,
+     * b[1][r] = V[r][1]*J11 + V[r][2]*J12, b[2] = 0) and only the three entries :141 reads are formed;
+     * every remaining sum is left-to-right as mat3_mul would do it. */
+    float j02 = -focal[1] * mx, j12 = -focal[1] * my;
+    float B0[3], B1[3], T0[3], T1[3];
+    for (int r = 0; r < 3; ++r) {
+        B0[r] = V[4 * r + 0] * focal[0] + V[4 * r + 2] * j02;
+        B1[r] = V[4 * r + 1] * focal[1] + V[4 * r + 2] * j12;
+    }
+    for (int cc = 0; cc < 3; ++cc) { /* t1 = transpose(b) * cov_3d: T0[c] = t1[c][0], T1[c] = t1[c][1] */
+        T0[cc] = (B0[0] * cov3.m[cc][0] + B0[1] * cov3.m[cc][1]) + B0[2] * cov3.m[cc][2];
+        T1[cc] = (B1[0] * cov3.m[cc][0] + B1[1] * cov3.m[cc][1]) + B1[2] * cov3.m[cc][2];
+    }
+    float c2_00 = (T0[0] * B0[0] + T0[1] * B0[1]) + T0[2] * B0[2];
+    float c2_01 = (T1[0] * B0[0] + T1[1] * B0[1]) + T1[2] * B0[2];
+    float c2_11 = (T1[0] * B1[0] + T1[1] * B1[1]) + T1[2] * B1[2];
+    float cx = c2_00 + 0.3f, cy = c2_01, cz = c2_11 + 0.3f;
 
     /* :177-182 */
     float det = cx * cz - cy * cy;
