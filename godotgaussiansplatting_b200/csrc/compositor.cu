@@ -19,6 +19,8 @@
 //   * the tile-stop vote `atomicAdd(shared_t, uint(t*255))` (:97) is a warp reduction + 4 shared words.
 // Arithmetic contract: "gsr deterministic math" (common.cuh): the GLSL-legal contractions of :84 and :89 are
 // explicit fma, exp() is the det_exp() polynomial (evaluated here two lanes at a time).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -197,7 +199,13 @@ __global__ void __launch_bounds__(THREADS) composite_kernel(const __grid_constan
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    composite_kernel<<<a.num_tiles, THREADS, 0, stream>>>(a);
+    static int pad = -1;  // experiment knob: extra dynamic shared memory caps the number of resident CTAs per SM
+    if (pad < 0) {
+        const char *e = getenv("GSR_COMP_SMEM_PAD");
+        pad = e ? atoi(e) : 0;
+        if (pad > 48 * 1024) cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
+    composite_kernel<<<a.num_tiles, THREADS, pad, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

@@ -44,6 +44,12 @@ struct gsr_ctx {
     uint64_t frame_counter = 0;
     uint2 *bounds = nullptr;
     float4 *fb = nullptr, *fb_ext = nullptr;
+    float4 *fb2 = nullptr;                       // second frame for pipelined read-back (gsr_render_async)
+    float4 *fb_last = nullptr;                   // frame written by the most recent render
+    cudaStream_t copy_stream = nullptr;          // D2H read-back overlaps the next frame's kernels
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool copied_valid[2] = {false, false};
+    uint64_t async_counter = 0;
     float4 *pick = nullptr;
     float4 *staging = nullptr;
     uint64_t staging_splats = 0;
@@ -91,7 +97,7 @@ int check_device(int device) {
     return GSR_OK;
 }
 
-float4 *framebuffer(gsr_ctx *c) { return c->fb_ext ? c->fb_ext : c->fb; }
+float4 *framebuffer(gsr_ctx *c) { return c->fb_ext ? c->fb_ext : (c->fb_last ? c->fb_last : c->fb); }
 
 void free_ctx(gsr_ctx *c) {
     if (!c) return;
@@ -99,7 +105,10 @@ void free_ctx(gsr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
     sort_workspace_destroy(c->sort);
-    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->fb); cudaFree(c->pick); cudaFree(c->staging);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
+    for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
     if (c->ev) {
         for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -163,6 +172,12 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     cudaError_t se = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(se)); free_ctx(c); return GSR_ERR_CUDA; }
     c->stream = c->own_stream;
+    se = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && se == cudaSuccess; ++i) {
+        se = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+        if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+    }
+    if (se != cudaSuccess) { set_last_error("copy stream/events -> %s", cudaGetErrorString(se)); free_ctx(c); return GSR_ERR_CUDA; }
     TRY_ALLOC(c->soa, sizeof(float4) * NUM_PLANES * c->plane_stride);
     TRY_ALLOC(c->records, sizeof(float4) * 3ull * c->max_splats);
     TRY_ALLOC(c->keys, sizeof(uint32_t) * 2ull * c->capacity);
@@ -235,10 +250,15 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     if (rc) return rc;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(c->bounds); c->bounds = nullptr;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaFree(c->fb); c->fb = nullptr;
+    cudaFree(c->fb2); c->fb2 = nullptr;
+    c->fb_last = nullptr; c->copied_valid[0] = c->copied_valid[1] = false;
     GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, sizeof(uint2) * (size_t)tx * ty));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb, sizeof(float4) * (size_t)width * height));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->fb2, sizeof(float4) * (size_t)width * height));
     GSR_CUDA_TRY(cudaMemsetAsync(c->fb, 0, sizeof(float4) * (size_t)width * height, c->stream));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->fb2, 0, sizeof(float4) * (size_t)width * height, c->stream));
     c->width = width; c->height = height; c->tiles_x = tx; c->tiles_y = ty;
     if (!c->band_set) { c->band_y0 = 0; c->band_y1 = ty; }
     if (c->band_y1 > ty) c->band_y1 = ty;
@@ -254,7 +274,7 @@ GSR_API int gsr_set_band(gsr_ctx *c, int32_t row_begin, int32_t row_end) {
     return GSR_OK;
 }
 
-static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor) {
+static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float4 *target = nullptr) {
     if (!c || !view_proj || !uniforms32) return GSR_ERR_INVALID;
     if (c->width == 0) { set_last_error("gsr_render before gsr_resize"); return GSR_ERR_STATE; }
     Uniforms u;
@@ -312,7 +332,9 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     GSR_CUDA_TRY(cudaEventRecord(ev[3], s));  // 'Boundaries'
 
     CompositeArgs ca;
-    ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
+    float4 *out_fb = c->fb_ext ? c->fb_ext : (target ? target : c->fb);
+    c->fb_last = out_fb;
+    ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = out_fb;
     ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
     ca.tile_begin = c->band_y0 * c->tiles_x;
     ca.num_tiles = (c->band_y1 - c->band_y0) * c->tiles_x;
@@ -340,10 +362,38 @@ GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *unifor
 }
 
 GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host) {
-    int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
+    if (!c) return GSR_ERR_INVALID;
+    if (!pinned_host || c->fb_ext) {  // nothing to read back, or the caller owns the frame memory: plain enqueue
+        int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
+        if (rc) return rc;
+        if (pinned_host)
+            GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, framebuffer(c), sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+        return GSR_OK;
+    }
+    // Pipelined read-back: frames alternate between two device framebuffers; the D2H copy of frame i runs on the
+    // copy stream while the render stream already works on frame i+1.  Frame i+2 waits for copy i before it
+    // overwrites the same buffer.
+    int rc = use_device(c->device);
     if (rc) return rc;
-    if (pinned_host)
-        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, framebuffer(c), sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+    const int slot = (int)(c->async_counter & 1u);
+    float4 *target = slot ? c->fb2 : c->fb;
+    if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+    if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, target))) return rc;
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
+    GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+    GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, target, sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->copy_stream));
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->copied_valid[slot] = true;
+    c->async_counter += 1;
+    return GSR_OK;
+}
+
+GSR_API int gsr_stream_join(gsr_ctx *c) {
+    if (!c) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i)
+        if (c->copied_valid[i]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));
     return GSR_OK;
 }
 
@@ -352,6 +402,7 @@ GSR_API int gsr_sync(gsr_ctx *c) {
     int rc = use_device(c->device);
     if (rc) return rc;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     return GSR_OK;
 }
 

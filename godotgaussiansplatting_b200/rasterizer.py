@@ -182,6 +182,10 @@ class GaussianSplattingRasterizer:
     def sync(self) -> None:
         _lib.check(_lib.lib().gsr_sync(self._ctx), "gsr_sync")
 
+    def stream_join(self) -> None:
+        """Make the render stream wait for the pipelined read-back copies enqueued so far."""
+        _lib.check(_lib.lib().gsr_stream_join(self._ctx), "gsr_stream_join")
+
     # ---- get_splat_position (rasterizer.gd:162-171) ----
     def get_splat_position(self, screen_position) -> np.ndarray:
         s = self.render_scale[0]

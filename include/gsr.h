@@ -125,10 +125,14 @@ GSR_API int gsr_set_band(gsr_ctx *ctx, int32_t row_begin, int32_t row_end);
 GSR_API int gsr_render(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
                        float *out_rgba32f_host);
 
-/* Pipelined host read-back: enqueue the frame and an async copy into `pinned_host` (may be pageable, then the
- * copy is synchronous); gsr_sync waits for everything enqueued so far. */
+/* Pipelined host read-back: enqueue the frame and an asynchronous device->host copy into `pinned_host` (page-locked
+ * memory; with pageable memory the copy degrades to a synchronous one).  Frames alternate between two internal
+ * framebuffers and the copy runs on a separate stream, so the read-back of frame i overlaps the kernels of frame i+1.
+ * gsr_stream_join makes the render stream wait for all copies enqueued so far (so that an event recorded on the
+ * render stream afterwards covers them); gsr_sync blocks the host until renders and copies are complete. */
 GSR_API int gsr_render_async(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
                              float *pinned_host);
+GSR_API int gsr_stream_join(gsr_ctx *ctx);
 GSR_API int gsr_sync(gsr_ctx *ctx);
 
 /* Device pointer of the RGBA32F frame (render_texture.texture_rd_rid, rasterizer.gd:48,101); row-major W*H. */
