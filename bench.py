@@ -235,11 +235,11 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
 
+    from godotgaussiansplatting_b200 import sharding
     W, H, N = wl["w"], wl["h"], wl["n"]
     tiles_y = (H + 15) // 16
-    rows_per = (tiles_y + world - 1) // world
-    band = (min(rank * rows_per, tiles_y), min((rank + 1) * rows_per, tiles_y))
-    h_pad = rows_per * 16 * world
+    band = sharding.band_partition(tiles_y, world)[rank]
+    h_pad = sharding.padded_height(H, world)
 
     # ---- scene: generated and uploaded chunk by chunk (PlyFile.load_gaussian_splats path, util/ply_file.gd:28-77) ----
     stub = PlyFile()
@@ -259,9 +259,6 @@ def main():
     rast.set_framebuffer_external(fb.data_ptr())
     if world > 1:
         rast.set_band(*band)
-    band_px = rows_per * 16
-    my_slab = fb[rank * band_px:(rank + 1) * band_px]
-    gather_list = [fb[r * band_px:(r + 1) * band_px] for r in range(world)] if rank == 0 else None
     # two page-locked host frames: the application consumes frame i while frame i+1 is being copied
     pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
     pinned = pinned2[0] if rank == 0 else None
@@ -274,7 +271,7 @@ def main():
             rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True)
         else:
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)
-            dist.gather(my_slab, gather_list, dst=0)  # one NCCL gather of the band framebuffers per frame
+            sharding.gather_bands(fb, rank, world, dst=0)  # one NCCL gather of the band framebuffers per frame
             if e2e and rank == 0:
                 pinned.copy_(fb[:H], non_blocking=True)
 

@@ -1,0 +1,135 @@
+"""Host-side logic without a GPU: PLY parsing, the GDScript-mirror's bookkeeping, synthetic scenes, sharding."""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from godotgaussiansplatting_b200 import camera as cam
+from godotgaussiansplatting_b200 import sharding
+from godotgaussiansplatting_b200.ply_file import PlyFile, default_properties, load_gaussian_splats, swizzle_splats
+from godotgaussiansplatting_b200.rasterizer import GaussianSplattingRasterizer, RenderTexture
+from godotgaussiansplatting_b200.synthetic import radix_keys, synthetic_ply, synthetic_ply_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def write_ply(path, table, big_endian=False):
+    names = default_properties(table.shape[1])
+    with open(path, "wb") as f:
+        f.write(b"ply\n")
+        f.write(b"format binary_big_endian 1.0\n" if big_endian else b"format binary_little_endian 1.0\n")
+        f.write(f"element vertex {table.shape[0]}\n".encode())
+        for n in names:
+            f.write(f"property float {n}\n".encode())
+        f.write(b"end_header\n")
+        f.write(table.astype(">f4" if big_endian else "<f4").tobytes())
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_plyfile_parse_roundtrip(tmp_path, big):
+    table = synthetic_ply_table(321, 5)
+    p = tmp_path / "t.ply"
+    write_ply(p, table, big_endian=big)
+    ply = PlyFile(str(p))
+    assert ply.size == 321 and ply.properties == default_properties(62)
+    np.testing.assert_array_equal(ply.table, table)
+    assert ply.get_vertex(7)["opacity"] == float(table[7, 54])
+
+
+def test_plyfile_truncated_body_raises(tmp_path):
+    table = synthetic_ply_table(10, 5)
+    p = tmp_path / "t.ply"
+    write_ply(p, table)
+    data = p.read_bytes()
+    p.write_bytes(data[:-40])
+    with pytest.raises(ValueError):
+        PlyFile(str(p))
+
+
+def test_load_gaussian_splats_chunks_and_terminates():
+    ply = synthetic_ply(2500, 3)
+    got, loaded, done = {}, [0], []
+    load_gaussian_splats(ply, 1000, lambda first, blk: got.__setitem__(first, blk), [False], loaded, lambda: done.append(1), clock=lambda: 2.5)
+    assert sorted(got) == [0, 1000, 2000] and loaded[0] == 2500 and done == [1]
+    full = np.concatenate([got[k] for k in sorted(got)])
+    np.testing.assert_array_equal(full, swizzle_splats(ply.table, 2.5))
+    assert np.all(full[:, 3] == np.float32(2.5))  # creation time stamp (ply_file.gd:40,47)
+    stop = [False]
+    seen = []
+
+    def upload(first, blk):
+        seen.append(first)
+        stop[0] = True
+
+    load_gaussian_splats(ply, 1000, upload, stop, [0], None)
+    assert seen == [0]  # cooperative cancel (rasterizer.gd:117)
+
+
+def test_swizzle_layout():
+    t = np.zeros((1, 62), dtype=np.float32)
+    t[0, 0:3] = (1, 2, 3)
+    t[0, 6:9] = (10, 11, 12)                      # f_dc
+    t[0, 9:54] = np.arange(45) + 100              # f_rest: R 0..14, G 15..29, B 30..44
+    t[0, 54] = 0.0                                # sigmoid -> 0.5
+    t[0, 55:58] = np.log([1.0, 2.0, 3.0])
+    t[0, 58:62] = (1, 0, 0, 0)                    # identity quaternion (w first in the file)
+    s = swizzle_splats(t, 9.0)[0]
+    assert s[:4].tolist() == [1, 2, 3, 9]
+    np.testing.assert_allclose(s[4:10], [1, 0, 0, 4, 0, 9], rtol=1e-6)  # R S^2 R^T upper triangle
+    assert s[10] == 0.5 and s[11] == 0
+    assert s[12:15].tolist() == [10, 11, 12]
+    assert s[15:18].tolist() == [100, 115, 130] and s[57:60].tolist() == [114, 129, 144]
+
+
+def test_rasterizer_mirror_bookkeeping_without_gpu():
+    ply = synthetic_ply(100, 1)
+    c = cam.default_camera(aspect=16 / 9)
+    r = GaussianSplattingRasterizer(ply, (1920, 1080), RenderTexture(), c)
+    assert r.texture_size == (1920, 1080) and r.tile_dims == (120, 68)
+    r.render_scale[0] = 0.5
+    r.texture_size = (1920, 1080)                  # rasterizer.gd:28: scaled by render_scale, min 1
+    assert r.texture_size == (960, 540) and r.tile_dims == (60, 34)
+    r.render_scale[0] = 1e-9
+    r.texture_size = (100, 100)
+    assert r.texture_size == (1, 1) and r.tile_dims == (1, 1)
+    assert r.update_camera_matrices() is True and r.update_camera_matrices() is False
+    c.global_position = np.array([0.5, 0.25, -1.0], dtype=np.float32)
+    assert r.update_camera_matrices() is True
+    u = r.uniforms_bytes(time=3.5)
+    f = np.frombuffer(u, dtype=np.float32)
+    i = np.frombuffer(u, dtype=np.int32)
+    assert len(u) == 32 and f[:4].tolist() == [-0.5, -0.25, -1.0, 1.0] and i[4:6].tolist() == [1, 1] and f[6] == 3.5
+    assert r.camera_push_constants.shape == (32,) and r.camera_push_constants[31] == 0.0 and r.camera_push_constants[27] == -1.0
+
+
+def test_synthetic_scene_is_deterministic_and_in_front_of_the_camera():
+    a, b = synthetic_ply_table(3000, 9), synthetic_ply_table(3000, 9)
+    np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(a, synthetic_ply_table(3000, 10))
+    r = np.linalg.norm(a[:, :3] - np.array([0, 0, 2.5], dtype=np.float32), axis=1)
+    assert r.max() <= 1.0 + 1e-5
+    np.testing.assert_allclose(np.linalg.norm(a[:, 58:62], axis=1), 1.0, rtol=1e-5)
+    k = radix_keys(10000, 1)
+    assert (k >> 16).max() < 8160 and 52000 <= (k & 0xFFFF).min() and (k & 0xFFFF).max() < 61500
+
+
+def test_band_partition():
+    assert sharding.band_partition(68, 1) == [(0, 68)]
+    assert sharding.band_partition(68, 8) == [(0, 9), (9, 18), (18, 27), (27, 36), (36, 45), (45, 54), (54, 63), (63, 68)]
+    assert sharding.band_partition(3, 8)[3:] == [(3, 3)] * 5           # more ranks than rows: empty bands
+    assert sharding.padded_height(1080, 8) == 9 * 16 * 8 and sharding.slab_rows(1080, 8) == 144
+    assert sharding.padded_height(2160, 4) >= 2160
+
+
+def test_two_rank_gloo_band_gather_reproduces_the_full_frame():
+    """world_size=2 on CPU (gloo): each rank renders its tile-row band with the ORACLE, the bands are gathered with
+    sharding.gather_bands, and rank 0 checks the result equals the oracle's full frame bit for bit."""
+    script = os.path.join(ROOT, "tests", "gloo_band_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", OMP_NUM_THREADS="2")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29517", script], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "BAND_GATHER_OK" in res.stdout
