@@ -166,7 +166,7 @@ def run_reference(args, wl, rank, world):
         "e2e": {"value": value, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def radix_microbench(torch, device_index, n=1 << 26):
@@ -201,8 +201,25 @@ def radix_microbench(torch, device_index, n=1 << 26):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Exactly one JSON line on the process's real stdout (library banners -- e.g. NCCL's version line -- were
+    redirected to stderr in main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # anything a library prints to fd 1 from here on goes to stderr
     wl = dict(WORKLOADS[args.workload])
     reduced = False
     if args.splats:
@@ -378,7 +395,7 @@ def main():
             "stage_ms": stage, "radix": radix,
             "reference_published": {"fps": 108, "scene": "bicycle.ply ~6.1M splats @1080p", "hw": "RTX 3060 Ti", "source": "README.md:58 (other hardware; not comparable)"},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     rast.cleanup_gpu()
     if world > 1:
         dist.destroy_process_group()
