@@ -14,13 +14,13 @@ LIB_PATH = os.environ.get("GSR_LIB_PATH") or os.path.join(HERE, "libgsr.so")  # 
 GSR_OK, GSR_ERR_INVALID, GSR_ERR_CUDA, GSR_ERR_OOM, GSR_ERR_STATE, GSR_ERR_OVERFLOW = range(6)
 GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES = 0x1, 0x2
 (GSR_BUF_RECORDS, GSR_BUF_KEYS, GSR_BUF_VALUES, GSR_BUF_BOUNDS, GSR_BUF_KEYS_UNSORTED, GSR_BUF_VALUES_UNSORTED,
- GSR_BUF_FRAMEBUFFER) = range(7)
+ GSR_BUF_FRAMEBUFFER, GSR_BUF_COMPOSITOR_TRACE, GSR_BUF_COMPOSITOR_TRACE_COUNT) = range(9)
 
 # every symbol include/gsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_resize", "gsr_set_band", "gsr_render",
     "gsr_render_async", "gsr_stream_join", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
-    "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
+    "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
     "gsr_device_count", "gsr_version",
 ]
@@ -82,6 +82,7 @@ def lib():
         L.gsr_get_frame_history.argtypes = [vp, u32, C.POINTER(GsrFrameRecord), C.POINTER(u32)]
         L.gsr_debug_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.gsr_debug_keep_unsorted.argtypes = [vp, C.c_int]
+        L.gsr_debug_enable_trace.argtypes = [vp, u32]
         L.gsr_sorter_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp)]
         L.gsr_sorter_destroy.argtypes = [vp]
         L.gsr_sorter_sort_device.argtypes = [vp, vp, vp, C.c_uint64, vp]

@@ -11,6 +11,7 @@ namespace gsr {
 constexpr int TILE = 16;            // rasterizer.gd:4 TILE_SIZE
 constexpr int NUM_PLANES = 15;      // 60-float Splat = 15 float4 planes in SoA
 constexpr int PROJ_THREADS = 256;   // gsplat_projection.glsl:31 local_size_x
+#define GSR_COMP_MAX_PUSHES 7         // a tile is handed back to the compositor queue at most this many times
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -91,7 +92,11 @@ struct FrameState {
     uint32_t proj_ticket;          // dynamic block id for the projection look-back
     uint32_t pad0;
     unsigned long long staged;     // C: instances staged by the compositor (sum of consumed chunk sizes)
-    uint32_t pad[6];
+    uint32_t comp_head;            // compositor work queue: next ticket
+    uint32_t comp_tail;            //                        next free slot for a re-queued tile
+    uint32_t comp_done;            //                        tiles finished
+    uint32_t comp_qhead;           //                        next re-queued entry to pop
+    uint32_t pad[2];
 };
 static_assert(sizeof(FrameState) == 64, "FrameState is one 64-byte slot of the history ring");
 
@@ -164,7 +169,14 @@ struct CompositeArgs {
     float heatmap_factor;
     uint32_t target_tile_id; // 0xFFFFFFFF = none (rasterizer.gd:158)
     float4 *pick;            // tile_splat_pos buffer (gsplat_render.glsl:33-36)
-    FrameState *frame;       // staged-instance counter (null: do not count, e.g. pick re-dispatch)
+    FrameState *frame;       // per-launch queue counters (comp_head/tail/done must be 0) + staged-instance counter
+    int32_t count_staged;    // add this launch's consumed instances to frame->staged (0 for the pick re-dispatch)
+    uint32_t *queue;         // [GSR_COMP_MAX_PUSHES * num_tiles] zero-initialised: re-queued tiles (tile id + 1)
+    float4 *state;           // [num_tiles][2][128] spilled per-pixel state of re-queued tiles
+    uint32_t *state_chunk;   // [num_tiles] first chunk still to blend
+    ulonglong4 *trace;       // optional schedule trace (debug): {tile<<32|smid, t0_ns, t1_ns, first_chunk<<32|iters<<1|finished}
+    uint32_t *trace_count;
+    uint32_t trace_cap;
 };
 int launch_composite(const CompositeArgs &a, cudaStream_t stream);
 

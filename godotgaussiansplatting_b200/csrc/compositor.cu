@@ -16,7 +16,11 @@
 //   * the gather `culled_buffer[sort_buffer[...]]` (:72) for chunk i+1 is issued into registers before the
 //     blend loop of chunk i (software prefetch); one shared buffer suffices because the vote barrier
 //     already separates blend(i) from store(i+1);
-//   * the tile-stop vote `atomicAdd(shared_t, uint(t*255))` (:97) is a warp reduction + 4 shared words.
+//   * the tile-stop vote `atomicAdd(shared_t, uint(t*255))` (:97) is a warp reduction + 4 shared words;
+//   * tiles are RE-QUEUEABLE: the grid is persistent (SMs x resident CTAs); a CTA blends at most GSR_COMP_QUANTUM
+//     chunks of a tile, then spills the tile's 4 KB of per-pixel state and pushes the tile back to a device queue,
+//     so a 19-chunk tile no longer pins one SM while others idle (ncu before: SMs active 60 % of the kernel).
+//     State is saved/restored verbatim, so the result is unchanged.
 // Arithmetic contract: "gsr deterministic math" (common.cuh): the GLSL-legal contractions of :84 and :89 are
 // explicit fma, exp() is the det_exp() polynomial (evaluated here two lanes at a time).
 #include <stdlib.h>
@@ -66,146 +70,267 @@ __device__ __forceinline__ Staged gather(const float4 *__restrict__ records, con
     return s;
 }
 
-__global__ void __launch_bounds__(THREADS) composite_kernel(const __grid_constant__ CompositeArgs p) {
+constexpr int COMP_MAX_PUSHES = GSR_COMP_MAX_PUSHES;  // common.cuh: queue capacity = COMP_MAX_PUSHES * tiles
+#ifndef GSR_COMP_QUANTUM
+#define GSR_COMP_QUANTUM 2  // chunks blended before an unfinished tile is handed back to the queue
+#endif
+constexpr uint32_t EXIT_TILE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+
+// Persistent CTAs + re-queueable tiles.  Work item = (tile, first chunk).  Tickets [0, num_tiles) are the tiles
+// themselves in natural order; an unfinished tile spills its per-pixel state (t, rgb of 256 pixels = 4 KB) and is
+// pushed to `queue`, where ticket num_tiles + k finds it.  Every item ends in exactly one of {tile done, tile
+// pushed}, so a CTA waiting for a queue slot either gets one or sees comp_done == num_tiles and leaves.
+#ifndef GSR_COMP_MIN_BLOCKS
+#define GSR_COMP_MIN_BLOCKS 4  // lets ptxas spend registers on interleaving the per-splat dependency chains
+#endif
+__global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel(const __grid_constant__ CompositeArgs p) {
     __shared__ float4 s_a[CHUNK];
     __shared__ float4 s_b[CHUNK];
     __shared__ float s_c[CHUNK];
     __shared__ uint32_t s_vote[THREADS / 32];
+    __shared__ uint32_t s_tile, s_resume;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile_id = (uint32_t)p.tile_begin + blockIdx.x;
-    const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
-    const int px0 = (int)(tx * TILE + 2u * (tid & 7u)), py = (int)(ty * TILE + (tid >> 3));
-    const u64 npx2 = pk(-(float)px0, -(float)(px0 + 1));  // ox = image_pos.x - pixel.x  ==  image_pos.x + (-pixel.x)
-    const float fpy = (float)py;
-
-    const uint2 bounds = p.bounds[tile_id];
-    const int32_t diff = (int32_t)(bounds.y - bounds.x);
-    const int num_splats = diff > 0 ? diff : 0;                              // :61
-    const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);  // :62
-
-    u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;  // blended colour of the two pixels
-    float t0 = 1.0f, t1 = 1.0f;                    // transmittance of the two pixels
-    uint32_t staged = 0;                           // SURVEY 8 symbol C (uniform across the CTA)
-
-    Staged n0 = null_splat(), n1 = null_splat();
-    if (num_iterations > 0) {
-        if ((int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + tid);
-        if ((int)tid + THREADS < num_splats) n1 = gather(p.records, p.values, bounds.x + tid + THREADS);
-    }
-
     const u64 L2E2 = bc(0x1.715476p+0f), MAGIC2 = bc(12582912.0f), ONE2 = bc(1.0f);
     const u64 C6 = bc(0x1.446c7ep-13f), C5 = bc(0x1.5f48c8p-10f), C4 = bc(0x1.3b29d8p-7f), C3 = bc(0x1.c6aeccp-5f),
               C2 = bc(0x1.ebfbe0p-3f), C1 = bc(0x1.62e430p-1f);
+    uint32_t staged = 0;  // SURVEY 8 symbol C, summed over the items this CTA processed (uniform across the CTA)
+    unsigned long long t_start = 0;  // trace only
 
-    for (int i = 0; i < num_iterations; ++i) {
-        const int sort_offset = CHUNK * i;
-        const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
-        staged += (uint32_t)chunk;
-        s_a[tid] = n0.a; s_b[tid] = n0.b; s_c[tid] = n0.c;
-        s_a[tid + THREADS] = n1.a; s_b[tid + THREADS] = n1.b; s_c[tid + THREADS] = n1.c;
+    for (;;) {
+        if (tid == 0) {
+            // FIFO: fresh tiles are tickets [0, num_tiles); ticket num_tiles + k waits for the k-th hand-back.  (Serving
+            // continuing tiles first was measured to be worse: the in-flight set monopolises the CTAs and the
+            // remaining busy tiles start as a second wave.)
+            const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
+            if (ticket < (uint32_t)p.num_tiles) {
+                s_tile = (uint32_t)p.tile_begin + ticket;
+                s_resume = 0u;
+            } else {
+                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                volatile uint32_t *done = &p.frame->comp_done;
+                uint32_t v;
+                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (v == 0u) v = *slot;  // a push may have landed between the two reads
+                s_tile = v ? v - 1u : EXIT_TILE;
+                s_resume = 1u;
+                __threadfence();
+            }
+            if (p.trace) t_start = globaltimer_ns();
+        }
         __syncthreads();
-        // prefetch the next chunk's records while this one is blended (slots past the list end become null splats)
-        n0 = null_splat(); n1 = null_splat();
-        if (i + 1 < num_iterations) {
-            const int nb = sort_offset + CHUNK;
+        const uint32_t tile_id = s_tile;
+        const bool resume = s_resume != 0u;
+        if (tile_id == EXIT_TILE) break;
+
+        const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
+        const int px0 = (int)(tx * TILE + 2u * (tid & 7u)), py = (int)(ty * TILE + (tid >> 3));
+        const u64 npx2 = pk(-(float)px0, -(float)(px0 + 1));  // ox = image_pos.x - pixel.x  ==  image_pos.x + (-pixel.x)
+        const float fpy = (float)py;
+
+        const uint2 bounds = p.bounds[tile_id];
+        const int32_t diff = (int32_t)(bounds.y - bounds.x);
+        const int num_splats = diff > 0 ? diff : 0;                              // :61
+        const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);  // :62
+
+        u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;  // blended colour of the two pixels
+        float t0 = 1.0f, t1 = 1.0f;                    // transmittance of the two pixels
+        int i0 = 0;
+        const uint32_t local_tile = tile_id - (uint32_t)p.tile_begin;
+        float4 *st = p.state + (uint64_t)local_tile * (2u * THREADS);
+        if (resume) {  // written by another SM during this launch: read through L2
+            const float4 sa = __ldcg(st + tid), sb = __ldcg(st + THREADS + tid);
+            cr2 = pk(sa.x, sa.y); cg2 = pk(sa.z, sa.w); cb2 = pk(sb.x, sb.y);
+            t0 = sb.z; t1 = sb.w;
+            i0 = (int)__ldcg(p.state_chunk + local_tile);
+        }
+
+        Staged n0 = null_splat(), n1 = null_splat();
+        if (i0 < num_iterations) {
+            const int nb = CHUNK * i0;
             if (nb + (int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + (uint32_t)nb + tid);
             if (nb + (int)tid + THREADS < num_splats) n1 = gather(p.records, p.values, bounds.x + (uint32_t)nb + tid + THREADS);
         }
 
-        // :79-91, four splats per liveness test; `chunk` rounded up to 4 reads null splats (opacity 0 => exact no-op)
-        const int chunk4 = (chunk + 3) & ~3;
-        for (int j = 0; j < chunk4; j += 4) {
-            if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
+        // at most COMP_MAX_PUSHES hand-backs per tile bound the queue: long lists get a proportionally longer quantum
+        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int i_begin = i0;
+        bool finished = true;
+        for (int i = i_begin; i < num_iterations; ++i) {
+            const int sort_offset = CHUNK * i;
+            const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
+            staged += (uint32_t)chunk;
+            s_a[tid] = n0.a; s_b[tid] = n0.b; s_c[tid] = n0.c;
+            s_a[tid + THREADS] = n1.a; s_b[tid + THREADS] = n1.b; s_c[tid + THREADS] = n1.c;
+            __syncthreads();
+            // prefetch the next chunk's records while this one is blended (slots past the list end become null splats)
+            n0 = null_splat(); n1 = null_splat();
+            if (i + 1 < num_iterations && i + 1 - i_begin < quantum) {
+                const int nb = sort_offset + CHUNK;
+                if (nb + (int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + (uint32_t)nb + tid);
+                if (nb + (int)tid + THREADS < num_splats) n1 = gather(p.records, p.values, bounds.x + (uint32_t)nb + tid + THREADS);
+            }
+
+            // :79-91, four splats per liveness test; `chunk` rounded up to 4 reads null splats (opacity 0 => exact no-op)
+            const int chunk4 = (chunk + 3) & ~3;
+            for (int j = 0; j < chunk4; j += 4) {
+                if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
+                // ---- phase A: alpha = opacity * exp(power) of four splats, written stage by stage so that the four
+                //      ~25-instruction dependency chains are interleaved instruction by instruction (a lone warp
+                //      otherwise runs this loop at IPC 0.23: measured 25 us per chunk for a tile that owns its SM)
+                float4 A[4], B[4];
+                float CB[4], oy[4];
+                u64 ox2[4], pw2[4], tm2[4], e2[4], al2[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 a = s_a[j + u];
-                const float4 b = s_b[j + u];
-                const float cbl = s_c[j + u];
-                const u64 ox2 = add2(bc(a.x), npx2);
-                const float oy = a.y - fpy;
+                for (int u = 0; u < 4; ++u) { A[u] = s_a[j + u]; B[u] = s_b[j + u]; CB[u] = s_c[j + u]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
                 // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy  with q = fma(cz*oy, oy, cx*ox*ox), power = fma(-(cy*ox), oy, -0.5*q)
-                const u64 a2 = mul2(mul2(bc(a.z), ox2), ox2);
-                const u64 h2 = fma2(bc(a.w * oy), bc(oy), a2);
-                const u64 pw2 = fma2(mul2(bc(b.x), ox2), bc(oy), h2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = mul2(bc(B[u].x), ox2[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
                 // exp(power): det_exp(), two lanes at a time
-                float tl, th;
-                upk(mul2(pw2, L2E2), tl, th);
-                tl = g_min(g_max(tl, -127.0f), 128.0f);
-                th = g_min(g_max(th, -127.0f), 128.0f);
-                const u64 tc2 = pk(tl, th);
-                const u64 tm2 = add2(tc2, MAGIC2);
-                const u64 f2 = sub2(tc2, sub2(tm2, MAGIC2));
-                u64 e2 = fma2(C6, f2, C5);
-                e2 = fma2(e2, f2, C4);
-                e2 = fma2(e2, f2, C3);
-                e2 = fma2(e2, f2, C2);
-                e2 = fma2(e2, f2, C1);
-                e2 = fma2(e2, f2, ONE2);
-                float ml, mh;
-                upk(tm2, ml, mh);
-                const u64 sc2 = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
-                                   __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
-                // alpha = opacity * exp(power); dead pixels take alpha = 0 (the reference's loop exit for that pixel)
-                float al, ah;
-                upk(mul2(bc(b.y), mul2(e2, sc2)), al, ah);
-                al = (t0 > MIN_ALPHA) ? al : 0.0f;
-                ah = (t1 > MIN_ALPHA) ? ah : 0.0f;
-                const u64 al2 = pk(al, ah);
-                const u64 t2 = pk(t0, t1);
-                cr2 = fma2(mul2(bc(b.z), al2), t2, cr2);
-                cg2 = fma2(mul2(bc(b.w), al2), t2, cg2);
-                cb2 = fma2(mul2(bc(cbl), al2), t2, cb2);
-                upk(mul2(t2, sub2(ONE2, al2)), t0, t1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pw2[u] = mul2(pw2[u], L2E2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float tl, th;
+                    upk(pw2[u], tl, th);
+                    tl = g_min(g_max(tl, -127.0f), 128.0f);
+                    th = g_min(g_max(th, -127.0f), 128.0f);
+                    pw2[u] = pk(tl, th);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tm2[u] = add2(pw2[u], MAGIC2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) al2[u] = sub2(tm2[u], MAGIC2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = fma2(C6, pw2[u], C5);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C3);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], ONE2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float ml, mh;
+                    upk(tm2[u], ml, mh);
+                    tm2[u] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
+                                __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e2[u] = mul2(e2[u], tm2[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) al2[u] = mul2(bc(B[u].y), e2[u]);
+                // ---- phase B: the sequential part (:89-90).  Dead pixels take alpha = 0: the reference's loop exit ----
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float al, ah;
+                    upk(al2[u], al, ah);
+                    al = (t0 > MIN_ALPHA) ? al : 0.0f;
+                    ah = (t1 > MIN_ALPHA) ? ah : 0.0f;
+                    const u64 m2 = pk(al, ah);
+                    const u64 t2 = pk(t0, t1);
+                    cr2 = fma2(mul2(bc(B[u].z), m2), t2, cr2);
+                    cg2 = fma2(mul2(bc(B[u].w), m2), t2, cg2);
+                    cb2 = fma2(mul2(bc(CB[u]), m2), t2, cb2);
+                    upk(mul2(t2, sub2(ONE2, m2)), t0, t1);
+                }
+            }
+
+            // :97 tile-stop vote: continue only if the sum over the tile's 256 pixels of uint(t*255) exceeds 255
+            const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t0 * 255.0f) + (uint32_t)(t1 * 255.0f));
+            if (lane == 0) s_vote[warp] = wsum;
+            __syncthreads();
+            uint32_t shared_t = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) shared_t += s_vote[w];
+            if (!(shared_t > 255u)) break;  // finished stays true
+            if (i + 1 < num_iterations && i + 1 - i_begin >= quantum) {  // quantum used up, tile still live
+                finished = false;
+                i0 = i + 1;  // resume point, spilled below
+                break;
             }
         }
 
-        // :97 tile-stop vote: continue only if the sum over the tile's 256 pixels of uint(t*255) exceeds 255
-        const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t0 * 255.0f) + (uint32_t)(t1 * 255.0f));
-        if (lane == 0) s_vote[warp] = wsum;
-        __syncthreads();
-        uint32_t shared_t = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) shared_t += s_vote[w];
-        if (!(shared_t > 255u)) break;
+        float r0, r1, g0, g1, b0, b1;
+        upk(cr2, r0, r1); upk(cg2, g0, g1); upk(cb2, b0, b1);
+        if (!finished) {
+            // spill the tile and hand it back: any CTA on any SM resumes it
+            __stcg(st + tid, make_float4(r0, r1, g0, g1));
+            __stcg(st + THREADS + tid, make_float4(b0, b1, t0, t1));
+            if (tid == 0) __stcg(p.state_chunk + local_tile, (uint32_t)i0);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t slot = atomicAdd(&p.frame->comp_tail, 1u);
+                __threadfence();
+                *(volatile uint32_t *)(p.queue + slot) = tile_id + 1u;
+            }
+        } else {
+            // :100-101
+            const float hx = (float)num_splats * 5e-4f;
+            const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
+            if (py < p.height) {
+                float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
+                const float k0 = 1.0f - t0, k1 = 1.0f - t1;
+                if (px0 < p.width)
+                    row[px0] = make_float4(r0 + h0 * k0 * p.heatmap_factor, g0 + h1 * k0 * p.heatmap_factor, b0 + h2c * k0 * p.heatmap_factor, 1.0f);
+                if (px0 + 1 < p.width)
+                    row[px0 + 1] = make_float4(r1 + h0 * k1 * p.heatmap_factor, g1 + h1 * k1 * p.heatmap_factor, b1 + h2c * k1 * p.heatmap_factor, 1.0f);
+            }
+            // :105-110 pick: the elected (first) lane of each 32-wide subgroup of the reference's 16x16 workgroup is local
+            // index 32*s = pixel (0, 2*s) of the tile = first pixel of thread 16*s here
+            if ((tid & 15u) == 0u && tile_id == p.target_tile_id && t0 != 1.0f) {
+                const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
+                const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
+                *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
+            }
+            if (tid == 0) atomicAdd(&p.frame->comp_done, 1u);
+        }
+        if (p.trace && tid == 0) {
+            const uint32_t k = atomicAdd(p.trace_count, 1u);
+            if (k < p.trace_cap) p.trace[k] = make_ulonglong4(((unsigned long long)tile_id << 32) | smid(), t_start, globaltimer_ns(), ((unsigned long long)(uint32_t)i_begin << 32) | (uint32_t)(finished ? 1u : 0u) | ((uint32_t)num_iterations << 1));
+        }
+        __syncthreads();  // s_tile / staging buffers are reused by the next item
     }
-
-    if (tid == 0 && staged && p.frame) atomicAdd(&p.frame->staged, (unsigned long long)staged);
-
-    // :100-101
-    const float hx = (float)num_splats * 5e-4f;
-    const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
-    float r0, r1, g0, g1, b0, b1;
-    upk(cr2, r0, r1); upk(cg2, g0, g1); upk(cb2, b0, b1);
-    if (py < p.height) {
-        float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
-        const float k0 = 1.0f - t0, k1 = 1.0f - t1;
-        if (px0 < p.width)
-            row[px0] = make_float4(r0 + h0 * k0 * p.heatmap_factor, g0 + h1 * k0 * p.heatmap_factor, b0 + h2c * k0 * p.heatmap_factor, 1.0f);
-        if (px0 + 1 < p.width)
-            row[px0 + 1] = make_float4(r1 + h0 * k1 * p.heatmap_factor, g1 + h1 * k1 * p.heatmap_factor, b1 + h2c * k1 * p.heatmap_factor, 1.0f);
-    }
-
-    // :105-110 pick: the elected (first) lane of each 32-wide subgroup of the reference's 16x16 workgroup is local
-    // index 32*s = pixel (0, 2*s) of the tile = first pixel of thread 16*s here
-    if ((tid & 15u) == 0u && tile_id == p.target_tile_id && t0 != 1.0f) {
-        const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
-        const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
-        *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
-    }
+    if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
 }
 
 }  // namespace
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int pad = -1;  // experiment knob: extra dynamic shared memory caps the number of resident CTAs per SM
-    if (pad < 0) {
-        const char *e = getenv("GSR_COMP_SMEM_PAD");
-        pad = e ? atoi(e) : 0;
-        if (pad > 48 * 1024) cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        int dev = 0;
+        GSR_CUDA_TRY(cudaGetDevice(&dev));
+        GSR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel, THREADS, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const char *e = getenv("GSR_COMP_CTAS_PER_SM");  // experiment knob
+        if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
-    composite_kernel<<<a.num_tiles, THREADS, pad, stream>>>(a);
+    const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
+    composite_kernel<<<grid, THREADS, 0, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

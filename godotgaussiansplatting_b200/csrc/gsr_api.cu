@@ -42,7 +42,13 @@ struct gsr_ctx {
     unsigned long long *lookback = nullptr;  // one word per projection block, cleared every frame
     uint32_t lookback_blocks = 0;
     uint64_t frame_counter = 0;
-    uint2 *bounds = nullptr;
+    uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
+    uint32_t *comp_queue = nullptr, *comp_chunk = nullptr;
+    float4 *comp_state = nullptr;
+    FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
+    ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
+    uint32_t *trace_count = nullptr;
+    uint32_t trace_cap = 0;
     float4 *fb = nullptr, *fb_ext = nullptr;
     float4 *fb2 = nullptr;                       // second frame for pipelined read-back (gsr_render_async)
     float4 *fb_last = nullptr;                   // frame written by the most recent render
@@ -106,10 +112,10 @@ void free_ctx(gsr_ctx *c) {
     cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
     sort_workspace_destroy(c->sort);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
+    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
+    cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); cudaFree(c->trace); cudaFree(c->trace_count);
     if (c->ev) {
         for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         delete[] c->ev;
@@ -250,11 +256,17 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     if (rc) return rc;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(c->bounds); c->bounds = nullptr;
+    cudaFree(c->comp_state); c->comp_state = nullptr;
+    cudaFree(c->comp_chunk); c->comp_chunk = nullptr;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaFree(c->fb); c->fb = nullptr;
     cudaFree(c->fb2); c->fb2 = nullptr;
     c->fb_last = nullptr; c->copied_valid[0] = c->copied_valid[1] = false;
-    GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, sizeof(uint2) * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)tx * ty));
+    c->comp_queue = reinterpret_cast<uint32_t *>(c->bounds + (size_t)tx * ty);
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_state, sizeof(float4) * 256ull * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_chunk, sizeof(uint32_t) * (size_t)tx * ty));
+    if (!c->pick_frame) GSR_CUDA_TRY(cudaMalloc((void **)&c->pick_frame, sizeof(FrameState)));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb, sizeof(float4) * (size_t)width * height));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb2, sizeof(float4) * (size_t)width * height));
     GSR_CUDA_TRY(cudaMemsetAsync(c->fb, 0, sizeof(float4) * (size_t)width * height, c->stream));
@@ -293,7 +305,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     cudaEvent_t *ev = c->ev + 5 * slot;
     GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
     GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)c->tiles_x * c->tiles_y, s));  // bounds + queue
     GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 
     ProjectionArgs pa;
@@ -341,7 +353,10 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     ca.heatmap_factor = heatmap_factor;
     ca.target_tile_id = 0xFFFFFFFFu;  // rasterizer.gd:158
     ca.pick = c->pick;
-    ca.frame = c->frame;
+    ca.frame = c->frame; ca.count_staged = 1;
+    ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
+    ca.trace = c->trace; ca.trace_count = c->trace_count; ca.trace_cap = c->trace_cap;
+    if (c->trace) GSR_CUDA_TRY(cudaMemsetAsync(c->trace_count, 0, sizeof(uint32_t), s));
     if ((rc = launch_composite(ca, s))) return rc;
     launches += ca.num_tiles > 0 ? 1 : 0;
     GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Render'
@@ -426,7 +441,12 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
         ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
         ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
         ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1;
-        ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick; ca.frame = nullptr;
+        ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
+        ca.frame = c->pick_frame; ca.count_staged = 0;  // own queue counters; slot 0 of the queue, state slot 0
+        ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
+        ca.trace = nullptr; ca.trace_count = nullptr; ca.trace_cap = 0;
+        GSR_CUDA_TRY(cudaMemsetAsync(c->pick_frame, 0, sizeof(FrameState), c->stream));
+        GSR_CUDA_TRY(cudaMemsetAsync(c->comp_queue, 0, sizeof(uint32_t) * GSR_COMP_MAX_PUSHES, c->stream));  // one tile => <= 7 pushes
         if ((rc = launch_composite(ca, c->stream))) return rc;
     }
     GSR_CUDA_TRY(cudaMemcpyAsync(out_xyzn, c->pick, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -499,6 +519,22 @@ GSR_API int gsr_debug_keep_unsorted(gsr_ctx *c, int enable) {
     return GSR_OK;
 }
 
+GSR_API int gsr_debug_enable_trace(gsr_ctx *c, uint32_t max_items) {
+    if (!c) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->trace); cudaFree(c->trace_count);
+    c->trace = nullptr; c->trace_count = nullptr; c->trace_cap = 0;
+    if (max_items) {
+        GSR_CUDA_TRY(cudaMalloc((void **)&c->trace, sizeof(ulonglong4) * (size_t)max_items + 32));
+        GSR_CUDA_TRY(cudaMalloc((void **)&c->trace_count, sizeof(uint32_t)));
+        GSR_CUDA_TRY(cudaMemset(c->trace_count, 0, sizeof(uint32_t)));
+        c->trace_cap = max_items;
+    }
+    return GSR_OK;
+}
+
 GSR_API int gsr_debug_copy(gsr_ctx *c, int which, void *dst, size_t bytes) {
     if (!c || !dst) return GSR_ERR_INVALID;
     int rc = use_device(c->device);
@@ -513,6 +549,8 @@ GSR_API int gsr_debug_copy(gsr_ctx *c, int which, void *dst, size_t bytes) {
         case GSR_BUF_KEYS_UNSORTED: src = c->unsorted_keys; avail = c->unsorted_keys ? sizeof(uint32_t) * c->capacity : 0; break;
         case GSR_BUF_VALUES_UNSORTED: src = c->unsorted_vals; avail = c->unsorted_vals ? sizeof(uint32_t) * c->capacity : 0; break;
         case GSR_BUF_FRAMEBUFFER: src = framebuffer(c); avail = sizeof(float4) * (size_t)c->width * c->height; break;
+        case GSR_BUF_COMPOSITOR_TRACE: src = c->trace; avail = c->trace ? sizeof(ulonglong4) * (size_t)c->trace_cap : 0; break;
+        case GSR_BUF_COMPOSITOR_TRACE_COUNT: src = c->trace_count; avail = c->trace_count ? sizeof(uint32_t) : 0; break;
         default: set_last_error("gsr_debug_copy: unknown buffer %d", which); return GSR_ERR_INVALID;
     }
     if (!src || bytes > avail) { set_last_error("gsr_debug_copy(%d): %zu bytes requested, %zu available", which, bytes, avail); return GSR_ERR_INVALID; }

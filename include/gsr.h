@@ -49,7 +49,9 @@ enum {
     GSR_BUF_BOUNDS = 3,  /* uvec2 per tile (descriptors['tile_bounds']) */
     GSR_BUF_KEYS_UNSORTED = 4,  /* keys in emission order (only valid if flags keep them; see gsr_debug_keep_unsorted) */
     GSR_BUF_VALUES_UNSORTED = 5,
-    GSR_BUF_FRAMEBUFFER = 6  /* RGBA32F W*H (descriptors['render_texture']) */
+    GSR_BUF_FRAMEBUFFER = 6,  /* RGBA32F W*H (descriptors['render_texture']) */
+    GSR_BUF_COMPOSITOR_TRACE = 7,       /* schedule trace of the last frame's compositor (gsr_debug_enable_trace) */
+    GSR_BUF_COMPOSITOR_TRACE_COUNT = 8  /* number of trace items written (uint32) */
 };
 
 typedef struct gsr_ctx gsr_ctx;       /* one rasterizer = one GaussianSplattingRasterizer instance */
@@ -154,6 +156,9 @@ GSR_API int gsr_get_frame_history(gsr_ctx *ctx, uint32_t max_frames, gsr_frame_r
 
 /* ---- parity taps: copy an internal buffer to host (synchronises).  bytes = size of dst. ---- */
 GSR_API int gsr_debug_copy(gsr_ctx *ctx, int which, void *dst, size_t bytes);
+/* Record, for every work item of the compositor, {tile<<32|SM id, start ns, end ns, first_chunk<<32|chunks<<1|finished}
+ * (4 x uint64 per item, %globaltimer).  max_items = 0 disables.  Profiling aid; not on the frame path by default. */
+GSR_API int gsr_debug_enable_trace(gsr_ctx *ctx, uint32_t max_items);
 /* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
 GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);
 
