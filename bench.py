@@ -272,12 +272,14 @@ def main():
         if keep_host:
             host_chunks.append(s60)
     t_gen = time.perf_counter() - t_gen
-    fb = torch.zeros((h_pad, W, 4), dtype=torch.float32, device="cuda")
-    rast.set_framebuffer_external(fb.data_ptr())
-    if world > 1:
+    fb = None
+    if world > 1:  # the gather needs a torch-visible frame; single GPU uses the library's own double buffer
+        fb = torch.zeros((h_pad, W, 4), dtype=torch.float32, device="cuda")
+        rast.set_framebuffer_external(fb.data_ptr())
         rast.set_band(*band)
     # two page-locked host frames: the application consumes frame i while frame i+1 is being copied
     pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+    rgb_readback = world == 1  # single GPU: RGB32F read-back (alpha == 1.0 stays on the device); multi-GPU root copies RGBA
     pinned = pinned2[0] if rank == 0 else None
 
     frames = frame_params(wl, args.warmup + args.steps)
@@ -285,7 +287,7 @@ def main():
     def step(i, e2e):
         vp, ub = frames[i]
         if world == 1:
-            rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True)
+            rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=e2e and rgb_readback)
         else:
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)
             sharding.gather_bands(fb, rank, world, dst=0)  # one NCCL gather of the band framebuffers per frame
@@ -388,8 +390,8 @@ def main():
                        "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * N / 1e6),
                        "duplicates_M": M, "visible_V": V, "staged_C": Cc, "reduced": reduced, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),
-                    "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * 16,
-                    "path": "gsr_render_async(ctx, view_proj, uniforms, pinned host RGBA32F) per frame; 160 B of camera constants in, full frame out; read-back of frame i overlaps frame i+1 (two device + two host frames); timed region ends after the last frame landed on the host"},
+                    "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * (12 if rgb_readback else 16),
+                    "path": "gsr_render_async_rgb(ctx, view_proj, uniforms, pinned host RGB32F; alpha is the constant 1.0 of gsplat_render.glsl:101) per frame; 160 B of camera constants in, full frame out; read-back of frame i overlaps frame i+1 (two device + two host frames); timed region ends after the last frame landed on the host"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "gpu_launches": int(st.kernel_launches) * args.steps, "kernel_launches_per_frame": int(st.kernel_launches),
             "stage_ms": stage, "radix": radix,

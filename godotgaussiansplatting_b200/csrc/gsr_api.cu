@@ -51,6 +51,7 @@ struct gsr_ctx {
     uint32_t trace_cap = 0;
     float4 *fb = nullptr, *fb_ext = nullptr;
     float4 *fb2 = nullptr;                       // second frame for pipelined read-back (gsr_render_async)
+    float4 *rgb[2] = {nullptr, nullptr};         // RGB32F staging of the two frames (gsr_render_async_rgb), lazily allocated
     float4 *fb_last = nullptr;                   // frame written by the most recent render
     cudaStream_t copy_stream = nullptr;          // D2H read-back overlaps the next frame's kernels
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -112,6 +113,7 @@ void free_ctx(gsr_ctx *c) {
     cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
     sort_workspace_destroy(c->sort);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->rgb[0]); cudaFree(c->rgb[1]);
     cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -261,6 +263,7 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaFree(c->fb); c->fb = nullptr;
     cudaFree(c->fb2); c->fb2 = nullptr;
+    cudaFree(c->rgb[0]); cudaFree(c->rgb[1]); c->rgb[0] = c->rgb[1] = nullptr;
     c->fb_last = nullptr; c->copied_valid[0] = c->copied_valid[1] = false;
     GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)tx * ty));
     c->comp_queue = reinterpret_cast<uint32_t *>(c->bounds + (size_t)tx * ty);
@@ -376,9 +379,10 @@ GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *unifor
     return GSR_OK;
 }
 
-GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host) {
+static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float *pinned_host, bool rgb_only) {
     if (!c) return GSR_ERR_INVALID;
     if (!pinned_host || c->fb_ext) {  // nothing to read back, or the caller owns the frame memory: plain enqueue
+        if (rgb_only && pinned_host) { set_last_error("gsr_render_async_rgb is unavailable with an external framebuffer"); return GSR_ERR_STATE; }
         int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
         if (rc) return rc;
         if (pinned_host)
@@ -392,15 +396,30 @@ GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *
     if (rc) return rc;
     const int slot = (int)(c->async_counter & 1u);
     float4 *target = slot ? c->fb2 : c->fb;
+    const size_t pixels = (size_t)c->width * c->height;
+    if (rgb_only && !c->rgb[slot]) GSR_CUDA_TRY(cudaMalloc((void **)&c->rgb[slot], sizeof(float) * 3 * pixels + 64));
     if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
     if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, target))) return rc;
     GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
     GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
-    GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, target, sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (rgb_only) {
+        if ((rc = launch_pack_rgb(target, c->rgb[slot], pixels, c->copy_stream))) return rc;
+        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, c->rgb[slot], sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
+    } else {
+        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, target, sizeof(float4) * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     GSR_CUDA_TRY(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
     c->copied_valid[slot] = true;
     c->async_counter += 1;
     return GSR_OK;
+}
+
+GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host) {
+    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host, false);
+}
+
+GSR_API int gsr_render_async_rgb(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host_rgb) {
+    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host_rgb, true);
 }
 
 GSR_API int gsr_stream_join(gsr_ctx *c) {

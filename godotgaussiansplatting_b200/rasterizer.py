@@ -135,9 +135,11 @@ class GaussianSplattingRasterizer:
         self._bind_texture()
 
     def render_raw(self, vp32: np.ndarray, uniforms32: bytes, heatmap: float = 0.0, host_ptr: int | None = None,
-                   asynchronous: bool = True) -> None:
-        """rasterize() with pre-packed push constants / uniform block (bench hot loop)."""
-        fn = _lib.lib().gsr_render_async if asynchronous else _lib.lib().gsr_render
+                   asynchronous: bool = True, rgb_only: bool = False) -> None:
+        """rasterize() with pre-packed push constants / uniform block (bench hot loop).  rgb_only: the host frame is
+        RGB32F (alpha is constant 1.0 and stays on the device)."""
+        L = _lib.lib()
+        fn = (L.gsr_render_async_rgb if rgb_only else L.gsr_render_async) if asynchronous else L.gsr_render
         _lib.check(fn(self._ctx, vp32.ctypes.data_as(C.POINTER(C.c_float)), uniforms32, float(heatmap),
                       None if host_ptr is None else C.c_void_p(host_ptr)), "gsr_render")
 

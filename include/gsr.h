@@ -134,6 +134,10 @@ GSR_API int gsr_render(gsr_ctx *ctx, const float view_proj[32], const void *unif
  * render stream afterwards covers them); gsr_sync blocks the host until renders and copies are complete. */
 GSR_API int gsr_render_async(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
                              float *pinned_host);
+/* Same, but the host frame is RGB32F (width*height*3 floats): the alpha channel of the reference's output is the
+ * constant 1.0 (gsplat_render.glsl:101), so it is packed away on the device before the PCIe transfer (-25 % bytes). */
+GSR_API int gsr_render_async_rgb(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
+                                 float *pinned_host_rgb);
 GSR_API int gsr_stream_join(gsr_ctx *ctx);
 GSR_API int gsr_sync(gsr_ctx *ctx);
 

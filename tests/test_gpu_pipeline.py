@@ -281,3 +281,21 @@ def test_mirror_class_end_to_end():
     assert tex.read().shape == (150, 200, 4)
     r.cleanup_gpu()
     assert tex.device_ptr == 0
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (333, 257)])
+def test_rgb_readback_equals_rgba_frame(w, h):
+    import ctypes as C
+    n = 8000
+    splat60, vp, ub = make_scene(n, 18, w, h)
+    with Ctx(n, w, h) as c:
+        c.upload(splat60)
+        want = c.render(vp, ub)
+        hosts = [np.zeros((h, w, 3), dtype=np.float32) for _ in range(3)]
+        vpc = np.ascontiguousarray(vp, dtype=np.float32)
+        for out in hosts:
+            _lib.check(c.L.gsr_render_async_rgb(c.h, vpc.ctypes.data_as(C.POINTER(C.c_float)), ub, 0.0, C.c_void_p(out.ctypes.data)), "async rgb")
+        _lib.check(c.L.gsr_sync(c.h), "sync")
+    assert np.all(want[..., 3] == 1.0)
+    for out in hosts:
+        np.testing.assert_array_equal(bits(out), bits(np.ascontiguousarray(want[..., :3])))
