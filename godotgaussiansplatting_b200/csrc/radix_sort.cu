@@ -15,6 +15,12 @@
 // forward-progress guarantee.
 #include "common.cuh"
 
+// Digit matching inside a warp: 8 ballots (1) or match.any (0).  Measured on B200: ballots are ~20 % faster and
+// insensitive to digit skew (MATCH.ANY cost grows with the number of distinct digits in the warp).
+#ifndef GSR_SORT_BALLOT
+#define GSR_SORT_BALLOT 1
+#endif
+
 namespace gsr {
 
 namespace {
@@ -91,7 +97,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 }
 
 template <int THREADS, int ITEMS, bool PAIRS>
-__global__ void __launch_bounds__(THREADS) onesweep_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) onesweep_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
                                                            const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
                                                            const uint32_t *__restrict__ n_ptr, uint32_t n_max,
                                                            const uint32_t *__restrict__ hist,  // [256], this pass
@@ -160,23 +166,37 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const uint32_t *__res
             }
         }
 
-        // ---- rank inside the warp: match lanes with the same digit, leader bumps the warp counter ----
+        // ---- rank inside the warp: lanes with the same digit are matched, the lowest of them (the leader) bumps the
+        //      warp-private counter.  The counter update is a RETURNING shared atomic whose result is not consumed
+        //      in this loop, so the 12 match + 12 atomic operations of a thread pipeline instead of forming a
+        //      load->add->store chain per row; __syncwarp() keeps row i's update ordered before row i+1's.
         uint32_t *wh = s_whist + warp * RADIX;
         const uint32_t lt_mask = (1u << lane) - 1u;
+        uint32_t old[ITEMS];  // counter value before this row (valid in the leader lane)
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t d = (key[i] >> shift) & 255u;
-            const uint32_t mask = __match_any_sync(0xffffffffu, d);
-            const uint32_t lower = __popc(mask & lt_mask);
-            const int leader = __ffs(mask) - 1;
-            uint32_t prev = 0;
-            if (lower == 0) {
-                prev = wh[d];
-                wh[d] = prev + __popc(mask);
+#if GSR_SORT_BALLOT
+            uint32_t mask = 0xffffffffu;  // 8 ballots -> lanes with the same digit (radix_sort_downsweep.glsl:95-102)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                mask &= bit ? bal : ~bal;
             }
-            prev = __shfl_sync(0xffffffffu, prev, leader);
-            rank[i] = prev + lower;
+#else
+            const uint32_t mask = __match_any_sync(0xffffffffu, d);
+#endif
+            rank[i] = (uint32_t)__popc(mask & lt_mask) | ((uint32_t)(__ffs(mask) - 1) << 8);  // lower | leader << 8
+            old[i] = 0u;
+            if ((mask & lt_mask) == 0u) old[i] = atomicAdd(&wh[d], (uint32_t)__popc(mask));
             __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t meta = rank[i];
+            const uint32_t prev = __shfl_sync(0xffffffffu, old[i], (int)(meta >> 8));
+            rank[i] = prev + (meta & 255u);
         }
         __syncthreads();  // (A) all warp histograms complete
 
