@@ -20,6 +20,9 @@
 #ifndef GSR_SORT_BALLOT
 #define GSR_SORT_BALLOT 1
 #endif
+#ifndef GSR_SORT_ATOMIC
+#define GSR_SORT_ATOMIC 0  // 1: returning shared atomics, consumed in a second loop; 0: load/add/store per row
+#endif
 
 namespace gsr {
 
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) onesweep_kernel(const
         //      load->add->store chain per row; __syncwarp() keeps row i's update ordered before row i+1's.
         uint32_t *wh = s_whist + warp * RADIX;
         const uint32_t lt_mask = (1u << lane) - 1u;
+#if GSR_SORT_ATOMIC
         uint32_t old[ITEMS];  // counter value before this row (valid in the leader lane)
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
@@ -198,6 +202,28 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) onesweep_kernel(const
             const uint32_t prev = __shfl_sync(0xffffffffu, old[i], (int)(meta >> 8));
             rank[i] = prev + (meta & 255u);
         }
+#else
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = (key[i] >> shift) & 255u;
+            uint32_t mask = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                mask &= bit ? bal : ~bal;
+            }
+            const uint32_t lower = __popc(mask & lt_mask);
+            uint32_t prev = 0;
+            if (lower == 0) {
+                prev = wh[d];
+                wh[d] = prev + __popc(mask);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, __ffs(mask) - 1);
+            rank[i] = prev + lower;
+            __syncwarp();
+        }
+#endif
         __syncthreads();  // (A) all warp histograms complete
 
         // ---- digit totals, cross-warp exclusive offsets, early publication of the tile aggregate ----
