@@ -75,6 +75,10 @@ constexpr int COMP_MAX_PUSHES = GSR_COMP_MAX_PUSHES;  // common.cuh: queue capac
 #define GSR_COMP_QUANTUM 2  // chunks blended before an unfinished tile is handed back to the queue
 #endif
 constexpr uint32_t EXIT_TILE = 0xFFFFFFFFu;
+#ifndef GSR_COMP_GROUP
+#define GSR_COMP_GROUP 4  // splats per software-pipelined group of the blend loop
+#endif
+constexpr int GU = GSR_COMP_GROUP;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
@@ -176,35 +180,35 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
             }
 
             // :79-91, four splats per liveness test; `chunk` rounded up to 4 reads null splats (opacity 0 => exact no-op)
-            const int chunk4 = (chunk + 3) & ~3;
-            for (int j = 0; j < chunk4; j += 4) {
+            const int chunk4 = (chunk + GU - 1) & ~(GU - 1);
+            for (int j = 0; j < chunk4; j += GU) {
                 if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
                 // ---- phase A: alpha = opacity * exp(power) of four splats, written stage by stage so that the four
                 //      ~25-instruction dependency chains are interleaved instruction by instruction (a lone warp
                 //      otherwise runs this loop at IPC 0.23: measured 25 us per chunk for a tile that owns its SM)
-                float4 A[4], B[4];
-                float CB[4], oy[4];
-                u64 ox2[4], pw2[4], tm2[4], e2[4], al2[4];
+                float4 A[GU], B[GU];
+                float CB[GU], oy[GU];
+                u64 ox2[GU], pw2[GU], tm2[GU], e2[GU], al2[GU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { A[u] = s_a[j + u]; B[u] = s_b[j + u]; CB[u] = s_c[j + u]; }
+                for (int u = 0; u < GU; ++u) { A[u] = s_a[j + u]; B[u] = s_b[j + u]; CB[u] = s_c[j + u]; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
+                for (int u = 0; u < GU; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
                 // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy  with q = fma(cz*oy, oy, cx*ox*ox), power = fma(-(cy*ox), oy, -0.5*q)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
+                for (int u = 0; u < GU; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
+                for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
+                for (int u = 0; u < GU; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = mul2(bc(B[u].x), ox2[u]);
+                for (int u = 0; u < GU; ++u) e2[u] = mul2(bc(B[u].x), ox2[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
+                for (int u = 0; u < GU; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
                 // exp(power): det_exp(), two lanes at a time
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pw2[u] = mul2(pw2[u], L2E2);
+                for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], L2E2);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < GU; ++u) {
                     float tl, th;
                     upk(pw2[u], tl, th);
                     tl = g_min(g_max(tl, -127.0f), 128.0f);
@@ -212,37 +216,37 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
                     pw2[u] = pk(tl, th);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) tm2[u] = add2(pw2[u], MAGIC2);
+                for (int u = 0; u < GU; ++u) tm2[u] = add2(pw2[u], MAGIC2);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) al2[u] = sub2(tm2[u], MAGIC2);
+                for (int u = 0; u < GU; ++u) al2[u] = sub2(tm2[u], MAGIC2);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
+                for (int u = 0; u < GU; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = fma2(C6, pw2[u], C5);
+                for (int u = 0; u < GU; ++u) e2[u] = fma2(C6, pw2[u], C5);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C4);
+                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C4);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C3);
+                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C3);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C2);
+                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C2);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], C1);
+                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C1);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = fma2(e2[u], pw2[u], ONE2);
+                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], ONE2);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < GU; ++u) {
                     float ml, mh;
                     upk(tm2[u], ml, mh);
                     tm2[u] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
                                 __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e2[u] = mul2(e2[u], tm2[u]);
+                for (int u = 0; u < GU; ++u) e2[u] = mul2(e2[u], tm2[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) al2[u] = mul2(bc(B[u].y), e2[u]);
+                for (int u = 0; u < GU; ++u) al2[u] = mul2(bc(B[u].y), e2[u]);
                 // ---- phase B: the sequential part (:89-90).  Dead pixels take alpha = 0: the reference's loop exit ----
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < GU; ++u) {
                     float al, ah;
                     upk(al2[u], al, ah);
                     al = (t0 > MIN_ALPHA) ? al : 0.0f;

@@ -178,9 +178,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
     extern __shared__ __align__(128) unsigned char proj_smem[];
     __shared__ uint32_t s_bid;
     __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS][2];
-    __shared__ uint32_t s_off[PROJ_WARPS][32];  // exclusive duplicate offsets inside the warp
-    __shared__ uint32_t s_xy[PROJ_WARPS][32];   // x0 | y0 << 16
-    __shared__ uint32_t s_wd[PROJ_WARPS][32];   // rect width | depth16 << 16
     __shared__ uint32_t s_wtotal[PROJ_WARPS];   // duplicate count of each warp
     __shared__ uint32_t s_count, s_ready, s_nvis;
     __shared__ int32_t s_last;
@@ -327,9 +324,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
     const uint32_t emit_mask = __ballot_sync(0xffffffffu, n != 0u);
     const uint32_t nvis = __popc(emit_mask);
     const int32_t wl = __reduce_max_sync(0xffffffffu, last_tile);
-    s_off[warp][lane] = incl - n;
-    s_xy[warp][lane] = x0u | (y0u << 16);
-    s_wd[warp][lane] = wu | (depth << 16);
     bool closer = false;
     uint32_t cta_total = 0;
     if (lane == 0) {
@@ -349,28 +343,14 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
     closer = __shfl_sync(0xffffffffu, (int)closer, 0) != 0;
     cta_total = __shfl_sync(0xffffffffu, cta_total, 0);
 
-    // ---- phase 2: SH planes -> colour -> record ----
-    if (nvis >= SH_BULK_MIN) {
-        if (lane == 0) {
-            mbar_expect_tx(&s_bar[warp][1], 12u * 512u);
+    // ---- phase 2: SH planes -> colour -> record.  The closer resolves the CTA's base (decoupled look-back over the
+    //      CTA aggregates) while its SH bulk copies are in flight, so the other warps rarely find `s_ready` unset ----
+    const bool bulk = nvis >= SH_BULK_MIN;
+    if (bulk && lane == 0) {
+        mbar_expect_tx(&s_bar[warp][1], 12u * 512u);
 #pragma unroll
-            for (int k = 3; k < NUM_PLANES; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][1]);
-        }
-        mbar_wait(&s_bar[warp][1], 0);
-        if (n) {
-            float col[3];
-            sh_color<true>(slab + 3 * 32 + lane, 32, vx, vy, vz, col);
-            float4 *rec = a.records + (uint64_t)id * 3u;
-            rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
-        }
-    } else if (n) {
-        float col[3];
-        sh_color<false>(a.soa + 3ull * a.plane_stride + id, a.plane_stride, vx, vy, vz, col);
-        float4 *rec = a.records + (uint64_t)id * 3u;
-        rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
+        for (int k = 3; k < NUM_PLANES; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][1]);
     }
-
-    // ---- chained scan across CTAs (decoupled look-back by the closer; aggregate already published) ----
     if (closer) {
         const unsigned long long cta_base = lookback_exclusive(a.lookback, bid, (unsigned long long)cta_total, lane);
         if (lane == 0) {
@@ -389,32 +369,65 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             }
         }
     }
+    if (bulk) {
+        mbar_wait(&s_bar[warp][1], 0);
+        if (n) {
+            float col[3];
+            sh_color<true>(slab + 3 * 32 + lane, 32, vx, vy, vz, col);
+            float4 *rec = a.records + (uint64_t)id * 3u;
+            rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
+        }
+    } else if (n) {
+        float col[3];
+        sh_color<false>(a.soa + 3ull * a.plane_stride + id, a.plane_stride, vx, vy, vz, col);
+        float4 *rec = a.records + (uint64_t)id * 3u;
+        rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
+    }
+
     unsigned long long base = 0;
     if (lane == 0) {
-        while (*(volatile uint32_t *)&s_ready == 0u) __nanosleep(32);
+        while (*(volatile uint32_t *)&s_ready == 0u) __nanosleep(100);
         __threadfence_block();
         base = *(volatile unsigned long long *)&s_cta_base;
         for (uint32_t w = 0; w < warp; ++w) base += ((volatile uint32_t *)s_wtotal)[w];
     }
     base = __shfl_sync(0xffffffffu, base, 0);
 
-    // ---- warp-cooperative emit (:219-226): output slot j of the warp -> owner splat by binary search ----
-    for (uint32_t j = lane; j < total; j += 32u) {
-        uint32_t lo = 0, hi = 31;
+    // ---- emit (:219-226): key slot base + off + j holds tile j (row-major) of the splat's rect.  Rects of up to
+    //      EMIT_SMALL tiles (the common case: M/V ~ 1.6) are written by their own lane -- neighbouring lanes own
+    //      neighbouring slots, so the stores still coalesce; larger rects are emitted by the whole warp, 32 tiles per
+    //      step, which keeps one huge splat from serialising a lane for hundreds of iterations. ----
+    constexpr uint32_t EMIT_SMALL = 4;
+    const uint32_t my_off = incl - n;
+    if (n != 0u && n <= EMIT_SMALL) {
+        uint32_t x = x0u, y = y0u;
+        const uint32_t x1 = x0u + wu;
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (s_off[warp][mid] <= j) lo = mid; else hi = mid - 1;
+        for (uint32_t j = 0; j < EMIT_SMALL; ++j) {
+            if (j < n) {
+                const unsigned long long g = base + my_off + j;
+                if (g < (unsigned long long)a.capacity) {
+                    a.keys[g] = ((y * gx + x) << 16) | depth;
+                    a.values[g] = id;
+                }
+                if (++x == x1) { x = x0u; ++y; }
+            }
         }
-        const uint32_t r = j - s_off[warp][lo];
-        const uint32_t xy = s_xy[warp][lo], wd = s_wd[warp][lo];
-        const uint32_t w = wd & 0xFFFFu;
-        const uint32_t ry = r / w, rx = r - ry * w;
-        const uint32_t tile_id = ((xy >> 16) + ry) * gx + (xy & 0xFFFFu) + rx;
-        const unsigned long long g = base + j;
-        if (g < (unsigned long long)a.capacity) {
-            a.keys[g] = (tile_id << 16) | (wd >> 16);
-            a.values[g] = id0 + lo;
+    }
+    uint32_t big = __ballot_sync(0xffffffffu, n > EMIT_SMALL);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1u;
+        const uint32_t sn = __shfl_sync(0xffffffffu, n, src), soff = __shfl_sync(0xffffffffu, my_off, src);
+        const uint32_t sx0 = __shfl_sync(0xffffffffu, x0u, src), sy0 = __shfl_sync(0xffffffffu, y0u, src);
+        const uint32_t sw = __shfl_sync(0xffffffffu, wu, src), sdepth = __shfl_sync(0xffffffffu, depth, src);
+        for (uint32_t j = lane; j < sn; j += 32u) {
+            const uint32_t ry = j / sw, rx = j - ry * sw;
+            const unsigned long long g = base + soff + j;
+            if (g < (unsigned long long)a.capacity) {
+                a.keys[g] = (((sy0 + ry) * gx + sx0 + rx) << 16) | sdepth;
+                a.values[g] = id0 + (uint32_t)src;
+            }
         }
     }
 }
