@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--splats", type=int, default=int(os.environ.get("GSR_BENCH_SPLATS", "0")), help="debug: override N (marks the line reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-radix", action="store_true")
+    ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["peer", "nccl"],
+                    help="N>1: 'peer' = compositor stores bands into the root's frame over NVLink peer memory + 4-byte NCCL sync; "
+                         "'nccl' = NCCL gather of the band framebuffers")
     return ap.parse_args()
 
 
@@ -273,13 +276,25 @@ def main():
             host_chunks.append(s60)
     t_gen = time.perf_counter() - t_gen
     fb = None
-    if world > 1:  # the gather needs a torch-visible frame; single GPU uses the library's own double buffer
+    peer = world > 1 and args.mgpu == "peer"
+    sync_flag = torch.zeros(1, dtype=torch.int32, device="cuda") if world > 1 else None
+    if peer:
+        # fused compositor + gather: the root exports CUDA-IPC handles of its two frames; every rank's compositor then
+        # stores its band directly into the root's memory over NVLink
+        handles = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            handles.copy_(torch.frombuffer(bytearray(rast.peer_export()), dtype=torch.uint8))
+        dist.broadcast(handles, src=0)
+        if rank != 0:
+            rast.peer_import(bytes(handles.cpu().numpy().tobytes()))
+        rast.set_band(*band)
+    elif world > 1:  # NCCL gather needs a torch-visible frame
         fb = torch.zeros((h_pad, W, 4), dtype=torch.float32, device="cuda")
         rast.set_framebuffer_external(fb.data_ptr())
         rast.set_band(*band)
     # two page-locked host frames: the application consumes frame i while frame i+1 is being copied
     pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
-    rgb_readback = world == 1  # single GPU: RGB32F read-back (alpha == 1.0 stays on the device); multi-GPU root copies RGBA
+    rgb_readback = world == 1 or peer  # RGB32F read-back (alpha == 1.0 stays on the device); the NCCL-gather mode copies RGBA
     pinned = pinned2[0] if rank == 0 else None
 
     frames = frame_params(wl, args.warmup + args.steps)
@@ -288,6 +303,13 @@ def main():
         vp, ub = frames[i]
         if world == 1:
             rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=e2e and rgb_readback)
+        elif peer:
+            rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # band lands in the root's frame (slot i & 1) over NVLink
+            if e2e and rank == 0:
+                rast.stream_join()                                 # previous read-backs done before peers may reuse a slot
+            dist.all_reduce(sync_flag)                             # 4-byte completion sync: all bands of this frame have landed
+            if e2e and rank == 0:
+                rast.readback_async(pinned2[i & 1].data_ptr(), rgb_only=True)
         else:
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)
             sharding.gather_bands(fb, rank, world, dst=0)  # one NCCL gather of the band framebuffers per frame
@@ -305,7 +327,7 @@ def main():
         e0.record(stream)
         for i in range(args.warmup, args.warmup + args.steps):
             step(i, e2e)
-        if e2e and world == 1:
+        if e2e and (world == 1 or (peer and rank == 0)):
             rast.stream_join()  # the timed region ends when the last frame has landed in host memory
         e1.record(stream)
         torch.cuda.synchronize()
@@ -386,7 +408,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": fps,
             "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": N, "width": W, "height": H, "sh_degree": 3,
-                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world} + NCCL framebuffer gather",
+                       "parallelism": "single GPU" if world == 1 else (f"tile-row bands x{world}, compositor stores into the root frame over NVLink peer memory + 4-byte NCCL sync" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
                        "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * N / 1e6),
                        "duplicates_M": M, "visible_V": V, "staged_C": Cc, "reduced": reduced, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),

@@ -19,7 +19,8 @@ GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES = 0x1, 0x2
 # every symbol include/gsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_resize", "gsr_set_band", "gsr_render",
-    "gsr_render_async", "gsr_render_async_rgb", "gsr_stream_join", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
+    "gsr_render_async", "gsr_render_async_rgb", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
+    "gsr_stream_join", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
     "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
     "gsr_device_count", "gsr_version",
@@ -75,6 +76,9 @@ def lib():
         L.gsr_render_async_rgb.argtypes = [vp, fp, vp, C.c_float, vp]
         L.gsr_sync.argtypes = [vp]
         L.gsr_stream_join.argtypes = [vp]
+        L.gsr_readback_async.argtypes = [vp, vp, C.c_int]
+        L.gsr_peer_export_framebuffers.argtypes = [vp, vp]
+        L.gsr_peer_import_framebuffers.argtypes = [vp, vp]
         L.gsr_framebuffer_device_ptr.argtypes = [vp]
         L.gsr_framebuffer_device_ptr.restype = vp
         L.gsr_set_framebuffer_external.argtypes = [vp, vp]

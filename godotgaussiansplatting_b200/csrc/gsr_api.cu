@@ -57,6 +57,10 @@ struct gsr_ctx {
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool copied_valid[2] = {false, false};
     uint64_t async_counter = 0;
+    // multi-GPU peer mode: every rank's compositor stores its band straight into the presenting rank's two frames
+    bool peer_mode = false, peer_opened = false;
+    float4 *peer_fb[2] = {nullptr, nullptr};
+    uint64_t peer_counter = 0;
     float4 *pick = nullptr;
     float4 *staging = nullptr;
     uint64_t staging_splats = 0;
@@ -113,6 +117,7 @@ void free_ctx(gsr_ctx *c) {
     cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
     sort_workspace_destroy(c->sort);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); }
     cudaFree(c->rgb[0]); cudaFree(c->rgb[1]);
     cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
@@ -379,8 +384,35 @@ GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *unifor
     return GSR_OK;
 }
 
+static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, float *pinned_host, bool rgb_only) {
+    const size_t pixels = (size_t)c->width * c->height;
+    int rc;
+    if (rgb_only && !c->rgb[slot]) GSR_CUDA_TRY(cudaMalloc((void **)&c->rgb[slot], sizeof(float) * 3 * pixels + 64));
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
+    GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+    if (rgb_only) {
+        if ((rc = launch_pack_rgb(frame, c->rgb[slot], pixels, c->copy_stream))) return rc;
+        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, c->rgb[slot], sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
+    } else {
+        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, frame, sizeof(float4) * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->copied_valid[slot] = true;
+    return GSR_OK;
+}
+
 static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float *pinned_host, bool rgb_only) {
     if (!c) return GSR_ERR_INVALID;
+    if (c->peer_mode) {  // frames alternate between the presenting rank's two frames; read-back is a separate call
+        if (pinned_host) { set_last_error("peer mode: render with a NULL host pointer, then gsr_readback_async on the presenting rank"); return GSR_ERR_STATE; }
+        int rc = use_device(c->device);
+        if (rc) return rc;
+        const int slot = (int)(c->peer_counter & 1u);
+        if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+        if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, c->peer_fb[slot]))) return rc;
+        c->peer_counter += 1;
+        return GSR_OK;
+    }
     if (!pinned_host || c->fb_ext) {  // nothing to read back, or the caller owns the frame memory: plain enqueue
         if (rgb_only && pinned_host) { set_last_error("gsr_render_async_rgb is unavailable with an external framebuffer"); return GSR_ERR_STATE; }
         int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
@@ -396,20 +428,9 @@ static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uni
     if (rc) return rc;
     const int slot = (int)(c->async_counter & 1u);
     float4 *target = slot ? c->fb2 : c->fb;
-    const size_t pixels = (size_t)c->width * c->height;
-    if (rgb_only && !c->rgb[slot]) GSR_CUDA_TRY(cudaMalloc((void **)&c->rgb[slot], sizeof(float) * 3 * pixels + 64));
     if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
     if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, target))) return rc;
-    GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
-    GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
-    if (rgb_only) {
-        if ((rc = launch_pack_rgb(target, c->rgb[slot], pixels, c->copy_stream))) return rc;
-        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, c->rgb[slot], sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
-    } else {
-        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, target, sizeof(float4) * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
-    }
-    GSR_CUDA_TRY(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
-    c->copied_valid[slot] = true;
+    if ((rc = readback_enqueue(c, target, slot, pinned_host, rgb_only))) return rc;
     c->async_counter += 1;
     return GSR_OK;
 }
@@ -420,6 +441,41 @@ GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *
 
 GSR_API int gsr_render_async_rgb(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host_rgb) {
     return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host_rgb, true);
+}
+
+GSR_API int gsr_readback_async(gsr_ctx *c, float *pinned_host, int rgb_only) {
+    if (!c || !pinned_host) return GSR_ERR_INVALID;
+    if (!c->fb_last || c->fb_ext) { set_last_error("gsr_readback_async: no library-owned frame rendered yet"); return GSR_ERR_STATE; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const int slot = (c->fb_last == c->fb2 || (c->peer_mode && c->fb_last == c->peer_fb[1])) ? 1 : 0;
+    return readback_enqueue(c, c->fb_last, slot, pinned_host, rgb_only != 0);
+}
+
+GSR_API int gsr_peer_export_framebuffers(gsr_ctx *c, void *handles128) {
+    if (!c || !handles128) return GSR_ERR_INVALID;
+    if (!c->fb || !c->fb2 || c->fb_ext) { set_last_error("gsr_peer_export_framebuffers: call gsr_resize first (library-owned frames only)"); return GSR_ERR_STATE; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h[2];
+    GSR_CUDA_TRY(cudaIpcGetMemHandle(&h[0], c->fb));
+    GSR_CUDA_TRY(cudaIpcGetMemHandle(&h[1], c->fb2));
+    memcpy(handles128, h, sizeof h);
+    c->peer_fb[0] = c->fb; c->peer_fb[1] = c->fb2;
+    c->peer_mode = true;
+    return GSR_OK;
+}
+
+GSR_API int gsr_peer_import_framebuffers(gsr_ctx *c, const void *handles128) {
+    if (!c || !handles128) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, handles128, sizeof h);
+    GSR_CUDA_TRY(cudaIpcOpenMemHandle((void **)&c->peer_fb[0], h[0], cudaIpcMemLazyEnablePeerAccess));
+    GSR_CUDA_TRY(cudaIpcOpenMemHandle((void **)&c->peer_fb[1], h[1], cudaIpcMemLazyEnablePeerAccess));
+    c->peer_mode = true; c->peer_opened = true;
+    return GSR_OK;
 }
 
 GSR_API int gsr_stream_join(gsr_ctx *c) {

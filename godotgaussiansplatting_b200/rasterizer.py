@@ -184,6 +184,19 @@ class GaussianSplattingRasterizer:
     def sync(self) -> None:
         _lib.check(_lib.lib().gsr_sync(self._ctx), "gsr_sync")
 
+    def readback_async(self, host_ptr: int, rgb_only: bool = False) -> None:
+        _lib.check(_lib.lib().gsr_readback_async(self._ctx, C.c_void_p(host_ptr), int(rgb_only)), "gsr_readback_async")
+
+    def peer_export(self) -> bytes:
+        """Presenting rank: CUDA-IPC handles (128 bytes) of its two frames."""
+        buf = (C.c_ubyte * 128)()
+        _lib.check(_lib.lib().gsr_peer_export_framebuffers(self._ctx, buf), "gsr_peer_export_framebuffers")
+        return bytes(buf)
+
+    def peer_import(self, handles: bytes) -> None:
+        buf = (C.c_ubyte * 128).from_buffer_copy(handles)
+        _lib.check(_lib.lib().gsr_peer_import_framebuffers(self._ctx, buf), "gsr_peer_import_framebuffers")
+
     def stream_join(self) -> None:
         """Make the render stream wait for the pipelined read-back copies enqueued so far."""
         _lib.check(_lib.lib().gsr_stream_join(self._ctx), "gsr_stream_join")

@@ -114,6 +114,14 @@ GSR_API int gsr_resize(gsr_ctx *ctx, int32_t width, int32_t height);
  * rows [row_begin, row_end) only; keys keep the global tile id.  (0, tiles_y) restores the full frame. */
 GSR_API int gsr_set_band(gsr_ctx *ctx, int32_t row_begin, int32_t row_end);
 
+/* Fused compositor + framebuffer gather over NVLink peer memory (replaces the NCCL gather of SURVEY 8e): the presenting
+ * rank exports CUDA-IPC handles of its two frames (2 x 64 bytes); every other rank imports them, after which its
+ * compositor stores its tile-row band straight into the presenting rank's memory.  In this mode gsr_render_async is
+ * called with a NULL host pointer on every rank (frames alternate between the two buffers in lockstep), the ranks
+ * synchronise per frame with any 4-byte collective, and the presenting rank calls gsr_readback_async. */
+GSR_API int gsr_peer_export_framebuffers(gsr_ctx *ctx, void *handles128);
+GSR_API int gsr_peer_import_framebuffers(gsr_ctx *ctx, const void *handles128);
+
 /* ---- rasterize() (rasterizer.gd:122-160).
  *      view_proj: the 128-byte push constant of update_camera_matrices (rasterizer.gd:181-193):
  *                 view_matrix then projection_matrix, GLSL column-major.
@@ -138,6 +146,9 @@ GSR_API int gsr_render_async(gsr_ctx *ctx, const float view_proj[32], const void
  * constant 1.0 (gsplat_render.glsl:101), so it is packed away on the device before the PCIe transfer (-25 % bytes). */
 GSR_API int gsr_render_async_rgb(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
                                  float *pinned_host_rgb);
+/* Read the most recently rendered library-owned frame back to page-locked host memory on the copy stream, ordered
+ * after everything enqueued on the render stream so far (multi-GPU: after the per-frame completion sync). */
+GSR_API int gsr_readback_async(gsr_ctx *ctx, float *pinned_host, int rgb_only);
 GSR_API int gsr_stream_join(gsr_ctx *ctx);
 GSR_API int gsr_sync(gsr_ctx *ctx);
 
