@@ -302,7 +302,11 @@ def main():
         dist.broadcast(handles, src=0)
         if rank != 0:
             rast.peer_import(bytes(handles.cpu().numpy().tobytes()))
-        rast.set_band(*band)
+        rast.set_row_interleave(rank, world)  # balanced: rank r owns tile rows r, r+G, ... ; fast sharded mode
+
+        class _Word:  # the library's int32 "local last occupied tile + 1" word as a torch tensor (all-reduced in place)
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (rast.band_sync_word_ptr(), False), "version": 2}
+        sync_flag = torch.as_tensor(_Word(), device="cuda")
     elif world > 1:  # NCCL gather needs a torch-visible frame
         fb = torch.zeros((h_pad, W, 4), dtype=torch.float32, device="cuda")
         rast.set_framebuffer_external(fb.data_ptr())
@@ -322,7 +326,8 @@ def main():
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # band lands in the root's frame (slot i & 1) over NVLink
             if e2e and rank == 0:
                 rast.stream_join()                                 # previous read-backs done before peers may reuse a slot
-            dist.all_reduce(sync_flag)                             # 4-byte completion sync: all bands of this frame have landed
+            dist.all_reduce(sync_flag, op=dist.ReduceOp.MAX)       # 4-byte sync: all rows have landed + frame-global last tile
+            rast.band_fixup()                                      # reference quirk Q10 on the rank that owns that tile
             if e2e and rank == 0:
                 rast.readback_async(pinned2[i & 1].data_ptr(), rgb_only=True)
         else:
@@ -426,7 +431,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": fps,
             "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": N, "width": W, "height": H, "sh_degree": 3,
-                       "parallelism": "single GPU" if world == 1 else (f"tile-row bands x{world}, compositor stores into the root frame over NVLink peer memory + 4-byte NCCL sync" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
+                       "parallelism": "single GPU" if world == 1 else (f"cyclic tile rows x{world} (row %% {world} == rank), early-reject projection, compositor stores into the root frame over NVLink peer memory + 4-byte NCCL all-reduce" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
                        "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * N / 1e6),
                        "duplicates_M": M, "visible_V": V, "staged_C": Cc, "reduced": reduced, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),

@@ -145,7 +145,12 @@ struct ProjectionArgs {
     Uniforms u;
     float focal_base[2];     // (dims*0.5) * (P00, P11)           gsplat_projection.glsl:127-128
     float lim_lo[2], lim_hi[2];  // -+ (1/(P00,P11)) * 1.3          gsplat_projection.glsl:129,133
-    int32_t band_y0, band_y1;
+    int32_t band_y0, band_y1;  // tile rows [band_y0, band_y1) ...
+    int32_t row_mod, row_rem;  // ... of which this context owns those with row % row_mod == row_rem (1, 0 = all)
+    int32_t fast_reject;       // sharded fast mode: conservative early reject of splats that cannot touch an owned row;
+                               // last_tile is then the LOCAL last emitted tile (global one by all-reduce, gsr_band_fixup)
+    int32_t fast_mode;         // fast sharded mode (row_mod > 1): last_tile is the LOCAL last emitted tile
+    float w_frob2;             // upper bound of |mat3(view_matrix)|_2^2 (for the early reject)
     float4 *records;         // 3 float4 per splat id (RasterizeData layout)
     uint32_t *keys, *values;
     uint32_t capacity;
@@ -155,8 +160,12 @@ struct ProjectionArgs {
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
 uint32_t projection_num_blocks(uint32_t num_splats);
 
+// sharded: 0 = full frame, 1 = exact sharded mode (global last tile known from the projection), 2 = fast sharded mode
+// (local last tile -> *sync_word = tile + 1; the frame-global quirk is applied later by launch_band_fixup).
 int launch_tile_ranges(const uint32_t *sorted_keys, const FrameState *frame, uint2 *bounds, uint32_t num_tiles,
-                       int quirks, int sharded, int grid, cudaStream_t stream);
+                       int quirks, int sharded, int32_t *sync_word, int grid, cudaStream_t stream);
+int launch_band_fixup(const int32_t *global_last_plus1, float4 *out, int32_t width, int32_t height, int32_t tiles_x, int32_t num_tiles_total,
+                      int32_t band_y0, int32_t band_y1, int32_t row_mod, int32_t row_rem, cudaStream_t stream);
 
 struct CompositeArgs {
     const float4 *records;
@@ -164,7 +173,8 @@ struct CompositeArgs {
     const uint2 *bounds;
     float4 *out;             // W*H RGBA32F
     int32_t width, height, tiles_x;
-    int32_t tile_begin;      // first tile id rendered (band_y0 * tiles_x)
+    int32_t tile_begin;      // first tile id rendered (band_y0 * tiles_x, or the first owned row)
+    int32_t row_step;        // distance in tile rows between consecutive owned rows (1 = contiguous band)
     int32_t num_tiles;       // tiles rendered
     float heatmap_factor;
     uint32_t target_tile_id; // 0xFFFFFFFF = none (rasterizer.gd:158)

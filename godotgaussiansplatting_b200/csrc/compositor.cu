@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
             // remaining busy tiles start as a second wave.)
             const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
             if (ticket < (uint32_t)p.num_tiles) {
-                s_tile = (uint32_t)p.tile_begin + ticket;
+                // owned tiles: rows tile_begin/tiles_x + k*row_step, all columns (row_step == 1: one contiguous band)
+                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
                 volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
@@ -143,7 +144,9 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
         u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;  // blended colour of the two pixels
         float t0 = 1.0f, t1 = 1.0f;                    // transmittance of the two pixels
         int i0 = 0;
-        const uint32_t local_tile = tile_id - (uint32_t)p.tile_begin;
+        // index of this tile among the owned tiles (slot of its spilled state)
+        const uint32_t rel = tile_id - (uint32_t)p.tile_begin;
+        const uint32_t local_tile = (rel / (uint32_t)(p.row_step * p.tiles_x)) * (uint32_t)p.tiles_x + rel % (uint32_t)p.tiles_x;
         float4 *st = p.state + (uint64_t)local_tile * (2u * THREADS);
         if (resume) {  // written by another SM during this launch: read through L2
             const float4 sa = __ldcg(st + tid), sb = __ldcg(st + THREADS + tid);

@@ -5,6 +5,7 @@
 // (util/render_context.gd).  Fifteen compute dispatches with full barriers per frame in the reference
 // become 1 + 5 + 1 + 1 kernel launches on one CUDA stream, with no host synchronisation on the frame path.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stddef.h>
 #include <string.h>
 
@@ -68,6 +69,8 @@ struct gsr_ctx {
     bool keep_unsorted = false;
     int width = 0, height = 0, tiles_x = 0, tiles_y = 0, band_y0 = 0, band_y1 = 0;
     bool band_set = false;
+    int row_mod = 1, row_rem = 0;   // cyclic tile-row ownership (gsr_set_row_interleave): fast sharded mode when row_mod > 1
+    int32_t *sync_word = nullptr;   // local (then all-reduced) last occupied tile + 1
     cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
     bool ev_valid = false;
     uint32_t last_launches = 0;
@@ -122,6 +125,7 @@ void free_ctx(gsr_ctx *c) {
     cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    cudaFree(c->sync_word);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); cudaFree(c->trace); cudaFree(c->trace_count);
     if (c->ev) {
         for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -200,6 +204,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     TRY_ALLOC(c->lookback, sizeof(unsigned long long) * (size_t)c->lookback_blocks);
     c->frame = c->ring;
     TRY_ALLOC(c->pick, sizeof(float4));
+    TRY_ALLOC(c->sync_word, sizeof(int32_t));
     c->staging_splats = c->max_splats < (1ull << 18) ? c->max_splats : (1ull << 18);
     TRY_ALLOC(c->staging, sizeof(float4) * NUM_PLANES * c->staging_splats);
 #undef TRY_ALLOC
@@ -213,6 +218,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     cudaMemsetAsync(c->soa, 0, sizeof(float4) * NUM_PLANES * c->plane_stride, c->stream);
     cudaMemsetAsync(c->records, 0, sizeof(float4) * 3ull * c->max_splats, c->stream);
     cudaMemsetAsync(c->pick, 0, sizeof(float4), c->stream);
+    cudaMemsetAsync(c->sync_word, 0, sizeof(int32_t), c->stream);
     cudaMemsetAsync(c->ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { set_last_error("init sync -> %s", cudaGetErrorString(e)); free_ctx(c); return GSR_ERR_CUDA; }
@@ -286,6 +292,24 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     return GSR_OK;
 }
 
+GSR_API int gsr_set_row_interleave(gsr_ctx *c, int32_t row_rem, int32_t row_mod) {
+    if (!c || row_mod < 1 || row_rem < 0 || row_rem >= row_mod) { set_last_error("gsr_set_row_interleave: need 0 <= rem < mod"); return GSR_ERR_INVALID; }
+    c->row_mod = row_mod; c->row_rem = row_rem;
+    return GSR_OK;
+}
+
+GSR_API void *gsr_band_sync_word(gsr_ctx *c) { return c ? (void *)c->sync_word : nullptr; }
+
+GSR_API int gsr_band_fixup(gsr_ctx *c) {
+    if (!c) return GSR_ERR_INVALID;
+    if (c->row_mod <= 1 || !c->fb_last) return GSR_OK;  // exact modes resolve the quirk inside tile_ranges_kernel
+    if (c->flags & GSR_FLAG_FIXED_RANGES) return GSR_OK;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    return launch_band_fixup(c->sync_word, c->fb_last, c->width, c->height, c->tiles_x, c->tiles_x * c->tiles_y, c->band_y0, c->band_y1,
+                             c->row_mod, c->row_rem, c->stream);
+}
+
 GSR_API int gsr_set_band(gsr_ctx *c, int32_t row_begin, int32_t row_end) {
     if (!c || c->tiles_y == 0) { set_last_error("gsr_set_band before gsr_resize"); return GSR_ERR_STATE; }
     if (row_begin < 0 || row_end > c->tiles_y || row_begin > row_end) { set_last_error("band [%d,%d) outside [0,%d]", row_begin, row_end, c->tiles_y); return GSR_ERR_INVALID; }
@@ -330,7 +354,29 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
         pa.lim_lo[0] = n0 * 1.3f; pa.lim_lo[1] = n1 * 1.3f;
         pa.lim_hi[0] = t0 * 1.3f; pa.lim_hi[1] = t1 * 1.3f;
     }
+    const bool fast = c->row_mod > 1;
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
+    pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
+    // The conservative early reject is exact but, measured at 4 GPUs, a net loss: under SIMT a warp saves work only if all
+    // 32 lanes reject, and sparsely surviving warps lose the TMA SH path.  Off unless GSR_FAST_REJECT=1 (experiments).
+    static const int want_reject = getenv("GSR_FAST_REJECT") ? atoi(getenv("GSR_FAST_REJECT")) : 0;
+    pa.fast_reject = (want_reject && c->row_mod >= 3) ? 1 : 0;
+    pa.fast_mode = fast ? 1 : 0;
+    {   // |W|_2^2 <= |W^T W|_inf (largest absolute row sum of the Gram matrix); exactly 1 for a rigid camera
+        float g[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                g[i][j] = 0.0f;
+                for (int r = 0; r < 3; ++r) g[i][j] += view_proj[4 * i + r] * view_proj[4 * j + r];
+            }
+        float nrm = 0.0f;
+        for (int i = 0; i < 3; ++i) {
+            float row = 0.0f;
+            for (int j = 0; j < 3; ++j) row += g[i][j] < 0.0f ? -g[i][j] : g[i][j];
+            nrm = row > nrm ? row : nrm;
+        }
+        pa.w_frob2 = nrm * 1.0001f;
+    }
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
     if ((rc = launch_projection(pa, s))) return rc;
@@ -345,9 +391,10 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     if ((rc = sort_pairs_device(c->sort, c->keys, c->vals, m_ptr, c->keys + c->capacity, c->vals + c->capacity, s, &launches))) return rc;
     GSR_CUDA_TRY(cudaEventRecord(ev[2], s));  // 'Sort'
 
-    const int sharded = !(c->band_y0 == 0 && c->band_y1 == c->tiles_y);
+    const int sharded = fast ? 2 : (!(c->band_y0 == 0 && c->band_y1 == c->tiles_y) ? 1 : 0);
+    if (fast) GSR_CUDA_TRY(cudaMemsetAsync(c->sync_word, 0, sizeof(int32_t), s));
     const int quirks = (c->flags & GSR_FLAG_FIXED_RANGES) ? 0 : 1;
-    if ((rc = launch_tile_ranges(c->keys, c->frame, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), quirks, sharded, c->sm_count * 8, s))) return rc;
+    if ((rc = launch_tile_ranges(c->keys, c->frame, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), quirks, sharded, fast ? c->sync_word : nullptr, c->sm_count * 8, s))) return rc;
     launches += 1;
     GSR_CUDA_TRY(cudaEventRecord(ev[3], s));  // 'Boundaries'
 
@@ -356,8 +403,13 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     c->fb_last = out_fb;
     ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = out_fb;
     ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
-    ca.tile_begin = c->band_y0 * c->tiles_x;
-    ca.num_tiles = (c->band_y1 - c->band_y0) * c->tiles_x;
+    {   // owned tile rows: band rows with row % row_mod == row_rem
+        int first = c->band_y0 + ((c->row_rem - c->band_y0 % c->row_mod) + c->row_mod) % c->row_mod;
+        int nrows = first < c->band_y1 ? (c->band_y1 - 1 - first) / c->row_mod + 1 : 0;
+        ca.tile_begin = first * c->tiles_x;
+        ca.row_step = c->row_mod;
+        ca.num_tiles = nrows * c->tiles_x;
+    }
     ca.heatmap_factor = heatmap_factor;
     ca.target_tile_id = 0xFFFFFFFFu;  // rasterizer.gd:158
     ca.pick = c->pick;
@@ -511,11 +563,11 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
     if (rc) return rc;
     const uint32_t T = (uint32_t)(c->tiles_x * c->tiles_y);
     const uint32_t t0 = (uint32_t)(c->band_y0 * c->tiles_x), t1 = (uint32_t)(c->band_y1 * c->tiles_x);
-    if (tile_id < T && tile_id >= t0 && tile_id < t1) {
+    if (tile_id < T && tile_id >= t0 && tile_id < t1 && (int)(tile_id / (uint32_t)c->tiles_x) % c->row_mod == c->row_rem) {
         CompositeArgs ca;
         ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
         ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
-        ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1;
+        ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1; ca.row_step = 1;
         ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
         ca.frame = c->pick_frame; ca.count_staged = 0;  // own queue counters; slot 0 of the queue, state slot 0
         ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;

@@ -241,18 +241,42 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             splat_opacity = cb.z * tfl * tfl;
             const float splat_scale = ms * (2.0f * (1.0f - tfl) + 1.0f * tfl);
 
-            // :124-142 project_covariance
-            Mat3 cov3 = {{{ca.x, ca.y, ca.z}, {ca.y, ca.w, cb.x}, {ca.z, cb.x, cb.y}}};
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) cov3.m[c][r] = cov3.m[c][r] * splat_scale * splat_scale;
             // per-frame constants (focal = dims*0.5*tan_fov_inv, +-tan_fov*1.3) are evaluated once on the host with
             // the same IEEE operations (ProjectionArgs::focal_base, lim_lo, lim_hi)
             const float z_inv = 1.0f / view[2];
             const float focal0 = a.focal_base[0] * z_inv, focal1 = a.focal_base[1] * z_inv;
             const float mx = g_clamp(view[0] * z_inv, a.lim_lo[0], a.lim_hi[0]);
             const float my = g_clamp(view[1] * z_inv, a.lim_lo[1], a.lim_hi[1]);
+            const float ndc0 = clip[0] / clip[3], ndc1 = clip[1] / clip[3], ndc2 = clip[2] / clip[3];
+            const float ipx = ((ndc0 + 1.0f) * 0.5f - 1.0f * (1.0f - tf)) * (float)(W - 1);
+            const float ipy = ((ndc1 + 1.0f) * 0.5f - 0.75f * (1.0f - tf)) * (float)(H - 1);
+
+            if (a.fast_reject) {
+                // Sharded fast mode: a CONSERVATIVE radius decides whether the splat can touch a tile row this context
+                // owns; if not, the exact math below would end in "nt == 0" anyway.  With e1 <= trace(cov_2d) + 0.32,
+                // trace(J W S' W^T J^T) <= lambda_max(S') |J|_F^2 |W|_2^2 <= |S'|_F |J|_F^2 |W|_2^2 and pow(op, 0.2) <= max(1, op):
+                //   radius <= max(1, op) * 2.5 * sqrt(|S'|_F |J|_F^2 |W|_2^2 + 0.92)        (w_norm2 >= |W|_2^2 from the host)
+                const float sf2 = (ca.x * ca.x + ca.w * ca.w + cb.y * cb.y) + 2.0f * (ca.y * ca.y + ca.z * ca.z + cb.x * cb.x);
+                const float lam = sqrtf(sf2) * splat_scale * splat_scale * 1.0001f;
+                const float jf2 = focal0 * focal0 + focal1 * focal1 * (1.0f + mx * mx + my * my);
+                const float rb = g_max(1.0f, splat_opacity) * 2.5f * sqrtf(lam * jf2 * a.w_frob2 + 0.92f) * 1.001f + 1.0f;
+                const float fa = floorf((ipy - rb) * 0.0625f), fb = floorf((ipy + rb) * 0.0625f);
+                if (fa == fa && fb == fb && fabsf(fa) < 1.0e9f && fabsf(fb) < 1.0e9f) {  // finite: otherwise let the exact path decide
+                    int32_t lo = (int32_t)fa, hi = (int32_t)fb;
+                    if (lo < a.band_y0) lo = a.band_y0;
+                    if (hi > a.band_y1 - 1) hi = a.band_y1 - 1;
+                    if (hi < lo) break;
+                    const int32_t first = lo + ((a.row_rem - lo % a.row_mod) + a.row_mod) % a.row_mod;
+                    if (first > hi) break;
+                }
+            }
+
+            // :124-142 project_covariance
+            Mat3 cov3 = {{{ca.x, ca.y, ca.z}, {ca.y, ca.w, cb.x}, {ca.z, cb.x, cb.y}}};
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) cov3.m[c][r] = cov3.m[c][r] * splat_scale * splat_scale;
             // jacobian columns (focal.x, 0, -focal.y*mean.x), (0, focal.y, -focal.y*mean.y), 0 (:134-137).  gsr spec: the
             // structurally-zero terms of b = transpose(mat3(view)) * jacobian are skipped; only the three entries of
             // cov_2d = transpose(b) * cov_3d * b that :141 reads are formed.  B0[r] = b[0][r], B1[r] = b[1][r].
@@ -284,10 +308,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             const float e1 = mid + 1.0f * sq, e2 = mid + -1.0f * sq;
             if (e1 < 0.0f || e2 < 0.0f) break;
 
-            // :184-185
-            const float ndc0 = clip[0] / clip[3], ndc1 = clip[1] / clip[3], ndc2 = clip[2] / clip[3];
-            const float ipx = ((ndc0 + 1.0f) * 0.5f - 1.0f * (1.0f - tf)) * (float)(W - 1);
-            const float ipy = ((ndc1 + 1.0f) * 0.5f - 0.75f * (1.0f - tf)) * (float)(H - 1);
+            // :184-185 ndc / image_pos: computed above (same operations), before the early reject
 
             // :190-194
             const float radius = det_pow(splat_opacity, 0.2f) * 2.5f * sqrtf(g_max(e1, e2));
@@ -297,12 +318,19 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             int32_t y0 = (int32_t)g_clamp((ipy - radius) / 16.0f, 0.0f, fgy);
             int32_t x1 = (int32_t)g_clamp(ceilf((ipx + radius) / 16.0f), 0.0f, fgx);
             int32_t y1 = (int32_t)g_clamp(ceilf((ipy + radius) / 16.0f), 0.0f, fgy);
-            // largest tile of the un-banded rect (global Q10 bookkeeping for sharded runs)
+            // largest tile of the un-banded rect (global Q10 bookkeeping for exact sharded runs)
             if ((uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) != 0u) last_tile = (y1 - 1) * (int32_t)gx + (x1 - 1);
             if (y0 < a.band_y0) y0 = a.band_y0;
             if (y1 > a.band_y1) y1 = a.band_y1;
             if (y1 < y0) y1 = y0;
-            const uint32_t nt = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+            // rows of [y0, y1) owned by this context: y0' = first row with row % row_mod == row_rem, then every row_mod-th
+            int32_t nrows = y1 - y0;
+            if (a.row_mod > 1) {
+                y0 += ((a.row_rem - y0 % a.row_mod) + a.row_mod) % a.row_mod;
+                nrows = y0 < y1 ? (y1 - 1 - y0) / a.row_mod + 1 : 0;
+            }
+            const uint32_t nt = (uint32_t)(x1 - x0) * (uint32_t)nrows;
+            if (a.fast_mode) last_tile = nt ? (y0 + (nrows - 1) * a.row_mod) * (int32_t)gx + (x1 - 1) : -1;  // LOCAL last tile
             if (nt == 0u) break;
 
             // :198-206 everything of the record except the colour
@@ -410,7 +438,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
                     a.keys[g] = ((y * gx + x) << 16) | depth;
                     a.values[g] = id;
                 }
-                if (++x == x1) { x = x0u; ++y; }
+                if (++x == x1) { x = x0u; y += (uint32_t)a.row_mod; }
             }
         }
     }
@@ -425,7 +453,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             const uint32_t ry = j / sw, rx = j - ry * sw;
             const unsigned long long g = base + soff + j;
             if (g < (unsigned long long)a.capacity) {
-                a.keys[g] = (((sy0 + ry) * gx + sx0 + rx) << 16) | sdepth;
+                a.keys[g] = (((sy0 + ry * (uint32_t)a.row_mod) * gx + sx0 + rx) << 16) | sdepth;
                 a.values[g] = id0 + (uint32_t)src;
             }
         }

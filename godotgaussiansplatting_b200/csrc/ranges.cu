@@ -19,7 +19,8 @@ namespace gsr {
 namespace {
 
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ keys, const FrameState *__restrict__ frame,
-                                                          uint2 *__restrict__ bounds, uint32_t num_tiles, int quirks, int sharded) {
+                                                          uint2 *__restrict__ bounds, uint32_t num_tiles, int quirks, int sharded,
+                                                          int32_t *__restrict__ sync_word) {
     const uint32_t m = frame->dup_sorted;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < m; id += stride) {
@@ -32,10 +33,13 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__rest
             }
         }
         if (id == m - 1) {  // tail rules for the last key's tile
+            if (sync_word) *sync_word = (int32_t)b + 1;  // local last occupied tile (fast sharded mode: all-reduced by the host)
             if (quirks) {
                 if (b == num_tiles - 1u) {
                     if (m - 1u >= 1u) bounds[b].y = m - 1u;
-                } else if (sharded && (int32_t)b != frame->last_tile_plus1 - 1) {
+                } else if (sharded == 2) {
+                    bounds[b].y = m;  // the frame-global "last occupied tile renders nothing" rule is applied by band_fixup_kernel
+                } else if (sharded == 1 && (int32_t)b != frame->last_tile_plus1 - 1) {
                     bounds[b].y = m;
                 }
             } else {
@@ -45,11 +49,32 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__rest
     }
 }
 
+// Fast sharded mode, after the ranks have all-reduced (MAX) their local last occupied tile: the rank that owns the
+// frame's last occupied tile L blanks it when L != T-1 -- in the reference that tile never gets its range end written
+// (gsplat_boundaries.glsl:47-49) and therefore renders nothing: rgb = 0, heat-map term (1 - t) = 0, alpha = 1.
+__global__ void __launch_bounds__(256) band_fixup_kernel(const int32_t *__restrict__ global_last_plus1, float4 *__restrict__ out, int32_t width,
+                                                         int32_t height, int32_t tiles_x, int32_t num_tiles_total, int32_t band_y0, int32_t band_y1,
+                                                         int32_t row_mod, int32_t row_rem) {
+    const int32_t L = *global_last_plus1 - 1;
+    if (L < 0 || L == num_tiles_total - 1) return;
+    const int32_t ty = L / tiles_x, tx = L % tiles_x;
+    if (ty < band_y0 || ty >= band_y1 || ty % row_mod != row_rem) return;  // another rank owns it
+    const int32_t px = tx * TILE + (int32_t)(threadIdx.x & 15u), py = ty * TILE + (int32_t)(threadIdx.x >> 4);
+    if (px < width && py < height) out[(uint64_t)py * (uint64_t)width + (uint64_t)px] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+}
+
 }  // namespace
 
+int launch_band_fixup(const int32_t *global_last_plus1, float4 *out, int32_t width, int32_t height, int32_t tiles_x, int32_t num_tiles_total,
+                      int32_t band_y0, int32_t band_y1, int32_t row_mod, int32_t row_rem, cudaStream_t stream) {
+    band_fixup_kernel<<<1, 256, 0, stream>>>(global_last_plus1, out, width, height, tiles_x, num_tiles_total, band_y0, band_y1, row_mod, row_rem);
+    GSR_CUDA_TRY(cudaGetLastError());
+    return GSR_OK;
+}
+
 int launch_tile_ranges(const uint32_t *sorted_keys, const FrameState *frame, uint2 *bounds, uint32_t num_tiles, int quirks,
-                       int sharded, int grid, cudaStream_t stream) {
-    tile_ranges_kernel<<<grid, 256, 0, stream>>>(sorted_keys, frame, bounds, num_tiles, quirks, sharded);
+                       int sharded, int32_t *sync_word, int grid, cudaStream_t stream) {
+    tile_ranges_kernel<<<grid, 256, 0, stream>>>(sorted_keys, frame, bounds, num_tiles, quirks, sharded, sync_word);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

@@ -149,6 +149,16 @@ class GaussianSplattingRasterizer:
     def set_band(self, row_begin: int, row_end: int) -> None:
         _lib.check(_lib.lib().gsr_set_band(self._ctx, row_begin, row_end), "gsr_set_band")
 
+    def set_row_interleave(self, rem: int, mod: int) -> None:
+        """Own the tile rows with row % mod == rem (balanced multi-GPU sharding, fast mode; see include/gsr.h)."""
+        _lib.check(_lib.lib().gsr_set_row_interleave(self._ctx, rem, mod), "gsr_set_row_interleave")
+
+    def band_sync_word_ptr(self) -> int:
+        return int(_lib.lib().gsr_band_sync_word(self._ctx) or 0)
+
+    def band_fixup(self) -> None:
+        _lib.check(_lib.lib().gsr_band_fixup(self._ctx), "gsr_band_fixup")
+
     def cleanup_gpu(self) -> None:  # rasterizer.gd:116-120
         self.should_terminate_thread[0] = True
         if self._ctx:

@@ -114,6 +114,17 @@ GSR_API int gsr_resize(gsr_ctx *ctx, int32_t width, int32_t height);
  * rows [row_begin, row_end) only; keys keep the global tile id.  (0, tiles_y) restores the full frame. */
 GSR_API int gsr_set_band(gsr_ctx *ctx, int32_t row_begin, int32_t row_end);
 
+/* Cyclic tile-row ownership for balanced multi-GPU sharding: this context owns the tile rows with
+ * row % row_mod == row_rem (inside its band).  row_mod > 1 selects the FAST sharded mode: the projection rejects, with a
+ * conservative radius bound, splats that cannot touch an owned row, so it no longer knows the frame-global last
+ * occupied tile that the reference's tile-range quirk (gsplat_boundaries.glsl:47-49) depends on.  Instead every rank
+ * leaves its local last occupied tile + 1 in the int32 at gsr_band_sync_word(); the host all-reduces that word (MAX,
+ * in place, on the render stream) after the frame and calls gsr_band_fixup, which blanks the one affected tile on the
+ * rank that owns it.  (1, 0) restores the exact single-context behaviour. */
+GSR_API int gsr_set_row_interleave(gsr_ctx *ctx, int32_t row_rem, int32_t row_mod);
+GSR_API void *gsr_band_sync_word(gsr_ctx *ctx);
+GSR_API int gsr_band_fixup(gsr_ctx *ctx);
+
 /* Fused compositor + framebuffer gather over NVLink peer memory (replaces the NCCL gather of SURVEY 8e): the presenting
  * rank exports CUDA-IPC handles of its two frames (2 x 64 bytes); every other rank imports them, after which its
  * compositor stores its tile-row band straight into the presenting rank's memory.  In this mode gsr_render_async is

@@ -41,6 +41,26 @@ class Ctx:
     def set_band(self, y0, y1):
         _lib.check(self.L.gsr_set_band(self.h, y0, y1), "gsr_set_band")
 
+    def set_row_interleave(self, rem, mod):
+        _lib.check(self.L.gsr_set_row_interleave(self.h, rem, mod), "gsr_set_row_interleave")
+
+    def band_fixup(self):
+        _lib.check(self.L.gsr_band_fixup(self.h), "gsr_band_fixup")
+        _lib.check(self.L.gsr_sync(self.h), "gsr_sync")
+
+    def sync_word(self, value=None):
+        """Read (or overwrite: emulates the all-reduce) the int32 at gsr_band_sync_word()."""
+        rt = C.CDLL("libcudart.so")
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        _lib.check(self.L.gsr_sync(self.h), "gsr_sync")
+        ptr = self.L.gsr_band_sync_word(self.h)
+        v = C.c_int32(0 if value is None else int(value))
+        if value is None:
+            assert rt.cudaMemcpy(C.byref(v), C.c_void_p(ptr), 4, 2) == 0
+        else:
+            assert rt.cudaMemcpy(C.c_void_p(ptr), C.byref(v), 4, 1) == 0
+        return int(v.value)
+
     def keep_unsorted(self):
         _lib.check(self.L.gsr_debug_keep_unsorted(self.h, 1), "keep_unsorted")
 

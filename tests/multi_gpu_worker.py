@@ -31,7 +31,7 @@ def main():
     with Ctx(n, w, h, device=local) as c:
         _lib.check(L.gsr_set_stream(c.h, C.c_void_p(stream.cuda_stream)), "stream")
         c.upload(splat60)
-        c.set_band(*band)
+        c.set_row_interleave(rank, world)   # balanced cyclic rows + fast sharded mode
         # ---- (a) peer-memory mode ----
         handles = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -42,14 +42,17 @@ def main():
         if rank != 0:
             buf = (C.c_ubyte * 128).from_buffer_copy(handles.cpu().numpy().tobytes())
             _lib.check(L.gsr_peer_import_framebuffers(c.h, buf), "import")
-        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        class _Word:  # the library's int32 sync word as a torch tensor (all-reduced in place)
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(L.gsr_band_sync_word(c.h)), False), "version": 2}
+        word = torch.as_tensor(_Word(), device="cuda")
         hosts = [torch.zeros((h, w, 3), dtype=torch.float32).pin_memory() for _ in frames]
         for k, (_, vp, ub) in enumerate(frames):
             vpc = np.ascontiguousarray(vp, dtype=np.float32)
             _lib.check(L.gsr_render_async(c.h, vpc.ctypes.data_as(C.POINTER(C.c_float)), ub, 0.0, None), "render")
             if rank == 0:
                 _lib.check(L.gsr_stream_join(c.h), "join")
-            dist.all_reduce(flag)
+            dist.all_reduce(word, op=dist.ReduceOp.MAX)   # completion sync + frame-global last occupied tile
+            _lib.check(L.gsr_band_fixup(c.h), "fixup")
             if rank == 0:
                 _lib.check(L.gsr_readback_async(c.h, C.c_void_p(hosts[k].data_ptr()), 1), "readback")
         _lib.check(L.gsr_sync(c.h), "sync")

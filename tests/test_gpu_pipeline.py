@@ -299,3 +299,37 @@ def test_rgb_readback_equals_rgba_frame(w, h):
     assert np.all(want[..., 3] == 1.0)
     for out in hosts:
         np.testing.assert_array_equal(bits(out), bits(np.ascontiguousarray(want[..., :3])))
+
+
+@pytest.mark.parametrize("G,n,seed,boost", [(2, 20000, 19, 0.0), (3, 20000, 20, 0.0), (5, 6000, 21, 1.5), (8, 30000, 22, 0.5)])
+def test_row_interleave_fast_mode_reassembles_the_full_frame(G, n, seed, boost):
+    """Cyclic tile-row ownership + conservative early reject + all-reduced last tile + fix-up (emulated on one GPU):
+    per-rank sorted pairs are exactly the full frame's pairs of the owned rows, and the assembled frame equals the
+    oracle's frame bit for bit (including the blanked last occupied tile of the reference's Q10 quirk)."""
+    w, h = 640, 360
+    gx = (w + 15) // 16
+    splat60, vp, ub = make_scene(n, seed, w, h, frame=30, scale_boost=boost)
+    factor = 60 if boost > 1.0 else 10
+    ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=factor * n)
+    assert not ref.overflow
+    rows = (ref.keys >> 16) // gx
+    with Ctx(n, w, h, factor=factor) as c:
+        c.upload(splat60)
+        words = []
+        for rem in range(G):
+            c.set_row_interleave(rem, G)
+            c.render(vp, ub, readback=False)
+            t = c.taps()
+            sel = rows % G == rem
+            np.testing.assert_array_equal(t["keys"], ref.keys[sel])
+            np.testing.assert_array_equal(t["values"], ref.values[sel])
+            assert t["stats"].duplicates == int(sel.sum())
+            words.append(c.sync_word())
+            assert words[-1] == (int(ref.keys[sel][-1] >> 16) + 1 if sel.any() else 0)
+        assert max(words) == ref.last_tile + 1
+        for rem in range(G):  # emulate all-reduce(MAX) + fix-up on every "rank"
+            c.set_row_interleave(rem, G)
+            c.sync_word(max(words))
+            c.band_fixup()
+        img = c.copy(_lib.GSR_BUF_FRAMEBUFFER, w * h * 4, np.float32).reshape(h, w, 4)
+    np.testing.assert_array_equal(bits(img), bits(ref.rgba))
