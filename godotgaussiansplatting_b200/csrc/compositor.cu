@@ -79,6 +79,9 @@ constexpr uint32_t EXIT_TILE = 0xFFFFFFFFu;
 #define GSR_COMP_GROUP 4  // splats per software-pipelined group of the blend loop
 #endif
 constexpr int GU = GSR_COMP_GROUP;
+#ifndef GSR_COMP_WS_DEFAULT
+#define GSR_COMP_WS_DEFAULT 0
+#endif
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
@@ -87,6 +90,102 @@ __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %
 // themselves in natural order; an unfinished tile spills its per-pixel state (t, rgb of 256 pixels = 4 KB) and is
 // pushed to `queue`, where ticket num_tiles + k finds it.  Every item ends in exactly one of {tile done, tile
 // pushed}, so a CTA waiting for a queue slot either gets one or sees comp_done == num_tiles and leaves.
+struct BlendK {  // broadcast constants of det_exp() for the packed lanes
+    u64 L2E2, MAGIC2, ONE2, C6, C5, C4, C3, C2, C1;
+};
+__device__ __forceinline__ BlendK make_blend_k() {
+    BlendK k;
+    k.L2E2 = bc(0x1.715476p+0f); k.MAGIC2 = bc(12582912.0f); k.ONE2 = bc(1.0f);
+    k.C6 = bc(0x1.446c7ep-13f); k.C5 = bc(0x1.5f48c8p-10f); k.C4 = bc(0x1.3b29d8p-7f); k.C3 = bc(0x1.c6aeccp-5f);
+    k.C2 = bc(0x1.ebfbe0p-3f); k.C1 = bc(0x1.62e430p-1f);
+    return k;
+}
+
+// ---- phase A: alpha = opacity * exp(power) of GU splats (slots j .. j+GU-1 of the staged chunk) for this thread's
+//      two pixels, written stage by stage so that the GU ~25-instruction dependency chains can be interleaved (a lone
+//      warp otherwise runs this at IPC 0.23: measured 25 us per chunk for a tile that owns its SM).  No dependence on
+//      the transmittance: this part of gsplat_render.glsl:84-88 can run ahead of the sequential blend.
+__device__ __forceinline__ void phase_a(const float4 *s_a, const float4 *s_b, int j, u64 npx2, float fpy, const BlendK &K, u64 al2[GU]) {
+    float4 A[GU];
+    float bx[GU], by[GU], oy[GU];
+    u64 ox2[GU], pw2[GU], tm2[GU], e2[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) { A[u] = s_a[j + u]; const float4 b = s_b[j + u]; bx[u] = b.x; by[u] = b.y; }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
+    // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy  with q = fma(cz*oy, oy, cx*ox*ox), power = fma(-(cy*ox), oy, -0.5*q)
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = mul2(bc(bx[u]), ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
+    // exp(power): det_exp(), two lanes at a time
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], K.L2E2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        float tl, th;
+        upk(pw2[u], tl, th);
+        tl = g_min(g_max(tl, -127.0f), 128.0f);
+        th = g_min(g_max(th, -127.0f), 128.0f);
+        pw2[u] = pk(tl, th);
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) tm2[u] = add2(pw2[u], K.MAGIC2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) al2[u] = sub2(tm2[u], K.MAGIC2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(K.C6, pw2[u], K.C5);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C4);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C3);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C1);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.ONE2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        float ml, mh;
+        upk(tm2[u], ml, mh);
+        tm2[u] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
+                    __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = mul2(e2[u], tm2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) al2[u] = mul2(bc(by[u]), e2[u]);
+}
+
+// ---- phase B: the sequential part (gsplat_render.glsl:89-90).  Dead pixels take alpha = 0: the reference's loop exit ----
+__device__ __forceinline__ void phase_b(const float4 *s_b, const float *s_c, int j, const u64 al2[GU], const BlendK &K, u64 &cr2, u64 &cg2,
+                                        u64 &cb2, float &t0, float &t1) {
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        const float4 b = s_b[j + u];
+        const float cbl = s_c[j + u];
+        float al, ah;
+        upk(al2[u], al, ah);
+        al = (t0 > MIN_ALPHA) ? al : 0.0f;
+        ah = (t1 > MIN_ALPHA) ? ah : 0.0f;
+        const u64 m2 = pk(al, ah);
+        const u64 t2 = pk(t0, t1);
+        cr2 = fma2(mul2(bc(b.z), m2), t2, cr2);
+        cg2 = fma2(mul2(bc(b.w), m2), t2, cg2);
+        cb2 = fma2(mul2(bc(cbl), m2), t2, cb2);
+        upk(mul2(t2, sub2(K.ONE2, m2)), t0, t1);
+    }
+}
+
 #ifndef GSR_COMP_MIN_BLOCKS
 #define GSR_COMP_MIN_BLOCKS 4  // lets ptxas spend registers on interleaving the per-splat dependency chains
 #endif
@@ -98,9 +197,7 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
     __shared__ uint32_t s_tile, s_resume;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u64 L2E2 = bc(0x1.715476p+0f), MAGIC2 = bc(12582912.0f), ONE2 = bc(1.0f);
-    const u64 C6 = bc(0x1.446c7ep-13f), C5 = bc(0x1.5f48c8p-10f), C4 = bc(0x1.3b29d8p-7f), C3 = bc(0x1.c6aeccp-5f),
-              C2 = bc(0x1.ebfbe0p-3f), C1 = bc(0x1.62e430p-1f);
+    const BlendK K = make_blend_k();
     uint32_t staged = 0;  // SURVEY 8 symbol C, summed over the items this CTA processed (uniform across the CTA)
     unsigned long long t_start = 0;  // trace only
 
@@ -186,81 +283,9 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
             const int chunk4 = (chunk + GU - 1) & ~(GU - 1);
             for (int j = 0; j < chunk4; j += GU) {
                 if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
-                // ---- phase A: alpha = opacity * exp(power) of four splats, written stage by stage so that the four
-                //      ~25-instruction dependency chains are interleaved instruction by instruction (a lone warp
-                //      otherwise runs this loop at IPC 0.23: measured 25 us per chunk for a tile that owns its SM)
-                float4 A[GU], B[GU];
-                float CB[GU], oy[GU];
-                u64 ox2[GU], pw2[GU], tm2[GU], e2[GU], al2[GU];
-#pragma unroll
-                for (int u = 0; u < GU; ++u) { A[u] = s_a[j + u]; B[u] = s_b[j + u]; CB[u] = s_c[j + u]; }
-#pragma unroll
-                for (int u = 0; u < GU; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
-                // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy  with q = fma(cz*oy, oy, cx*ox*ox), power = fma(-(cy*ox), oy, -0.5*q)
-#pragma unroll
-                for (int u = 0; u < GU; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = mul2(bc(B[u].x), ox2[u]);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
-                // exp(power): det_exp(), two lanes at a time
-#pragma unroll
-                for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], L2E2);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) {
-                    float tl, th;
-                    upk(pw2[u], tl, th);
-                    tl = g_min(g_max(tl, -127.0f), 128.0f);
-                    th = g_min(g_max(th, -127.0f), 128.0f);
-                    pw2[u] = pk(tl, th);
-                }
-#pragma unroll
-                for (int u = 0; u < GU; ++u) tm2[u] = add2(pw2[u], MAGIC2);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) al2[u] = sub2(tm2[u], MAGIC2);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = fma2(C6, pw2[u], C5);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C4);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C3);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C2);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], C1);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], ONE2);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) {
-                    float ml, mh;
-                    upk(tm2[u], ml, mh);
-                    tm2[u] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
-                                __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
-                }
-#pragma unroll
-                for (int u = 0; u < GU; ++u) e2[u] = mul2(e2[u], tm2[u]);
-#pragma unroll
-                for (int u = 0; u < GU; ++u) al2[u] = mul2(bc(B[u].y), e2[u]);
-                // ---- phase B: the sequential part (:89-90).  Dead pixels take alpha = 0: the reference's loop exit ----
-#pragma unroll
-                for (int u = 0; u < GU; ++u) {
-                    float al, ah;
-                    upk(al2[u], al, ah);
-                    al = (t0 > MIN_ALPHA) ? al : 0.0f;
-                    ah = (t1 > MIN_ALPHA) ? ah : 0.0f;
-                    const u64 m2 = pk(al, ah);
-                    const u64 t2 = pk(t0, t1);
-                    cr2 = fma2(mul2(bc(B[u].z), m2), t2, cr2);
-                    cg2 = fma2(mul2(bc(B[u].w), m2), t2, cg2);
-                    cb2 = fma2(mul2(bc(CB[u]), m2), t2, cb2);
-                    upk(mul2(t2, sub2(ONE2, m2)), t0, t1);
-                }
+                u64 al2[GU];
+                phase_a(s_a, s_b, j, npx2, fpy, K, al2);
+                phase_b(s_b, s_c, j, al2, K, cr2, cg2, cb2, t0, t1);
             }
 
             // :97 tile-stop vote: continue only if the sum over the tile's 256 pixels of uint(t*255) exceeds 255
@@ -322,22 +347,228 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
     if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
 }
 
+// ==============================================================================================================
+// EXPERIMENTAL warp-specialised variant (GSR_COMP_WS=1; off by default).  Measured on B200 (c3): 0.77 ms vs 0.54 ms for
+// composite_kernel -- the per-4-splat hand-off through shared memory (poll, 4 x 64-bit loads, two warp syncs) costs more
+// than the instruction-level parallelism it buys, both in the saturated phase (-30 % throughput) and for a lone tile
+// (47 us vs 34 us per 512 splats).  Kept for the next round: a coarser hand-off (16+ splats) is the obvious follow-up.
+// Same tiles, same queue, same arithmetic -- but each 64-pixel group of a tile is served by
+// TWO warps: a blend warp that owns the pixels' state and an alpha warp that runs phase A ahead of it and hands the
+// packed alphas over through a shared-memory ring.  Phase A does not depend on the transmittance, so it parallelises
+// over splats; only phase B is sequential.  Of every three 4-splat groups the alpha warp computes two and the blend warp
+// one (plus all three blends): 152 vs 172 FMA-pipe operations, i.e. a lone tile advances ~1.9x faster, which is what
+// bounds the kernel's tail (and all of it when a GPU owns only a slice of the frame).
+constexpr int WS_THREADS = 256;  // warps 0-3: blend, warps 4-7: alpha; pixel group g = warp & 3
+constexpr int RING_D = 4;        // ring depth in 4-splat groups per pixel group
+
+__global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __grid_constant__ CompositeArgs p) {
+    __shared__ float4 s_a[CHUNK];
+    __shared__ float4 s_b[CHUNK];
+    __shared__ float s_c[CHUNK];
+    __shared__ u64 s_ring[4][RING_D][GU][32];
+    __shared__ uint32_t s_prod[4], s_cons[4], s_stop[4];
+    __shared__ uint32_t s_vote[4];
+    __shared__ uint32_t s_tile, s_resume;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool is_blend = warp < 4u;
+    const uint32_t g = warp & 3u;
+    const uint32_t ptid = g * 32u + lane;  // pixel-pair index 0..127 inside the tile (same mapping as composite_kernel)
+    const BlendK K = make_blend_k();
+    uint32_t staged = 0;
+    unsigned long long t_start = 0;
+
+    for (;;) {
+        if (tid == 0) {
+            const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
+            if (ticket < (uint32_t)p.num_tiles) {
+                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                s_resume = 0u;
+            } else {
+                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                volatile uint32_t *done = &p.frame->comp_done;
+                uint32_t v;
+                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (v == 0u) v = *slot;
+                s_tile = v ? v - 1u : EXIT_TILE;
+                s_resume = 1u;
+                __threadfence();
+            }
+            if (p.trace) t_start = globaltimer_ns();
+        }
+        __syncthreads();
+        const uint32_t tile_id = s_tile;
+        const bool resume = s_resume != 0u;
+        if (tile_id == EXIT_TILE) break;
+
+        const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
+        const int px0 = (int)(tx * TILE + 2u * (ptid & 7u)), py = (int)(ty * TILE + (ptid >> 3));
+        const u64 npx2 = pk(-(float)px0, -(float)(px0 + 1));
+        const float fpy = (float)py;
+
+        const uint2 bounds = p.bounds[tile_id];
+        const int32_t diff = (int32_t)(bounds.y - bounds.x);
+        const int num_splats = diff > 0 ? diff : 0;                              // :61
+        const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);  // :62
+
+        u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;
+        float t0 = 1.0f, t1 = 1.0f;
+        int i0 = 0;
+        const uint32_t rel = tile_id - (uint32_t)p.tile_begin;
+        const uint32_t local_tile = (rel / (uint32_t)(p.row_step * p.tiles_x)) * (uint32_t)p.tiles_x + rel % (uint32_t)p.tiles_x;
+        float4 *st = p.state + (uint64_t)local_tile * (2u * THREADS);
+        if (resume) {
+            if (is_blend) {
+                const float4 sa = __ldcg(st + ptid), sb = __ldcg(st + THREADS + ptid);
+                cr2 = pk(sa.x, sa.y); cg2 = pk(sa.z, sa.w); cb2 = pk(sb.x, sb.y);
+                t0 = sb.z; t1 = sb.w;
+            }
+            i0 = (int)__ldcg(p.state_chunk + local_tile);
+        }
+
+        Staged n0 = null_splat();  // 256 threads stage one record each
+        if (i0 < num_iterations && CHUNK * i0 + (int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + (uint32_t)(CHUNK * i0) + tid);
+
+        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int i_begin = i0;
+        bool finished = true;
+        for (int i = i_begin; i < num_iterations; ++i) {
+            const int sort_offset = CHUNK * i;
+            const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
+            staged += (uint32_t)chunk;
+            s_a[tid] = n0.a; s_b[tid] = n0.b; s_c[tid] = n0.c;
+            if (lane == 0) {
+                if (is_blend) { s_cons[g] = 0u; s_stop[g] = 0u; }
+                else s_prod[g] = 0u;
+            }
+            __syncthreads();
+            n0 = null_splat();
+            if (i + 1 < num_iterations && i + 1 - i_begin < quantum && sort_offset + CHUNK + (int)tid < num_splats)
+                n0 = gather(p.records, p.values, bounds.x + (uint32_t)(sort_offset + CHUNK) + tid);
+
+            const int ngroups = ((chunk + GU - 1) & ~(GU - 1)) / GU;
+            if (is_blend) {
+                uint32_t jq = 0;  // alpha-warp groups consumed so far
+                for (int k = 0; k < ngroups; ++k) {
+                    if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) {
+                        if (lane == 0) *(volatile uint32_t *)&s_stop[g] = 1u;  // tell the alpha warp to stop producing
+                        break;
+                    }
+                    u64 al2[GU];
+                    if (k % 3 == 0) {
+                        phase_a(s_a, s_b, k * GU, npx2, fpy, K, al2);
+                    } else {
+                        if (lane == 0) { while (*(volatile uint32_t *)&s_prod[g] <= jq) {} }
+                        __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < GU; ++u) al2[u] = *(volatile u64 *)&s_ring[g][jq % RING_D][u][lane];
+                        __syncwarp();
+                        ++jq;
+                        if (lane == 0) *(volatile uint32_t *)&s_cons[g] = jq;
+                    }
+                    phase_b(s_b, s_c, k * GU, al2, K, cr2, cg2, cb2, t0, t1);
+                }
+            } else {
+                uint32_t jq = 0;  // groups produced so far
+                for (int k = 0; k < ngroups; ++k) {
+                    if (k % 3 == 0) continue;
+                    uint32_t stop = 0u;
+                    if (lane == 0) {
+                        while (jq - *(volatile uint32_t *)&s_cons[g] >= (uint32_t)RING_D && *(volatile uint32_t *)&s_stop[g] == 0u) {}
+                        stop = *(volatile uint32_t *)&s_stop[g];
+                    }
+                    stop = __shfl_sync(0xffffffffu, stop, 0);
+                    if (stop) break;
+                    u64 al2[GU];
+                    phase_a(s_a, s_b, k * GU, npx2, fpy, K, al2);
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) s_ring[g][jq % RING_D][u][lane] = al2[u];
+                    __syncwarp();
+                    ++jq;
+                    if (lane == 0) { __threadfence_block(); *(volatile uint32_t *)&s_prod[g] = jq; }
+                }
+            }
+
+            // :97 tile-stop vote over the tile's 256 pixels (owned by the four blend warps)
+            if (is_blend) {
+                const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t0 * 255.0f) + (uint32_t)(t1 * 255.0f));
+                if (lane == 0) s_vote[g] = wsum;
+            }
+            __syncthreads();
+            const uint32_t shared_t = s_vote[0] + s_vote[1] + s_vote[2] + s_vote[3];
+            if (!(shared_t > 255u)) break;
+            if (i + 1 < num_iterations && i + 1 - i_begin >= quantum) {
+                finished = false;
+                i0 = i + 1;
+                break;
+            }
+        }
+
+        float r0, r1, g0, g1, b0, b1;
+        upk(cr2, r0, r1); upk(cg2, g0, g1); upk(cb2, b0, b1);
+        if (!finished) {
+            if (is_blend) {
+                __stcg(st + ptid, make_float4(r0, r1, g0, g1));
+                __stcg(st + THREADS + ptid, make_float4(b0, b1, t0, t1));
+            }
+            if (tid == 0) __stcg(p.state_chunk + local_tile, (uint32_t)i0);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t slot = atomicAdd(&p.frame->comp_tail, 1u);
+                __threadfence();
+                *(volatile uint32_t *)(p.queue + slot) = tile_id + 1u;
+            }
+        } else {
+            if (is_blend) {
+                const float hx = (float)num_splats * 5e-4f;  // :100-101
+                const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
+                if (py < p.height) {
+                    float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
+                    const float k0 = 1.0f - t0, k1 = 1.0f - t1;
+                    if (px0 < p.width)
+                        row[px0] = make_float4(r0 + h0 * k0 * p.heatmap_factor, g0 + h1 * k0 * p.heatmap_factor, b0 + h2c * k0 * p.heatmap_factor, 1.0f);
+                    if (px0 + 1 < p.width)
+                        row[px0 + 1] = make_float4(r1 + h0 * k1 * p.heatmap_factor, g1 + h1 * k1 * p.heatmap_factor, b1 + h2c * k1 * p.heatmap_factor, 1.0f);
+                }
+                if ((ptid & 15u) == 0u && tile_id == p.target_tile_id && t0 != 1.0f) {  // :105-110 pick
+                    const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
+                    const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
+                    *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
+                }
+            }
+            if (tid == 0) atomicAdd(&p.frame->comp_done, 1u);
+        }
+        if (p.trace && tid == 0) {
+            const uint32_t k = atomicAdd(p.trace_count, 1u);
+            if (k < p.trace_cap) p.trace[k] = make_ulonglong4(((unsigned long long)tile_id << 32) | smid(), t_start, globaltimer_ns(), ((unsigned long long)(uint32_t)i_begin << 32) | (uint32_t)(finished ? 1u : 0u) | ((uint32_t)num_iterations << 1));
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
+}
+
 }  // namespace
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0;
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT;
     if (!ctas_per_sm) {
         int dev = 0;
         GSR_CUDA_TRY(cudaGetDevice(&dev));
         GSR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel, THREADS, 0));
+        const char *w = getenv("GSR_COMP_WS");  // experiment knob: 1 = warp-specialised kernel, 0 = plain
+        if (w) use_ws = atoi(w) != 0;
+        if (use_ws) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_ws_kernel, WS_THREADS, 0));
+        else GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel, THREADS, 0));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         const char *e = getenv("GSR_COMP_CTAS_PER_SM");  // experiment knob
         if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
     const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
-    composite_kernel<<<grid, THREADS, 0, stream>>>(a);
+    if (use_ws) composite_ws_kernel<<<grid, WS_THREADS, 0, stream>>>(a);
+    else composite_kernel<<<grid, THREADS, 0, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
