@@ -32,6 +32,7 @@ WORKLOADS = {
     # name: (N splats, W, H, seed, orbit?)      BASELINE.json configs[1..3]
     "c2": dict(n=1_000_000, w=1920, h=1080, seed=1, orbit=False, desc="1M synthetic Gaussians, SH deg 3, 1920x1080, default camera"),
     "c3": dict(n=6_000_000, w=1920, h=1080, seed=2, orbit=True, desc="6M-splat bicycle-scale synthetic scene, 1920x1080, 360-frame orbit sweep"),
+    "c5": dict(n=0, w=0, h=0, seed=5, orbit=False, desc="radix-sort microbench: 2^20..2^28 32-bit tile|depth keys (+u32 values), device resident"),
     "c4": dict(n=10_000_000, w=3840, h=2160, seed=3, orbit=True, desc="10M synthetic splats, 3840x2160, tile-row bands + NCCL framebuffer gather"),
 }
 
@@ -69,11 +70,23 @@ def frame_params(wl, n_frames, first=0):
     return out
 
 
-def scene_chunks(wl):
-    from godotgaussiansplatting_b200.ply_file import swizzle_splats
+def raw_chunks(wl):
+    """The scene as the 62-float vertex table a .ply of it would hold, chunk by chunk."""
     from godotgaussiansplatting_b200.synthetic import synthetic_ply_chunks
-    for lo, blk in synthetic_ply_chunks(wl["n"], wl["seed"]):
+    yield from synthetic_ply_chunks(wl["n"], wl["seed"])
+
+
+def scene_chunks(wl):
+    """Host-side ingest (numpy mirror of util/ply_file.gd:44-69) of the same scene: 60-float Splat structs."""
+    from godotgaussiansplatting_b200.ply_file import swizzle_splats
+    for lo, blk in raw_chunks(wl):
         yield lo, swizzle_splats(blk, 0.0)
+
+
+def oracle_scene(wl):
+    """CPU-baseline legs only: the oracle's own restatement of the ingest (OpenMP) builds its input."""
+    from oracle import oracle as orc
+    return np.concatenate([orc.preprocess_ply(blk, 0.0) for _, blk in raw_chunks(wl)])
 
 
 class ClockSampler:
@@ -165,7 +178,7 @@ def run_reference(args, wl, rank, world):
     """--impl reference: the reference's own pipeline on the host cores (CPU restatement; see module docstring)."""
     if rank != 0:
         return
-    splat60 = np.concatenate([b for _, b in scene_chunks(wl)])
+    splat60 = oracle_scene(wl)
     frames = frame_params(wl, args.warmup + args.steps)
     # one untimed warm-up frame (page-in, thread pool), then as many of the K frames as fit in ~150 s
     _ = cpu_reference_frames(wl, splat60, frames[:1], 1e9)
@@ -185,6 +198,27 @@ def run_reference(args, wl, rank, world):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_c5(args):
+    """--workload c5: the radix-sort microbench as its own JSON line (metric Gkeys/s at the largest size)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libgsr has no CPU fallback")
+    torch.cuda.set_device(0)
+    sizes = [20, 22, 24, 26, 28]
+    res = {}
+    for lg in sizes:
+        res[f"2^{lg}"] = radix_microbench(torch, 0, 1 << lg)
+    top = res[f"2^{sizes[-1]}"]
+    peak, peak_src = measured_peak_gbs()
+    emit({"metric": "Gkeys/s", "value": top["pairs"]["gkeys_s"], "unit": "Gpairs/s (32-bit key + 32-bit value)", "n_gpus": 1, "steps": 3, "warmup": 1,
+          "ms_per_step": top["pairs"]["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+          "config": {"workload": "c5: " + WORKLOADS["c5"]["desc"], "sizes": res, "l2": "2^26 and 2^28 exceed L2; smaller sizes are L2-resident"},
+          "roofline": {"kernel": "sort_hist_kernel + 4x onesweep_kernel", "bound": "hbm", "achieved": top["pairs"]["hbm_frac_of_measured"] * peak, "peak": peak,
+                       "unit": "GB/s", "frac": top["pairs"]["hbm_frac_of_measured"], "traffic": None, "peak_source": peak_src,
+                       "algorithmic_bytes": "68 B per pair (36 B per key keys-only), SURVEY 8d"},
+          "keys_only_gkeys_s": top["keys"]["gkeys_s"], "gpu_launches": 5 * 4 * 2 * len(sizes), "e2e": None, "cpu_baseline": None})
 
 
 def radix_microbench(torch, device_index, n=1 << 26):
@@ -248,6 +282,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return
+    if args.workload == "c5":
+        if rank == 0:
+            run_c5(args)
+        return
 
     import torch
     import torch.distributed as dist
@@ -285,10 +323,10 @@ def main():
     keep_host = rank == 0 and world == 1 and not args.no_cpu_baseline
     host_chunks = []
     t_gen = time.perf_counter()
-    for lo, s60 in scene_chunks(wl):
-        rast.upload_splats(s60, lo)
+    for lo, blk in raw_chunks(wl):
+        rast.upload_ply_raw(blk, lo, 0.0)  # device-side ingest (scope row f1): exp/sigmoid/quat->cov/SH interleave on the GPU
         if keep_host:
-            host_chunks.append(s60)
+            host_chunks.append(blk)
     t_gen = time.perf_counter() - t_gen
     fb = None
     peer = world > 1 and args.mgpu == "peer"
@@ -416,7 +454,8 @@ def main():
 
     cpu_baseline = None
     if keep_host:
-        splat60 = np.concatenate(host_chunks)
+        from oracle import oracle as orc
+        splat60 = np.concatenate([orc.preprocess_ply(blk, 0.0) for blk in host_chunks])
         del host_chunks
         _ = cpu_reference_frames(wl, splat60, frames[:1], 1e9)  # warm-up
         ms, stages, threads, info = cpu_reference_frames(wl, splat60, frames[args.warmup:args.warmup + 3], 30.0)

@@ -18,7 +18,7 @@ GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES = 0x1, 0x2
 
 # every symbol include/gsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
-    "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_resize", "gsr_set_band", "gsr_set_row_interleave", "gsr_band_sync_word", "gsr_band_fixup", "gsr_render",
+    "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_upload_ply_raw", "gsr_resize", "gsr_set_band", "gsr_set_row_interleave", "gsr_band_sync_word", "gsr_band_fixup", "gsr_render",
     "gsr_render_async", "gsr_render_async_rgb", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
     "gsr_stream_join", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
     "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
@@ -69,6 +69,7 @@ def lib():
         L.gsr_destroy.argtypes = [vp]
         L.gsr_set_stream.argtypes = [vp, vp]
         L.gsr_upload_splats_aos.argtypes = [vp, fp, C.c_uint64, C.c_uint64]
+        L.gsr_upload_ply_raw.argtypes = [vp, fp, u32, C.c_uint64, C.c_uint64, C.c_float]
         L.gsr_resize.argtypes = [vp, C.c_int32, C.c_int32]
         L.gsr_set_band.argtypes = [vp, C.c_int32, C.c_int32]
         L.gsr_set_row_interleave.argtypes = [vp, C.c_int32, C.c_int32]

@@ -190,6 +190,8 @@ struct CompositeArgs {
 };
 int launch_composite(const CompositeArgs &a, cudaStream_t stream);
 
+int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
+                      cudaStream_t stream);
 int launch_pack_rgb(const float4 *rgba, float4 *rgb, uint64_t pixels, cudaStream_t stream);
 int launch_aos_to_soa(const float4 *aos, uint64_t count, float4 *soa, uint64_t plane_stride, uint64_t first, cudaStream_t stream);
 

@@ -258,6 +258,27 @@ GSR_API int gsr_upload_splats_aos(gsr_ctx *c, const float *splat60, uint64_t fir
     return GSR_OK;
 }
 
+GSR_API int gsr_upload_ply_raw(gsr_ctx *c, const float *ply, uint32_t nprops, uint64_t first, uint64_t count, float creation_time) {
+    if (!c || (!ply && count)) return GSR_ERR_INVALID;
+    if (nprops < 62 || nprops > 256) { set_last_error("gsr_upload_ply_raw: %u properties; need the 62 standard 3DGS floats (x..rot_3) first", nprops); return GSR_ERR_INVALID; }
+    if (first + count > c->max_splats) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const uint64_t staging_floats = c->staging_splats * 60ull;  // the AoS staging buffer, reused for raw vertices
+    const uint64_t per = staging_floats / nprops;
+    if (per == 0) { set_last_error("gsr_upload_ply_raw: staging buffer too small"); return GSR_ERR_INVALID; }
+    uint64_t done = 0;
+    while (done < count) {
+        const uint64_t m = (count - done) < per ? (count - done) : per;
+        GSR_CUDA_TRY(cudaMemcpyAsync(c->staging, ply + done * nprops, m * nprops * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = launch_ply_to_soa(reinterpret_cast<const float *>(c->staging), nprops, m, creation_time, c->soa, c->plane_stride, first + done, c->stream))) return rc;
+        done += m;
+    }
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (first + count > c->num_splats) c->num_splats = first + count;
+    return GSR_OK;
+}
+
 GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     if (!c || width < 1 || height < 1) { set_last_error("gsr_resize: bad size %dx%d", width, height); return GSR_ERR_INVALID; }
     const int tx = (width + TILE - 1) / TILE, ty = (height + TILE - 1) / TILE;

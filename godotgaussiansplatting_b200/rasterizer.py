@@ -95,8 +95,9 @@ class GaussianSplattingRasterizer:
         return self._clock() - self._t0
 
     # ---- init_gpu (rasterizer.gd:65-114) ----
-    def init_gpu(self, load: bool = True) -> None:
-        """load=False creates the context only; the caller then streams splats in with `upload_splats`."""
+    def init_gpu(self, load: bool = True, device_ingest: bool = False) -> None:
+        """load=False creates the context only; the caller then streams splats in with `upload_splats` / `upload_ply_raw`.
+        device_ingest=True runs the per-splat preprocessing of ply_file.gd:44-69 on the GPU instead of in numpy."""
         assert self.render_texture is not None, "An output Texture2DRD must be set!"
         L = _lib.lib()
         cfg = _lib.GsrConfig(self._device, self._flags, max(1, self.point_cloud.size), self._factor, 0)
@@ -110,6 +111,14 @@ class GaussianSplattingRasterizer:
             return
         # the reference starts a loader thread (:114); here the load runs inline, chunk by chunk
         stride = max(1, self.point_cloud.size // 1000)
+        if device_ingest:
+            table, n, i = self.point_cloud.table, self.point_cloud.size, 0
+            while i * stride < n and not self.should_terminate_thread[0]:
+                lo, hi = i * stride, min(n, (i + 1) * stride)
+                self.upload_ply_raw(table[lo:hi], lo, self.ticks())
+                i += 1
+            self._emit_loaded()
+            return
         load_gaussian_splats(self.point_cloud, stride, self._upload, self.should_terminate_thread, self.num_splats_loaded,
                              self._emit_loaded, clock=self.ticks)
 
@@ -124,6 +133,15 @@ class GaussianSplattingRasterizer:
             raise RuntimeError("init_gpu() first")
         self._upload(first, splat60)
         self.num_splats_loaded[0] = max(self.num_splats_loaded[0], first + splat60.shape[0])
+
+    def upload_ply_raw(self, table: np.ndarray, first: int = 0, creation_time: float = 0.0) -> None:
+        """Device-side ingest (scope row f1): raw (m, nprops) PLY vertices -> SoA planes, preprocessing on the GPU."""
+        if not self._ctx:
+            raise RuntimeError("init_gpu() first")
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        _lib.check(_lib.lib().gsr_upload_ply_raw(self._ctx, t.ctypes.data_as(C.POINTER(C.c_float)), t.shape[1], first, t.shape[0],
+                                                 float(creation_time)), "gsr_upload_ply_raw")
+        self.num_splats_loaded[0] = max(self.num_splats_loaded[0], first + t.shape[0])
 
     def _emit_loaded(self):
         self.is_loaded = True

@@ -107,6 +107,12 @@ GSR_API int gsr_set_stream(gsr_ctx *ctx, void *cuda_stream);
  *      May be called repeatedly with disjoint or overlapping ranges (chunked async load). ---- */
 GSR_API int gsr_upload_splats_aos(gsr_ctx *ctx, const float *splat60, uint64_t first, uint64_t count);
 
+/* Same, but from RAW PLY vertices (scope row f1): `ply` = `count` vertices of `nprops` float32 each in the standard 3DGS
+ * order (x,y,z,nx,ny,nz,f_dc_0..2,f_rest_0..44,opacity,scale_0..2,rot_0..3,...).  The per-splat preprocessing of
+ * PlyFile.load_gaussian_splats (util/ply_file.gd:44-69: exp(scale), quaternion -> R, Sigma = R S^2 R^T, sigmoid(opacity),
+ * SH re-interleave) runs on the device and writes the SoA planes directly; `creation_time` stamps the chunk (:40,47). */
+GSR_API int gsr_upload_ply_raw(gsr_ctx *ctx, const float *ply, uint32_t nprops, uint64_t first, uint64_t count, float creation_time);
+
 /* ---- texture_size setter (rasterizer.gd:26-48): reallocates tile_bounds + render_texture ---- */
 GSR_API int gsr_resize(gsr_ctx *ctx, int32_t width, int32_t height);
 

@@ -34,6 +34,10 @@ class Ctx:
         s = np.ascontiguousarray(splat60, dtype=np.float32)
         _lib.check(self.L.gsr_upload_splats_aos(self.h, s.ctypes.data_as(C.POINTER(C.c_float)), first, s.shape[0]), "upload")
 
+    def upload_ply_raw(self, table, first=0, creation_time=0.0):
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        _lib.check(self.L.gsr_upload_ply_raw(self.h, t.ctypes.data_as(C.POINTER(C.c_float)), t.shape[1], first, t.shape[0], float(creation_time)), "upload raw")
+
     def resize(self, w, h):
         _lib.check(self.L.gsr_resize(self.h, w, h), "gsr_resize")
         self.w, self.hgt = w, h

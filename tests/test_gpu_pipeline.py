@@ -333,3 +333,35 @@ def test_row_interleave_fast_mode_reassembles_the_full_frame(G, n, seed, boost):
             c.band_fixup()
         img = c.copy(_lib.GSR_BUF_FRAMEBUFFER, w * h * 4, np.float32).reshape(h, w, 4)
     np.testing.assert_array_equal(bits(img), bits(ref.rgba))
+
+
+def test_device_ply_ingest_matches_host_ingest():
+    """Scope row f1: gsr_upload_ply_raw (exp/sigmoid/quat->cov/SH interleave on the GPU) feeds the projection the same
+    splats as the host mirror + oracle restatement of util/ply_file.gd:44-69: identical keys, ranges and pixels."""
+    from godotgaussiansplatting_b200 import camera as cam
+    from godotgaussiansplatting_b200.ply_file import swizzle_splats
+    from godotgaussiansplatting_b200.synthetic import synthetic_ply_table
+    from tests.scenes import uniforms_bytes
+    n, w, h = 50000, 640, 480
+    table = synthetic_ply_table(n, 23)
+    table[:5, 54] = [np.inf, -np.inf, 40.0, -40.0, 0.0]           # opacity-logit extremes (demo.ply has +inf)
+    table[5, 58:62] = (1.0, 0.0, 0.0, 0.0)                          # identity rotation: exact zeros in the covariance
+    table = np.concatenate([table, np.zeros((n, 3), np.float32)], axis=1)  # 65 properties: extra columns are ignored
+    c0 = cam.default_camera(aspect=w / h)
+    vp = cam.pack_camera_push_constants(c0.get_camera_transform(), c0.get_camera_projection())
+    ub = uniforms_bytes(c0.global_position, 1.0, w, h, 10.0)
+    splat60 = swizzle_splats(table, 2.5)
+    np.testing.assert_array_equal(splat60.view(np.uint32), orc.preprocess_ply(table, 2.5).view(np.uint32))
+    with Ctx(n, w, h) as c:
+        c.upload(splat60)
+        a = c.render(vp, ub)
+        ta = c.taps()
+    with Ctx(n, w, h) as c:
+        for lo in range(0, n, 17000):
+            c.upload_ply_raw(table[lo:lo + 17000], first=lo, creation_time=2.5)
+        b = c.render(vp, ub)
+        tb = c.taps()
+    np.testing.assert_array_equal(ta["keys"], tb["keys"])
+    np.testing.assert_array_equal(ta["values"], tb["values"])
+    np.testing.assert_array_equal(ta["bounds"], tb["bounds"])
+    np.testing.assert_array_equal(bits(a), bits(b))
