@@ -149,6 +149,7 @@ struct ProjectionArgs {
     int32_t row_mod, row_rem;  // ... of which this context owns those with row % row_mod == row_rem (1, 0 = all)
     int32_t fast_reject;       // sharded fast mode: conservative early reject of splats that cannot touch an owned row;
                                // last_tile is then the LOCAL last emitted tile (global one by all-reduce, gsr_band_fixup)
+    int32_t sh_bulk_min;       // warps with at least this many emitting lanes fetch their SH planes with TMA bulk copies
     int32_t fast_mode;         // fast sharded mode (row_mod > 1): last_tile is the LOCAL last emitted tile
     float w_frob2;             // upper bound of |mat3(view_matrix)|_2^2 (for the early reject)
     float4 *records;         // 3 float4 per splat id (RasterizeData layout)

@@ -28,6 +28,10 @@ void set_last_error(const char *fmt, ...) {
 
 using namespace gsr;
 
+#ifndef GSR_FAST_REJECT_DEFAULT
+#define GSR_FAST_REJECT_DEFAULT 0
+#endif
+
 struct gsr_ctx {
     int device = 0;
     uint32_t flags = 0;
@@ -168,7 +172,8 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     gsr_ctx *c = new (std::nothrow) gsr_ctx();
     if (!c) return GSR_ERR_OOM;
     c->device = cfg->device;
-    c->flags = cfg->flags ? cfg->flags : GSR_FLAG_REFERENCE_QUIRKS;
+    c->flags = cfg->flags;
+    if (!(c->flags & (GSR_FLAG_REFERENCE_QUIRKS | GSR_FLAG_FIXED_RANGES))) c->flags |= GSR_FLAG_REFERENCE_QUIRKS;
     c->max_splats = cfg->max_splats;
     const uint64_t factor = cfg->dup_capacity_factor ? cfg->dup_capacity_factor : 10;  // rasterizer.gd:79
     c->capacity = c->max_splats * factor;
@@ -378,11 +383,16 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     const bool fast = c->row_mod > 1;
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
     pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
-    // The conservative early reject is exact but, measured at 4 GPUs, a net loss: under SIMT a warp saves work only if all
-    // 32 lanes reject, and sparsely surviving warps lose the TMA SH path.  Off unless GSR_FAST_REJECT=1 (experiments).
-    static const int want_reject = getenv("GSR_FAST_REJECT") ? atoi(getenv("GSR_FAST_REJECT")) : 0;
-    pa.fast_reject = (want_reject && c->row_mod >= 3) ? 1 : 0;
+    // The conservative early reject (with CTA-level compaction of the survivors) is exact, but measured slower than the
+    // plain path on B200 (G=8: 0.70 vs 0.46 ms): after compaction only ~2 of a CTA's 8 warps are busy and the kernel turns
+    // latency-bound.  Opt-in (GSR_FLAG_FAST_REJECT / GSR_FAST_REJECT=1) until the compaction domain spans several groups.
+    static const int env_reject = getenv("GSR_FAST_REJECT") ? atoi(getenv("GSR_FAST_REJECT")) : GSR_FAST_REJECT_DEFAULT;
+    pa.fast_reject = ((env_reject || (c->flags & GSR_FLAG_FAST_REJECT)) && c->row_mod >= 2) ? 1 : 0;
     pa.fast_mode = fast ? 1 : 0;
+    // full frame: 12 of 32 lanes (below that, per-lane 128-bit gathers move fewer bytes); sharded: few lanes of a warp land in
+    // this rank's rows and the latency-bound gather path was measured slower than fetching the whole 6 KB slice (0.60 vs 0.46 ms)
+    static const int bulk_env = getenv("GSR_SH_BULK_MIN") ? atoi(getenv("GSR_SH_BULK_MIN")) : 0;
+    pa.sh_bulk_min = bulk_env > 0 ? bulk_env : (fast ? 1 : 12);
     {   // |W|_2^2 <= |W^T W|_inf (largest absolute row sum of the Gram matrix); exactly 1 for a rigid camera
         float g[3][3];
         for (int i = 0; i < 3; ++i)

@@ -156,71 +156,22 @@ __device__ __forceinline__ void sh_color(const float4 *src, uint64_t stride, flo
     }
 }
 
-// One warp = 32 consecutive splats; one CTA (8 warps, 256 splats) = one link of the chained scan.  There is no CTA
-// barrier after the ticket broadcast: warps meet only through shared-memory flags.  Data movement per warp:
-//   phase 1: lane 0 issues three 512-byte TMA bulk copies (planes 0-2: position/time, covariance, opacity of the
-//            warp's 32 splats) into the warp's shared slab and everybody waits on the warp's mbarrier;
-//            cull + EWA + rect => duplicate count; the last warp of the CTA to get here publishes the CTA
-//            aggregate, before phase 2, so that successor CTAs never wait on this CTA's colour work;
-//   phase 2: if at least SH_BULK_MIN lanes emit keys, twelve more 512-byte bulk copies bring the SH planes
-//            (6 KB in flight per warp at zero register cost); otherwise the few live lanes gather their
-//            192 bytes with plain 128-bit loads (sparse view / out-of-band warps of a multi-GPU shard);
-//   then records are written, the closer's look-back resolves the CTA's base offset, and every warp emits its keys.
-constexpr int PROJ_WARPS = PROJ_THREADS / 32;
-constexpr int SH_BULK_MIN = 12;
-#ifndef GSR_PROJ_MIN_BLOCKS
-#define GSR_PROJ_MIN_BLOCKS 3
-#endif
-constexpr size_t PROJ_SLAB_BYTES = sizeof(float4) * NUM_PLANES * 32;             // 7680 B per warp
-constexpr size_t PROJ_SMEM_BYTES = PROJ_SLAB_BYTES * PROJ_WARPS;                // 61440 B per CTA
+struct LaneOut {  // what one splat contributes (valid when n > 0)
+    uint32_t n, x0, y0, w, depth;
+    int32_t last_tile;
+    float4 r0, r1;  // record words 0,1
+    float opacity, vx, vy, vz;
+};
 
-__global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_kernel(const __grid_constant__ ProjectionArgs a) {
-    extern __shared__ __align__(128) unsigned char proj_smem[];
-    __shared__ uint32_t s_bid;
-    __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS][2];
-    __shared__ uint32_t s_wtotal[PROJ_WARPS];   // duplicate count of each warp
-    __shared__ uint32_t s_count, s_ready, s_nvis;
-    __shared__ int32_t s_last;
-    __shared__ unsigned long long s_cta_base;
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    float4 *slab = reinterpret_cast<float4 *>(proj_smem + (size_t)warp * PROJ_SLAB_BYTES);  // [15][32]
-    if (lane == 0) {
-        mbar_init(&s_bar[warp][0], 1);
-        mbar_init(&s_bar[warp][1], 1);
-        fence_mbar_init();
-    }
-    if (tid == 0) {
-        s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
-        s_count = 0u; s_ready = 0u; s_nvis = 0u; s_last = -1;
-    }
-    __syncthreads();
-    const uint32_t bid = s_bid;                      // position of this CTA in the chained scan
-    const uint32_t vwarp = bid * PROJ_WARPS + warp;  // 32 consecutive splats
-    const uint32_t id0 = vwarp * 32u;
-    const uint32_t id = id0 + lane;
-
-    // ---- phase 1: TMA the warp's slices of planes 0..2 (planes are padded to a multiple of 256 splats) ----
-    if (lane == 0) {
-        mbar_expect_tx(&s_bar[warp][0], 3u * 512u);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][0]);
-    }
-
+// gsplat_projection.glsl:158-218 for one splat given its plane-0..2 values.  Returns false when the splat is culled (or,
+// in fast sharded mode, provably outside this context's rows).  QUICK: stop after the cull + conservative reject.
+template <bool QUICK>
+__device__ __forceinline__ bool project_lane(const ProjectionArgs &a, const float4 pt, const float4 ca, const float4 cb, LaneOut &o) {
     const float *V = a.vp, *P = a.vp + 16;  // X[c][r] = X[4*c + r]
     const int W = a.u.dims[0], H = a.u.dims[1];
     const uint32_t gx = (uint32_t)((W + TILE - 1) / TILE), gy = (uint32_t)((H + TILE - 1) / TILE);
     const float ms = a.u.model_scale;
-
-    uint32_t n = 0, x0u = 0, y0u = 0, wu = 0, depth = 0;
-    int32_t last_tile = -1;
-    float4 r0, r1;           // record words 0,1 (valid when n > 0)
-    float splat_opacity = 0.0f, vx = 0.0f, vy = 0.0f, vz = 0.0f;
-
-    mbar_wait(&s_bar[warp][0], 0);
-    if (id < a.num_splats) {
-        do {
-            const float4 pt = slab[lane];  // plane 0: position.xyz, time
+    o.n = 0; o.last_tile = -1;
             // :158-166 frustum cull
             const float sp0 = pt.x * ms, sp1 = pt.y * ms, sp2 = pt.z * ms;
             float view[4], clip[4];
@@ -229,16 +180,14 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
 #pragma unroll
             for (int r = 0; r < 4; ++r) clip[r] = ((P[0 + r] * view[0] + P[4 + r] * view[1]) + P[8 + r] * view[2]) + P[12 + r] * view[3];
             const float vb = clip[3] * 1.2f;
-            if (clip[0] < -vb || clip[1] < -vb || clip[2] < 0.0f || clip[0] > vb || clip[1] > vb || clip[2] > clip[3]) break;
+            if (clip[0] < -vb || clip[1] < -vb || clip[2] < 0.0f || clip[0] > vb || clip[1] > vb || clip[2] > clip[3]) return false;
 
-            const float4 ca = slab[32 + lane];  // c00 c01 c02 c11
-            const float4 cb = slab[64 + lane];  // c12 c22 opacity pad
 
             // :169-174 load-in animation
             const float splat_time = a.u.time - pt.w;
             const float tf = ease_out_cubic(g_clamp(splat_time, 0.0f, 1.0f));
             const float tfl = ease_out_cubic(g_clamp(splat_time - 0.35f, 0.0f, 1.0f));
-            splat_opacity = cb.z * tfl * tfl;
+            const float splat_opacity = cb.z * tfl * tfl;
             const float splat_scale = ms * (2.0f * (1.0f - tfl) + 1.0f * tfl);
 
             // per-frame constants (focal = dims*0.5*tan_fov_inv, +-tan_fov*1.3) are evaluated once on the host with
@@ -265,11 +214,13 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
                     int32_t lo = (int32_t)fa, hi = (int32_t)fb;
                     if (lo < a.band_y0) lo = a.band_y0;
                     if (hi > a.band_y1 - 1) hi = a.band_y1 - 1;
-                    if (hi < lo) break;
+                    if (hi < lo) return false;
                     const int32_t first = lo + ((a.row_rem - lo % a.row_mod) + a.row_mod) % a.row_mod;
-                    if (first > hi) break;
+                    if (first > hi) return false;
                 }
             }
+
+            if (QUICK) return true;  // compaction pass: cull + conservative reject only
 
             // :124-142 project_covariance
             Mat3 cov3 = {{{ca.x, ca.y, ca.z}, {ca.y, ca.w, cb.x}, {ca.z, cb.x, cb.y}}};
@@ -302,24 +253,24 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
 
             // :177-182
             const float det = cx * cz - cy * cy;
-            if (det == 0.0f) break;
+            if (det == 0.0f) return false;
             const float mid = 0.5f * (cx + cz);
             const float sq = sqrtf(g_max(0.1f, mid * mid - det));
             const float e1 = mid + 1.0f * sq, e2 = mid + -1.0f * sq;
-            if (e1 < 0.0f || e2 < 0.0f) break;
+            if (e1 < 0.0f || e2 < 0.0f) return false;
 
             // :184-185 ndc / image_pos: computed above (same operations), before the early reject
 
             // :190-194
             const float radius = det_pow(splat_opacity, 0.2f) * 2.5f * sqrtf(g_max(e1, e2));
-            if (!(fabsf(ipx) <= 3.0e38f) || !(fabsf(ipy) <= 3.0e38f) || !(radius <= 3.0e38f)) break;  // gsr spec: non-finite => culled
+            if (!(fabsf(ipx) <= 3.0e38f) || !(fabsf(ipy) <= 3.0e38f) || !(radius <= 3.0e38f)) return false;  // gsr spec: non-finite => culled
             const float fgx = (float)gx, fgy = (float)gy;
             int32_t x0 = (int32_t)g_clamp((ipx - radius) / 16.0f, 0.0f, fgx);
             int32_t y0 = (int32_t)g_clamp((ipy - radius) / 16.0f, 0.0f, fgy);
             int32_t x1 = (int32_t)g_clamp(ceilf((ipx + radius) / 16.0f), 0.0f, fgx);
             int32_t y1 = (int32_t)g_clamp(ceilf((ipy + radius) / 16.0f), 0.0f, fgy);
             // largest tile of the un-banded rect (global Q10 bookkeeping for exact sharded runs)
-            if ((uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) != 0u) last_tile = (y1 - 1) * (int32_t)gx + (x1 - 1);
+            if ((uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) != 0u) o.last_tile = (y1 - 1) * (int32_t)gx + (x1 - 1);
             if (y0 < a.band_y0) y0 = a.band_y0;
             if (y1 > a.band_y1) y1 = a.band_y1;
             if (y1 < y0) y1 = y0;
@@ -330,19 +281,128 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
                 nrows = y0 < y1 ? (y1 - 1 - y0) / a.row_mod + 1 : 0;
             }
             const uint32_t nt = (uint32_t)(x1 - x0) * (uint32_t)nrows;
-            if (a.fast_mode) last_tile = nt ? (y0 + (nrows - 1) * a.row_mod) * (int32_t)gx + (x1 - 1) : -1;  // LOCAL last tile
-            if (nt == 0u) break;
+            if (a.fast_mode) o.last_tile = nt ? (y0 + (nrows - 1) * a.row_mod) * (int32_t)gx + (x1 - 1) : -1;  // LOCAL last tile
+            if (nt == 0u) return false;
 
             // :198-206 everything of the record except the colour
             const float d0 = sp0 - a.u.camera_pos[0], d1 = sp1 - a.u.camera_pos[1], d2 = sp2 - a.u.camera_pos[2];
             const float inv_len = 1.0f / sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
-            vx = d0 * inv_len; vy = d1 * inv_len; vz = d2 * inv_len;
-            r0.x = ipx; r0.y = ipy; r0.z = sp0; r0.w = sp1;                        // image_pos, pos_xy
-            r1.x = cz / det; r1.y = -cy / det; r1.z = cx / det; r1.w = sp2;        // conic, pos_z
+            o.vx = d0 * inv_len; o.vy = d1 * inv_len; o.vz = d2 * inv_len; o.opacity = splat_opacity;
+            o.r0.x = ipx; o.r0.y = ipy; o.r0.z = sp0; o.r0.w = sp1;                        // image_pos, pos_xy
+            o.r1.x = cz / det; o.r1.y = -cy / det; o.r1.z = cx / det; o.r1.w = sp2;        // conic, pos_z
             // :218
-            depth = ((uint32_t)(ndc2 * ndc2 * ndc2 * 65535.0f)) & 0xFFFFu;
-            n = nt; x0u = (uint32_t)x0; y0u = (uint32_t)y0; wu = (uint32_t)(x1 - x0);
-        } while (false);
+            o.depth = ((uint32_t)(ndc2 * ndc2 * ndc2 * 65535.0f)) & 0xFFFFu;
+            o.n = nt; o.x0 = (uint32_t)x0; o.y0 = (uint32_t)y0; o.w = (uint32_t)(x1 - x0);
+
+    return true;
+}
+
+// One warp = 32 consecutive splats; one CTA (8 warps, 256 splats) = one link of the chained scan.  There is no CTA
+// barrier after the ticket broadcast: warps meet only through shared-memory flags.  Data movement per warp:
+//   phase 1: lane 0 issues three 512-byte TMA bulk copies (planes 0-2: position/time, covariance, opacity of the
+//            warp's 32 splats) into the warp's shared slab and everybody waits on the warp's mbarrier;
+//            cull + EWA + rect => duplicate count; the last warp of the CTA to get here publishes the CTA
+//            aggregate, before phase 2, so that successor CTAs never wait on this CTA's colour work;
+//   phase 2: if at least `sh_bulk_min` lanes emit keys, twelve more 512-byte bulk copies bring the SH planes
+//            (6 KB in flight per warp at zero register cost); otherwise the few live lanes gather their
+//            192 bytes with plain 128-bit loads (sparse view / out-of-band warps of a multi-GPU shard);
+//   then records are written, the closer's look-back resolves the CTA's base offset, and every warp emits its keys.
+constexpr int PROJ_WARPS = PROJ_THREADS / 32;
+#ifndef GSR_PROJ_MIN_BLOCKS
+#define GSR_PROJ_MIN_BLOCKS 3
+#endif
+constexpr size_t PROJ_SLAB_BYTES = sizeof(float4) * NUM_PLANES * 32;             // 7680 B per warp
+constexpr size_t PROJ_SMEM_BYTES = PROJ_SLAB_BYTES * PROJ_WARPS;                // 61440 B per CTA
+
+__global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_kernel(const __grid_constant__ ProjectionArgs a) {
+    extern __shared__ __align__(128) unsigned char proj_smem[];
+    __shared__ uint32_t s_bid;
+    __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS][2];
+    __shared__ uint32_t s_wtotal[PROJ_WARPS];   // duplicate count of each warp
+    __shared__ uint32_t s_count, s_ready, s_nvis;
+    __shared__ int32_t s_last;
+    __shared__ unsigned long long s_cta_base;
+    __shared__ uint4 s_res[PROJ_THREADS];     // compaction path: (n, x0|y0<<16, w|depth<<16, last_tile) per splat slot
+    __shared__ uint16_t s_list[PROJ_THREADS]; // compaction path: slots of the surviving splats
+    __shared__ uint32_t s_ncomp;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    float4 *slab = reinterpret_cast<float4 *>(proj_smem + (size_t)warp * PROJ_SLAB_BYTES);  // [15][32]
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_mbar_init();
+    }
+    if (tid == 0) {
+        s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
+        s_count = 0u; s_ready = 0u; s_nvis = 0u; s_last = -1; s_ncomp = 0u;
+    }
+    __syncthreads();
+    const uint32_t bid = s_bid;                      // position of this CTA in the chained scan
+    const uint32_t vwarp = bid * PROJ_WARPS + warp;  // 32 consecutive splats
+    const uint32_t id0 = vwarp * 32u;
+    const uint32_t id = id0 + lane;
+
+    // ---- phase 1: TMA the warp's slices of planes 0..2 (planes are padded to a multiple of 256 splats) ----
+    if (lane == 0) {
+        mbar_expect_tx(&s_bar[warp][0], 3u * 512u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][0]);
+    }
+
+    const uint32_t gx = (uint32_t)((a.u.dims[0] + TILE - 1) / TILE);
+
+    uint32_t n = 0, x0u = 0, y0u = 0, wu = 0, depth = 0;
+    int32_t last_tile = -1;
+    float4 r0, r1;           // record words 0,1 (valid when n > 0)
+    float splat_opacity = 0.0f, vx = 0.0f, vy = 0.0f, vz = 0.0f;
+
+    mbar_wait(&s_bar[warp][0], 0);
+    bool colour_done = false;  // compaction path: records (incl. colour) are already written
+    if (!a.fast_reject) {
+        if (id < a.num_splats) {
+            LaneOut o;
+            if (project_lane<false>(a, slab[lane], slab[32 + lane], slab[64 + lane], o) && o.n) {
+                n = o.n; x0u = o.x0; y0u = o.y0; wu = o.w; depth = o.depth;
+                r0 = o.r0; r1 = o.r1; splat_opacity = o.opacity; vx = o.vx; vy = o.vy; vz = o.vz;
+            }
+            last_tile = o.last_tile;
+        }
+    } else {
+        // ---- fast sharded mode with CTA-level compaction.  Under SIMT a warp only saves the expensive EWA / pow / SH
+        //      work if ALL its lanes are rejected, and with cyclic rows 1/G of the lanes survive in nearly every warp.
+        //      So: every lane runs the cheap cull + conservative reject, the survivors of the CTA's 256 splats are
+        //      compacted into s_list, and dense warps run the full math for them (results go back to the splat's own
+        //      slot, so scan and emit below are unchanged and the emission order stays the splat-id order).
+        bool live = false;
+        LaneOut q;
+        if (id < a.num_splats) live = project_lane<true>(a, slab[lane], slab[32 + lane], slab[64 + lane], q);
+        s_res[tid] = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
+        const uint32_t lmask = __ballot_sync(0xffffffffu, live);
+        uint32_t wbase = 0;
+        if (lane == 0 && lmask) wbase = atomicAdd(&s_ncomp, (uint32_t)__popc(lmask));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (live) s_list[wbase + __popc(lmask & ((1u << lane) - 1u))] = (uint16_t)tid;
+        __syncthreads();
+        const uint32_t nsurv = s_ncomp;
+        if (tid < nsurv) {
+            const uint32_t li = s_list[tid];
+            const float4 *sl = reinterpret_cast<const float4 *>(proj_smem + (size_t)(li >> 5) * PROJ_SLAB_BYTES);
+            const uint32_t l2 = li & 31u;
+            const uint32_t gid = bid * PROJ_THREADS + li;
+            LaneOut o;
+            if (project_lane<false>(a, sl[l2], sl[32 + l2], sl[64 + l2], o) && o.n) {
+                float col[3];
+                sh_color<false>(a.soa + 3ull * a.plane_stride + gid, a.plane_stride, o.vx, o.vy, o.vz, col);
+                float4 *rec = a.records + (uint64_t)gid * 3u;
+                rec[0] = o.r0; rec[1] = o.r1; rec[2] = make_float4(col[0], col[1], col[2], o.opacity);
+                s_res[li] = make_uint4(o.n, o.x0 | (o.y0 << 16), o.w | (o.depth << 16), (uint32_t)o.last_tile);
+            }
+        }
+        __syncthreads();
+        const uint4 r = s_res[tid];
+        n = r.x; x0u = r.y & 0xFFFFu; y0u = r.y >> 16; wu = r.z & 0xFFFFu; depth = r.z >> 16; last_tile = (int32_t)r.w;
+        colour_done = true;
     }
 
     // ---- warp scan of the duplicate counts; the warp that finishes phase 1 LAST in its CTA (the "closer") publishes
@@ -373,7 +433,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
 
     // ---- phase 2: SH planes -> colour -> record.  The closer resolves the CTA's base (decoupled look-back over the
     //      CTA aggregates) while its SH bulk copies are in flight, so the other warps rarely find `s_ready` unset ----
-    const bool bulk = nvis >= SH_BULK_MIN;
+    const bool bulk = !colour_done && nvis >= (uint32_t)a.sh_bulk_min;
     if (bulk && lane == 0) {
         mbar_expect_tx(&s_bar[warp][1], 12u * 512u);
 #pragma unroll
@@ -405,7 +465,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
             float4 *rec = a.records + (uint64_t)id * 3u;
             rec[0] = r0; rec[1] = r1; rec[2] = make_float4(col[0], col[1], col[2], splat_opacity);
         }
-    } else if (n) {
+    } else if (n && !colour_done) {
         float col[3];
         sh_color<false>(a.soa + 3ull * a.plane_stride + id, a.plane_stride, vx, vy, vz, col);
         float4 *rec = a.records + (uint64_t)id * 3u;

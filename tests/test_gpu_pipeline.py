@@ -301,8 +301,9 @@ def test_rgb_readback_equals_rgba_frame(w, h):
         np.testing.assert_array_equal(bits(out), bits(np.ascontiguousarray(want[..., :3])))
 
 
+@pytest.mark.parametrize("flags", [0, _lib.GSR_FLAG_FAST_REJECT])
 @pytest.mark.parametrize("G,n,seed,boost", [(2, 20000, 19, 0.0), (3, 20000, 20, 0.0), (5, 6000, 21, 1.5), (8, 30000, 22, 0.5)])
-def test_row_interleave_fast_mode_reassembles_the_full_frame(G, n, seed, boost):
+def test_row_interleave_fast_mode_reassembles_the_full_frame(G, n, seed, boost, flags):
     """Cyclic tile-row ownership + conservative early reject + all-reduced last tile + fix-up (emulated on one GPU):
     per-rank sorted pairs are exactly the full frame's pairs of the owned rows, and the assembled frame equals the
     oracle's frame bit for bit (including the blanked last occupied tile of the reference's Q10 quirk)."""
@@ -313,7 +314,7 @@ def test_row_interleave_fast_mode_reassembles_the_full_frame(G, n, seed, boost):
     ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=factor * n)
     assert not ref.overflow
     rows = (ref.keys >> 16) // gx
-    with Ctx(n, w, h, factor=factor) as c:
+    with Ctx(n, w, h, factor=factor, flags=flags) as c:
         c.upload(splat60)
         words = []
         for rem in range(G):
