@@ -725,6 +725,13 @@ int orc_frame(const float *splat60, int64_t n, const float *vp, const orc_unifor
 float orc_test_exp(float x) { return orc_exp(x); }
 float orc_test_pow(float x, float y) { return orc_pow(x, y); }
 float orc_test_log2(float x) { return orc_log2(x); }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

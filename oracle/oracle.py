@@ -66,6 +66,7 @@ def lib():
         L.orc_test_pow.restype = C.c_float
         L.orc_test_pow.argtypes = [C.c_float, C.c_float]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -96,6 +97,10 @@ def uniforms_from_bytes(buf) -> _Uniforms:
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
 
 
 def preprocess_ply(ply: np.ndarray, creation_time: float = 0.0) -> np.ndarray:
