@@ -553,10 +553,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT;
-    if (!ctas_per_sm) {
-        int dev = 0;
-        GSR_CUDA_TRY(cudaGetDevice(&dev));
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, cfg_dev = -1;
+    int dev = 0;
+    GSR_CUDA_TRY(cudaGetDevice(&dev));
+    if (cfg_dev != dev) {
+        cfg_dev = dev;
         GSR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const char *w = getenv("GSR_COMP_WS");  // experiment knob: 1 = warp-specialised kernel, 0 = plain
         if (w) use_ws = atoi(w) != 0;

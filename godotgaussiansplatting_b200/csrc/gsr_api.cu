@@ -28,10 +28,6 @@ void set_last_error(const char *fmt, ...) {
 
 using namespace gsr;
 
-#ifndef GSR_FAST_REJECT_DEFAULT
-#define GSR_FAST_REJECT_DEFAULT 0
-#endif
-
 struct gsr_ctx {
     int device = 0;
     uint32_t flags = 0;
@@ -383,11 +379,12 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     const bool fast = c->row_mod > 1;
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
     pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
-    // The conservative early reject (with CTA-level compaction of the survivors) is exact, but measured slower than the
-    // plain path on B200 (G=8: 0.70 vs 0.46 ms): after compaction only ~2 of a CTA's 8 warps are busy and the kernel turns
-    // latency-bound.  Opt-in (GSR_FLAG_FAST_REJECT / GSR_FAST_REJECT=1) until the compaction domain spans several groups.
-    static const int env_reject = getenv("GSR_FAST_REJECT") ? atoi(getenv("GSR_FAST_REJECT")) : GSR_FAST_REJECT_DEFAULT;
-    pa.fast_reject = ((env_reject || (c->flags & GSR_FLAG_FAST_REJECT)) && c->row_mod >= 2) ? 1 : 0;
+    // Conservative early reject + compaction of the survivors over 1024-splat CTAs (projection_sharded_kernel): exact, and
+    // measured on B200 (c3, one rank of G emulated): G=8 0.39 vs 0.46 ms, G=4 equal, G=2 slower (with two ranks nearly every
+    // splat's conservative extent touches both).  So: on by default from 6 ranks, or on request (flag / GSR_FAST_REJECT=1).
+    static const int env_reject = getenv("GSR_FAST_REJECT") ? atoi(getenv("GSR_FAST_REJECT")) : -1;
+    const bool want_reject = env_reject >= 0 ? env_reject != 0 : ((c->flags & GSR_FLAG_FAST_REJECT) != 0 || c->row_mod >= 6);
+    pa.fast_reject = (want_reject && c->row_mod >= 2) ? 1 : 0;
     pa.fast_mode = fast ? 1 : 0;
     // full frame: 12 of 32 lanes (below that, per-lane 128-bit gathers move fewer bytes); sharded: few lanes of a warp land in
     // this rank's rows and the latency-bound gather path was measured slower than fetching the whole 6 KB slice (0.60 vs 0.46 ms)

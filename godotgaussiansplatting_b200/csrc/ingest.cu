@@ -110,11 +110,7 @@ int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float c
                       cudaStream_t stream) {
     if (count == 0) return GSR_OK;
     const size_t smem = sizeof(float) * (size_t)INGEST_SPLATS * nprops;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        GSR_CUDA_TRY(cudaFuncSetAttribute(ply_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024) GSR_CUDA_TRY(cudaFuncSetAttribute(ply_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (uint32_t)((count + INGEST_SPLATS - 1) / INGEST_SPLATS);
     ply_to_soa_kernel<<<blocks, INGEST_SPLATS, smem, stream>>>(ply, nprops, count, creation_time, soa, plane_stride, first);
     GSR_CUDA_TRY(cudaGetLastError());

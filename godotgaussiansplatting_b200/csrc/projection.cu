@@ -520,6 +520,180 @@ __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_
     }
 }
 
+// ==============================================================================================================
+// Sharded variant (fast sharded mode with GSR_FLAG_FAST_REJECT): compaction domain = 1024 splats per CTA.
+// With cyclic tile rows only ~1/G of the splats can touch this rank, but under SIMT a warp pays for the expensive
+// part (EWA, pow, SH, record) unless all 32 lanes are rejected.  So the CTA (8 warps) first runs the cheap
+// cull + conservative row test for 4 x 256 consecutive splats (planes 0-2 of all of them are TMA-staged up front: 48 KB),
+// compacts the survivors, and only then runs the full math on dense warps -- with ~1024/G survivors there is enough
+// work to keep all 8 warps busy (a 256-splat domain left 2 of 8 busy and was slower than no reject at all).  Results go
+// back to the splat's own slot, so the scan and the emit see splat-id order exactly like projection_kernel.
+constexpr int SH_GROUPS = 4;
+constexpr int SH_SPLATS = SH_GROUPS * PROJ_THREADS;  // 1024 splats per CTA = one link of the chained scan
+constexpr size_t SH_SLAB_BYTES = sizeof(float4) * 3 * SH_SPLATS;  // planes 0..2 of the CTA's splats: [group][warp][plane][lane]
+
+__global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(const __grid_constant__ ProjectionArgs a) {
+    extern __shared__ __align__(128) unsigned char proj_smem[];
+    __shared__ uint4 s_res[SH_SPLATS];      // (n, x0|y0<<16, w|depth<<16, last_tile) per splat slot
+    __shared__ uint16_t s_list[SH_SPLATS];  // slots of the surviving splats
+    __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS];
+    __shared__ uint32_t s_bid, s_ncomp, s_wsum[PROJ_WARPS], s_nvis;
+    __shared__ int32_t s_last;
+    __shared__ unsigned long long s_base;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    float4 *slab = reinterpret_cast<float4 *>(proj_smem);
+    auto slab_at = [&](uint32_t slot, int plane) -> const float4 & {  // slot = group*256 + warp*32 + lane
+        return slab[((slot >> 5) * 3u + (uint32_t)plane) * 32u + (slot & 31u)];
+    };
+    if (lane == 0) { mbar_init(&s_bar[warp], 1); fence_mbar_init(); }
+    if (tid == 0) { s_bid = atomicAdd(&a.frame->proj_ticket, 1u); s_ncomp = 0u; s_nvis = 0u; s_last = -1; }
+#pragma unroll
+    for (int r = 0; r < SH_GROUPS; ++r) s_res[r * PROJ_THREADS + tid] = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const uint32_t base_id = bid * SH_SPLATS;
+    const uint32_t gx = (uint32_t)((a.u.dims[0] + TILE - 1) / TILE);
+
+    // ---- TMA: planes 0..2 of the warp's four 32-splat slices (12 x 512 B onto the warp's mbarrier) ----
+    if (lane == 0) {
+        mbar_expect_tx(&s_bar[warp], 12u * 512u);
+#pragma unroll
+        for (int g = 0; g < SH_GROUPS; ++g)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                bulk_g2s(slab + ((g * PROJ_WARPS + warp) * 3u + k) * 32u, a.soa + (uint64_t)k * a.plane_stride + base_id + g * PROJ_THREADS + warp * 32u,
+                         512u, &s_bar[warp]);
+    }
+    mbar_wait(&s_bar[warp], 0);
+
+    // ---- quick pass: cull + conservative row test, CTA-wide compaction of the survivors ----
+#pragma unroll
+    for (int g = 0; g < SH_GROUPS; ++g) {
+        const uint32_t slot = g * PROJ_THREADS + tid;
+        bool live = false;
+        LaneOut q;
+        if (base_id + slot < a.num_splats) live = project_lane<true>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), q);
+        const uint32_t lmask = __ballot_sync(0xffffffffu, live);
+        uint32_t wbase = 0;
+        if (lane == 0 && lmask) wbase = atomicAdd(&s_ncomp, (uint32_t)__popc(lmask));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (live) s_list[wbase + __popc(lmask & ((1u << lane) - 1u))] = (uint16_t)slot;
+    }
+    __syncthreads();
+
+    // ---- dense pass: full math + SH colour + record for the survivors ----
+    const uint32_t nsurv = s_ncomp;
+    for (uint32_t it = tid; it < nsurv; it += PROJ_THREADS) {
+        const uint32_t slot = s_list[it];
+        const uint32_t gid = base_id + slot;
+        LaneOut o;
+        if (project_lane<false>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), o) && o.n) {
+            float col[3];
+            sh_color<false>(a.soa + 3ull * a.plane_stride + gid, a.plane_stride, o.vx, o.vy, o.vz, col);
+            float4 *rec = a.records + (uint64_t)gid * 3u;
+            rec[0] = o.r0; rec[1] = o.r1; rec[2] = make_float4(col[0], col[1], col[2], o.opacity);
+            s_res[slot] = make_uint4(o.n, o.x0 | (o.y0 << 16), o.w | (o.depth << 16), (uint32_t)o.last_tile);
+        }
+    }
+    __syncthreads();
+
+    // ---- scan: thread t owns the four consecutive slots 4t .. 4t+3 (splat-id order) ----
+    uint4 r[SH_GROUPS];
+    uint32_t tsum = 0, tvis = 0;
+    int32_t tlast = -1;
+#pragma unroll
+    for (int j = 0; j < SH_GROUPS; ++j) {
+        r[j] = s_res[SH_GROUPS * tid + j];
+        tsum += r[j].x;
+        tvis += r[j].x != 0u;
+        tlast = tlast > (int32_t)r[j].w ? tlast : (int32_t)r[j].w;
+    }
+    const uint32_t incl = warp_incl_scan_u32(tsum, lane);
+    if (lane == 31) s_wsum[warp] = incl;
+    const uint32_t wvis = __reduce_add_sync(0xffffffffu, tvis);
+    const int32_t wlast = __reduce_max_sync(0xffffffffu, tlast);
+    if (lane == 0) {
+        if (wvis) atomicAdd(&s_nvis, wvis);
+        if (wlast >= 0) atomicMax(&s_last, wlast);
+    }
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < PROJ_WARPS; ++w) {
+        const uint32_t sw = s_wsum[w];
+        if (w < warp) woff += sw;
+        total += sw;
+    }
+    uint32_t off = woff + incl - tsum;  // exclusive offset of slot 4t inside the CTA
+
+    // ---- chained scan across CTAs ----
+    if (warp == 0) {
+        if (lane == 0) {
+            volatile unsigned long long *st = a.lookback + bid;
+            *st = (bid == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)total;
+        }
+        __syncwarp();
+        const unsigned long long cb = lookback_exclusive(a.lookback, bid, (unsigned long long)total, lane);
+        if (lane == 0) {
+            s_base = cb;
+            const uint32_t nv = s_nvis;
+            const int32_t lt = s_last;
+            if (nv) atomicAdd(&a.frame->visible, nv);
+            if (lt >= 0) atomicMax(&a.frame->last_tile_plus1, lt + 1);
+            if (bid == gridDim.x - 1) {
+                const unsigned long long m = cb + total;
+                a.frame->dup_total = m;
+                a.frame->dup_sorted = m < (unsigned long long)a.capacity ? (uint32_t)m : a.capacity;
+                a.frame->overflow = m > (unsigned long long)a.capacity ? 1u : 0u;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+
+    // ---- emit (same rules as projection_kernel) ----
+    constexpr uint32_t EMIT_SMALL = 4;
+#pragma unroll
+    for (int j = 0; j < SH_GROUPS; ++j) {
+        const uint32_t n = r[j].x, x0u = r[j].y & 0xFFFFu, y0u = r[j].y >> 16, wu = r[j].z & 0xFFFFu, depth = r[j].z >> 16;
+        const uint32_t id = base_id + SH_GROUPS * tid + j;
+        if (n != 0u && n <= EMIT_SMALL) {
+            uint32_t x = x0u, y = y0u;
+            const uint32_t x1 = x0u + wu;
+#pragma unroll
+            for (uint32_t e = 0; e < EMIT_SMALL; ++e) {
+                if (e < n) {
+                    const unsigned long long gpos = base + off + e;
+                    if (gpos < (unsigned long long)a.capacity) {
+                        a.keys[gpos] = ((y * gx + x) << 16) | depth;
+                        a.values[gpos] = id;
+                    }
+                    if (++x == x1) { x = x0u; y += (uint32_t)a.row_mod; }
+                }
+            }
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, n > EMIT_SMALL);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1u;
+            const uint32_t sn = __shfl_sync(0xffffffffu, n, src), soff = __shfl_sync(0xffffffffu, off, src);
+            const uint32_t sx0 = __shfl_sync(0xffffffffu, x0u, src), sy0 = __shfl_sync(0xffffffffu, y0u, src);
+            const uint32_t sw = __shfl_sync(0xffffffffu, wu, src), sdepth = __shfl_sync(0xffffffffu, depth, src);
+            const uint32_t sid = __shfl_sync(0xffffffffu, id, src);
+            for (uint32_t e = lane; e < sn; e += 32u) {
+                const uint32_t ry = e / sw, rx = e - ry * sw;
+                const unsigned long long gpos = base + soff + e;
+                if (gpos < (unsigned long long)a.capacity) {
+                    a.keys[gpos] = (((sy0 + ry * (uint32_t)a.row_mod) * gx + sx0 + rx) << 16) | sdepth;
+                    a.values[gpos] = sid;
+                }
+            }
+        }
+        off += n;
+    }
+}
+
 }  // namespace
 
 uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_THREADS - 1) / PROJ_THREADS; }
@@ -527,10 +701,25 @@ uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     const uint32_t blocks = projection_num_blocks(a.num_splats);
     if (blocks == 0) return GSR_OK;
-    static bool attr_set = false;  // per process; every context uses the same kernel
-    if (!attr_set) {
+    if (a.fast_reject) {  // sharded variant: 1024 splats per CTA
+        static int sh_dev = -1;
+        int d = 0;
+        GSR_CUDA_TRY(cudaGetDevice(&d));
+        if (sh_dev != d) {
+            GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
+            sh_dev = d;
+        }
+        const uint32_t sblocks = (a.num_splats + SH_SPLATS - 1) / SH_SPLATS;
+        projection_sharded_kernel<<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
+        GSR_CUDA_TRY(cudaGetLastError());
+        return GSR_OK;
+    }
+    static int attr_dev = -1;  // function attributes are per device: re-apply when the calling context's device changes
+    int dev = 0;
+    GSR_CUDA_TRY(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
         GSR_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROJ_SMEM_BYTES));
-        attr_set = true;
+        attr_dev = dev;
     }
     projection_kernel<<<blocks, PROJ_THREADS, PROJ_SMEM_BYTES, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());

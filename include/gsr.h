@@ -40,8 +40,8 @@ enum {
 /* ---- gsr_config.flags ---- */
 #define GSR_FLAG_REFERENCE_QUIRKS 0x1u /* reproduce gsplat_boundaries.glsl:47-49 tile-range quirks (Q10); default */
 #define GSR_FLAG_FIXED_RANGES     0x2u /* corrected tile ranges instead (every occupied tile gets [start,end)) */
-#define GSR_FLAG_FAST_REJECT      0x4u /* sharded (row-interleaved) contexts: conservative early reject + CTA-level compaction in the
-                                          projection (exact; experimental, currently slower than the default path) */
+#define GSR_FLAG_FAST_REJECT      0x4u /* sharded (row-interleaved) contexts: force the conservative early reject + CTA-level compaction
+                                          in the projection (exact; selected automatically from 6 ranks, where it is faster) */
 
 /* ---- gsr_debug_copy selectors (parity taps; not on the frame path) ---- */
 enum {
