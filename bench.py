@@ -33,7 +33,7 @@ WORKLOADS = {
     "c2": dict(n=1_000_000, w=1920, h=1080, seed=1, orbit=False, desc="1M synthetic Gaussians, SH deg 3, 1920x1080, default camera"),
     "c3": dict(n=6_000_000, w=1920, h=1080, seed=2, orbit=True, desc="6M-splat bicycle-scale synthetic scene, 1920x1080, 360-frame orbit sweep"),
     "c5": dict(n=0, w=0, h=0, seed=5, orbit=False, desc="radix-sort microbench: 2^20..2^28 32-bit tile|depth keys (+u32 values), device resident"),
-    "c4": dict(n=10_000_000, w=3840, h=2160, seed=3, orbit=True, desc="10M synthetic splats, 3840x2160, tile-row bands + NCCL framebuffer gather"),
+    "c4": dict(n=10_000_000, w=3840, h=2160, seed=3, orbit=True, desc="10M synthetic splats, 3840x2160 orbit (multi-GPU config of BASELINE.json; sharding named in `parallelism`)"),
 }
 
 
@@ -489,7 +489,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": fps,
             "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": N, "width": W, "height": H, "sh_degree": 3,
-                       "parallelism": "single GPU" if world == 1 else (f"cyclic tile rows x{world} (row %% {world} == rank), early-reject projection, compositor stores into the root frame over NVLink peer memory + 4-byte NCCL all-reduce" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
+                       "parallelism": "single GPU" if world == 1 else (f"cyclic tile rows x{world} (row % {world} == rank), early-reject projection, compositor stores into the root frame over NVLink peer memory + 4-byte NCCL all-reduce" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
                        "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * N / 1e6),
                        "duplicates_M": M, "visible_V": V, "staged_C": Cc, "reduced": reduced, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),
