@@ -5,12 +5,14 @@
  * bench.py's cpu_baseline / --impl reference leg may load it.  The product path
  * (godotgaussiansplatting_b200/csrc -> libgsr.so) never links, imports or calls anything here.
  *
- * PARITY STATUS: *parity unpinned by the reference's own tests* -- the reference ships no tests,
- * golden vectors or known-answer files, and cannot be executed in this environment (needs
- * Godot 4.3 + a Vulkan device).  The oracle is pinned instead by (i) a literal emulation of the
- * vendored radix-sort shaders (orc_sort_pairs_shader_emulation, checked == stable sort),
- * (ii) an independent float64 numpy transliteration of the shaders (oracle/refmath_numpy.py),
- * (iii) the SURVEY.md Appendix-B scratch statistics on resources/demo.ply (V, M, occupied tiles).
+ * PARITY STATUS: the shader path is PINNED against the reference's own shader sources, executed on the CPU
+ * (oracle/glsl_cpu -> oracle/_ref/libgsr_refshaders.so, tests/test_refshaders.py): projection records, keys,
+ * values, M, the sort, the tile ranges and -- in the uncontracted mode, orc_set_blend_contraction(0) -- the
+ * pixels are bit-identical.  The reference ships no tests, golden vectors or known-answer files and cannot be
+ * executed as a whole here (Godot 4.3 + Vulkan), so the two GDScript host functions restated below
+ * (orc_preprocess_ply, orc_pack_camera) remain "parity unpinned"; secondary evidence: a literal emulation of
+ * the radix-sort shaders, an independent float64 transliteration (oracle/refmath_numpy.py) and the SURVEY.md
+ * Appendix-B statistics on resources/demo.ply.
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  *
@@ -600,6 +602,25 @@ void orc_boundaries(const uint32_t *keys, int64_t m, int64_t T, uint32_t *bounds
     }
 }
 
+/* Q20 (found by running the shader under oracle/glsl_cpu): gsplat_boundaries.glsl:27 makes invocation 0 of
+ * workgroup 0 return before its load at :33, so the word `local[1]` that invocation id = 1 reads as its left
+ * neighbour (:36) is never written -- an uninitialised `shared` read.  With that word = G the shader does
+ * `bounds[G].y = 1` (dropped when G >= T) and `bounds[keys[1]>>16].x = 1` whenever G != keys[1]>>16, i.e. the
+ * front-most instance of the first occupied tile is lost.  orc_boundaries() above defines the word as the
+ * author evidently meant it (G = keys[0]>>16); this variant reproduces the shader for any G, stores applied
+ * in ascending invocation order (the order oracle/glsl_cpu runs them).  Reference quirks (Q10) included. */
+void orc_boundaries_uninit(const uint32_t *keys, int64_t m, int64_t T, uint32_t *bounds, uint32_t garbage) {
+    memset(bounds, 0, sizeof(uint32_t) * 2 * (size_t)T);
+    for (int64_t id = 1; id < m; ++id) {
+        uint32_t a = (id == 1) ? garbage : (keys[id - 1] >> 16), b = keys[id] >> 16;
+        if (a != b) {
+            if ((int64_t)a < T) bounds[2 * a + 1] = (uint32_t)id;
+            if ((int64_t)b < T) bounds[2 * b + 0] = (uint32_t)id;
+        }
+        if ((int64_t)b == T - 1) bounds[2 * b + 1] = (uint32_t)(m - 1); /* :47-49 */
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* a6: gsplat_render.glsl:50-111                                                               */
 /* ------------------------------------------------------------------------------------------ */
@@ -607,6 +628,10 @@ void orc_boundaries(const uint32_t *keys, int64_t m, int64_t T, uint32_t *bounds
  * written only when the reference would write it (:105-110), otherwise left untouched.
  * tile_y0/tile_y1: tile-row band to render (pixels outside the band are not touched).
  * staged_out (nullable): C = sum over tiles and consumed chunks of chunk_size (SURVEY 8 symbol C). */
+/* 1 (default): the gsr spec's five explicit contractions in the blend; 0: none (see orc_render) */
+static int g_blend_contraction = 1;
+void orc_set_blend_contraction(int on) { g_blend_contraction = on != 0; }
+
 void orc_render(const orc_record *records, const uint32_t *values, const uint32_t *bounds, int W, int H, float heatmap_factor,
                 uint32_t target_tile_id, int tile_y0, int tile_y1, float *out, float *pick, int64_t *staged_out,
                 uint32_t *tile_staged /* nullable: per-tile consumed instance count */) {
@@ -633,6 +658,20 @@ void orc_render(const orc_record *records, const uint32_t *values, const uint32_
                 for (int l = 0; l < ORC_WG; ++l) {
                     const float px = (float)(tx * ORC_TILE + (l & 15)), py = (float)(ty * ORC_TILE + (l >> 4));
                     float tt = t[l], r = col[l][0], g = col[l][1], b = col[l][2];
+                    if (!g_blend_contraction) {
+                        /* strict evaluation of :84-90, no contraction anywhere: what the reference's own shader
+                         * text gives under oracle/glsl_cpu (tests/test_refshaders.py compares bit for bit) */
+                        for (int j = 0; j < chunk && tt > MIN_ALPHA; ++j) {
+                            const orc_record *s = &records[values[bx + (uint32_t)sort_offset + (uint32_t)j]];
+                            float ox = s->image_pos[0] - px, oy = s->image_pos[1] - py;
+                            float power = -0.5f * (s->conic[0] * ox * ox + s->conic[2] * oy * oy) - s->conic[1] * ox * oy;
+                            float alpha = s->color[3] * orc_exp(power);
+                            r = r + s->color[0] * alpha * tt;
+                            g = g + s->color[1] * alpha * tt;
+                            b = b + s->color[2] * alpha * tt;
+                            tt = tt * (1.0f - alpha);
+                        }
+                    } else
                     for (int j = 0; j < chunk && tt > MIN_ALPHA; ++j) {
                         const orc_record *s = &records[values[bx + (uint32_t)sort_offset + (uint32_t)j]];
                         float ox = s->image_pos[0] - px, oy = s->image_pos[1] - py;

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference leg.  Nothing under godotgaussiansplatting_b200/ imports this.
-Parity status: unpinned by the reference's own tests (it has none); see gsr_oracle.c header.
+Parity status: the shader path is pinned against the reference's own shaders run on the CPU (oracle/refshaders.py,
+tests/test_refshaders.py); the GDScript host functions remain unpinned -- see the gsr_oracle.c header.
 """
 from __future__ import annotations
 
@@ -55,6 +56,7 @@ def lib():
         L.orc_sort_pairs.argtypes = [u32p, u32p, i64]
         L.orc_sort_pairs_shader_emulation.argtypes = [u32p, u32p, i64, i64]
         L.orc_boundaries.argtypes = [u32p, i64, i64, u32p, C.c_int, i64]
+        L.orc_boundaries_uninit.argtypes = [u32p, i64, i64, u32p, C.c_uint32]
         L.orc_render.argtypes = [C.c_void_p, u32p, u32p, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_int, C.c_int, fp, fp,
                                  C.POINTER(i64), u32p]
         L.orc_frame.restype = C.c_int
@@ -65,6 +67,7 @@ def lib():
             getattr(L, n).argtypes = [C.c_float]
         L.orc_test_pow.restype = C.c_float
         L.orc_test_pow.argtypes = [C.c_float, C.c_float]
+        L.orc_set_blend_contraction.argtypes = [C.c_int]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -101,6 +104,12 @@ def num_threads() -> int:
 
 def set_num_threads(n: int) -> None:
     lib().orc_set_num_threads(int(n))
+
+
+def set_blend_contraction(on: bool) -> None:
+    """True (default): the gsr spec (five explicit fmaf in the blend, what the CUDA compositor computes);
+    False: no contraction at all -- the evaluation oracle/glsl_cpu gives the reference's own shader text."""
+    lib().orc_set_blend_contraction(int(bool(on)))
 
 
 def preprocess_ply(ply: np.ndarray, creation_time: float = 0.0) -> np.ndarray:
@@ -170,6 +179,14 @@ def boundaries(sorted_keys, num_tiles, quirks=True, global_last_tile=-1) -> np.n
     k = np.ascontiguousarray(sorted_keys, dtype=np.uint32)
     b = np.zeros((int(num_tiles), 2), dtype=np.uint32)
     lib().orc_boundaries(_u(k), k.size, int(num_tiles), _u(b), int(bool(quirks)), int(global_last_tile))
+    return b
+
+
+def boundaries_uninit(sorted_keys, num_tiles, garbage: int) -> np.ndarray:
+    """gsplat_boundaries.glsl with the uninitialised shared word of :36 (quirk Q20) holding `garbage`."""
+    k = np.ascontiguousarray(sorted_keys, dtype=np.uint32)
+    b = np.zeros((int(num_tiles), 2), dtype=np.uint32)
+    lib().orc_boundaries_uninit(_u(k), k.size, int(num_tiles), _u(b), int(garbage) & 0xFFFFFFFF)
     return b
 
 
