@@ -93,6 +93,94 @@ def test_reference_shaders_equal_oracle_bit_for_bit(name):
     assert np.all(ref.rgba[..., 3] == 1.0)
 
 
+def check_scene(splat60, vp, ub, w, h, heat=0.0):
+    spec, strict, u = oracle_frames(splat60, vp, ub, heat)
+    first = int(spec.keys[0] >> 16) if spec.duplicates else 0
+    ref = reference_frame(splat60, vp, ub, w, h, heat, first)
+    assert_stages_equal(ref, spec, splat60, vp, u)
+    np.testing.assert_array_equal(bits(ref.rgba), bits(strict.rgba))
+    assert np.abs(ref.rgba - spec.rgba).max() <= RGBA_TOL
+    return ref, spec
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (15, 15), (16, 16), (17, 17), (31, 33), (257, 1), (640, 16)])
+def test_ragged_resolutions(w, h):
+    """Partial tiles: off-image invocations still vote in the tile-stop rule (Q9/Q17) and imageStore drops their texels."""
+    splat60, vp, ub = make_scene(3000, 50, w, h, scale_boost=1.0)
+    check_scene(splat60, vp, ub, w, h)
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 257])
+def test_splat_counts_around_subgroup_and_workgroup_sizes(n):
+    splat60, vp, ub = make_scene(n, 60 + n, 320, 240, scale_boost=-1.5)   # capacity is the static 10 n (Q12): keep M below it
+    check_scene(splat60, vp, ub, 320, 240)
+
+
+def test_one_splat_covering_every_tile_hits_the_last_grid_tile_rule():
+    """A splat whose rect is the whole grid: the last occupied tile IS tile T-1, so gsplat_boundaries.glsl:47-49 stores
+    M-1 as its end (Q10: the final instance of the last grid tile is dropped)."""
+    w, h, n = 640, 480, 200                       # cap = 10 n = 2000 >= the 1200 tiles
+    splat60, vp, ub = make_scene(n, 70, w, h)
+    splat60[:, 0:3] = (0.0, 0.0, 2.5)
+    splat60[:, 4:10] = 0.0
+    splat60[0, 4], splat60[0, 7], splat60[0, 9] = 4.0, 4.0, 4.0
+    splat60[1:, 4], splat60[1:, 7], splat60[1:, 9] = 1e-6, 1e-6, 1e-6
+    splat60[:, 10] = 0.5
+    ref, spec = check_scene(splat60, vp, ub, w, h)
+    T = ref.bounds.shape[0]
+    assert spec.duplicates >= T and int(ref.keys[-1] >> 16) == T - 1
+    assert ref.bounds[T - 1, 1] == spec.duplicates - 1
+
+
+def test_everything_culled():
+    """M = 0: the sort runs on one empty partition, no range is written, the frame is black with alpha 1."""
+    w, h, n = 160, 96, 500
+    splat60, vp, ub = make_scene(n, 90, w, h)
+    splat60[:, 2] = -np.abs(splat60[:, 2]) - 50.0     # behind the camera / outside the frustum
+    spec, _, u = oracle_frames(splat60, vp, ub, 0.0)
+    if spec.duplicates:                                  # the camera looks down the other axis: flip
+        splat60[:, 2] = -splat60[:, 2]
+        spec, _, u = oracle_frames(splat60, vp, ub, 0.0)
+    assert spec.duplicates == 0
+    ref = reference_frame(splat60, vp, ub, w, h, 0.0, 0)
+    assert ref.duplicates == 0 and not ref.bounds.any()
+    np.testing.assert_array_equal(bits(ref.rgba), bits(spec.rgba))
+    assert not ref.rgba[..., :3].any() and np.all(ref.rgba[..., 3] == 1.0)
+
+
+def test_degenerate_splats():
+    """opacity 0 (pow(0, .2) = 0 -> radius 0), zero covariance (only the +0.3 dilation), opacity logit extremes."""
+    n, w, h = 2000, 320, 240
+    splat60, vp, ub = make_scene(n, 80, w, h, scale_boost=1.0)
+    splat60[8, 10] = 0.0
+    splat60[9, 4:10] = 0.0
+    splat60[10, 10] = 1.0
+    splat60[11, 10] = 1e-30
+    ref, spec = check_scene(splat60, vp, ub, w, h)
+    assert (ref.values == 8).sum() <= 1          # radius 0 still rounds out to the one tile under the centre
+
+
+REF_PLY = "/root/reference/resources/demo.ply"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_PLY), reason="reference tree not mounted (GPU box)")
+def test_reference_demo_asset_through_the_reference_shaders():
+    """The reference's own demo.ply, 640x480, default camera: every stage of the shaders == the oracle (271 123 splats,
+    M = 428 272, Q10 fires on tile 1198 -- SURVEY Appendix B)."""
+    from godotgaussiansplatting_b200 import camera as cam
+    from godotgaussiansplatting_b200.ply_file import PlyFile
+
+    ply = PlyFile(REF_PLY)
+    s = orc.preprocess_ply(ply.table, 0.0)
+    c = cam.default_camera(aspect=640 / 480)
+    vp = cam.pack_camera_push_constants(c.get_camera_transform(), c.get_camera_projection())
+    from tests.scenes import uniforms_bytes
+    ub = uniforms_bytes([0.0, 0.0, 0.0], 1.0, 640, 480, 10.0)
+    ref, spec = check_scene(s, vp, ub, 640, 480)
+    assert ref.duplicates == 428272 and spec.visible == 226063
+    assert ref.bounds[1198, 1] == 0          # Q10: the last occupied tile never gets its end
+
+
 def test_boundaries_uninitialised_shared_word():
     """Q20: invocation 0 of workgroup 0 returns before storing local[1]; invocation 1 reads it as its left neighbour."""
     splat60, vp, ub, w, h, heat = build("orbit_ragged_size")
