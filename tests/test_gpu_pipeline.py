@@ -234,7 +234,7 @@ def test_pipelined_readback_matches_sync_render():
 
 
 def test_golden_demo_subset_on_gpu():
-    """Real data: 8216 splats of the reference's demo.ply (tests/golden/demo_subset.npz, minted by the oracle)."""
+    """Real data: 8216 splats of the reference's demo.ply (tests/golden/demo_subset.npz: oracle outputs + the reference shaders' own outputs)."""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "demo_subset.npz"))
     w, h = int(g["width"]), int(g["height"])
@@ -248,6 +248,11 @@ def test_golden_demo_subset_on_gpu():
     np.testing.assert_array_equal(t["bounds"], g["bounds"])
     assert np.abs(img - g["rgba"]).max() <= RGBA_TOL
     np.testing.assert_array_equal(bits(img), bits(g["rgba"]))
+    # ref_*: the same frame minted by the reference's own shaders executed on the CPU (tests/golden/make_golden.py)
+    np.testing.assert_array_equal(t["keys"], g["ref_keys"])
+    np.testing.assert_array_equal(t["values"], g["ref_values"])
+    np.testing.assert_array_equal(t["bounds"], g["ref_bounds"])
+    assert np.abs(img - g["ref_rgba"]).max() <= RGBA_TOL
 
 
 def test_mirror_class_end_to_end():

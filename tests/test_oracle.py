@@ -200,3 +200,15 @@ def test_golden_demo_subset_fixture():
     np.testing.assert_array_equal(fr.values, g["values"])
     np.testing.assert_array_equal(fr.bounds, g["bounds"])
     np.testing.assert_array_equal(fr.rgba.view(np.uint32), g["rgba"].view(np.uint32))
+    # ref_*: minted by the reference's own shaders executed on the CPU (oracle/refshaders.py)
+    assert fr.duplicates == int(g["ref_duplicates"])
+    np.testing.assert_array_equal(fr.keys, g["ref_keys"])
+    np.testing.assert_array_equal(fr.values, g["ref_values"])
+    np.testing.assert_array_equal(fr.bounds, g["ref_bounds"])
+    assert np.abs(fr.rgba - g["ref_rgba"]).max() <= 1e-4
+    orc.set_blend_contraction(False)
+    try:
+        strict = orc.frame(s, g["vp"], orc.uniforms_from_bytes(g["uniforms"]))
+    finally:
+        orc.set_blend_contraction(True)
+    np.testing.assert_array_equal(strict.rgba.view(np.uint32), g["ref_rgba"].view(np.uint32))
