@@ -2,7 +2,7 @@
  * gsr.h -- C-ABI of libgsr.so: the B200-native (sm_100a) forward 3D-Gaussian-splatting rasterizer that
  * replaces the body of 2Retr0/GodotGaussianSplatting's `GaussianSplattingRasterizer`
  * (util/gaussian_splatting_rasterizer.gd) plus the six compute shaders it dispatches
- * (resources/shaders/compute/*.glsl) and the RenderingDevice wrapper (util/render_context.gd).
+ * (the .glsl files of resources/shaders/compute) and the RenderingDevice wrapper (util/render_context.gd).
  *
  * The reference has no native/FFI boundary of its own: its "plugin API" is the GDScript class.  Each
  * entry point below cites the reference interface it replaces (paths relative to the reference root).

@@ -2,7 +2,7 @@
  * glsl_emu.hpp -- a small CPU execution environment for Vulkan-GLSL compute shaders.
  *
  * TEST INFRASTRUCTURE (part of oracle/).  It exists so that the reference's OWN shader sources
- * (/root/reference/resources/shaders/compute/*.glsl) can be executed in the build container:
+ * (the .glsl files under /root/reference/resources/shaders/compute) can be executed in the build container:
  * oracle/glsl_cpu/translate.py turns each .glsl file -- read where it lies, never copied into this
  * repository -- into one C++ translation unit whose body is the shader text (declarations rewrapped,
  * expressions untouched), compiled against this header into oracle/_ref/libgsr_refshaders.so.
