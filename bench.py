@@ -205,6 +205,7 @@ def run_reference(args, wl, rank, world):
     ms, stages, threads, info = cpu_reference_frames(wl, splat60, frames[args.warmup::stride][:args.steps], 150.0)
     mean_ms = float(np.mean(ms))
     value = wl["n"] / 1e6 * 1000.0 / mean_ms
+    ref_shaders = reference_shaders_sample(wl, splat60, frames[args.warmup])
     sample = f"{len(ms)} of {args.steps} orbit frames timed in full (all {wl['n']} splats, {wl['w']}x{wl['h']}); CPU restatement of the reference pipeline (Godot/lavapipe unavailable)"
     line = {
         "impl": "reference", "metric": "Msplats/s", "value": value, "unit": "Msplats/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -212,11 +213,38 @@ def run_reference(args, wl, rank, world):
         "dtype": "f32", "data": "synthetic", "fps": 1000.0 / mean_ms,
         "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": wl["n"], "width": wl["w"], "height": wl["h"], "parallelism": "host threads"},
         "cpu_baseline": {"value": value, "unit": "Msplats/s", "cores": threads, "kind": "port", "sample": sample,
-                         "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}, **info},
+                         "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}, **info,
+                         "reference_shaders": ref_shaders},
         "e2e": {"value": value, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def reference_shaders_sample(wl, splat60, frame, every=4):
+    """The reference's OWN shaders (oracle/_ref: the six .glsl files compiled for the CPU, workgroups emulated as fibers on
+    one thread) timed on a bounded sample -- every 4th splat of one frame of the workload.  Reported beside the port, not
+    instead of it: the port (OpenMP, all cores) is the faster, i.e. the more demanding, CPU baseline and stays `value`."""
+    try:
+        from oracle import oracle as orc
+        from oracle import refshaders
+        if not refshaders.available():
+            return {"unavailable": "oracle/_ref not built (no /root/reference in this container and no prebuilt libraries)"}
+        sub = np.ascontiguousarray(splat60[::every])
+        vp, ub = frame
+        spec = orc.frame(sub, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+        refshaders.set_shared_fill(int(spec.keys[0] >> 16) if spec.duplicates else 0)
+        pipe = refshaders.ReferencePipeline(sub, wl["w"], wl["h"])
+        t0 = time.perf_counter()
+        rf = pipe.rasterize(vp, ub)
+        dt = time.perf_counter() - t0
+        same = bool(rf.duplicates == spec.duplicates and np.array_equal(rf.keys, spec.keys) and np.array_equal(rf.bounds, spec.bounds))
+        return {"value": sub.shape[0] / 1e6 / dt, "unit": "Msplats/s", "cores": 1, "kind": "reference", "seconds": dt,
+                "sample": f"every {every}th splat ({sub.shape[0]}) of one {wl['w']}x{wl['h']} frame through the reference's six compute "
+                          "shaders compiled for the CPU (oracle/glsl_cpu: fibers emulate the GPU workgroups; a correctness pin, not a tuned CPU path)",
+                "keys_and_ranges_identical_to_port": same, "max_abs_rgba_vs_port": float(np.abs(rf.rgba - spec.rgba).max())}
+    except Exception as e:  # the extra measurement must never break the arm
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def run_c5(args):
