@@ -244,7 +244,7 @@ GSR_API int gsr_set_stream(gsr_ctx *c, void *cuda_stream) {
 
 GSR_API int gsr_upload_splats_aos(gsr_ctx *c, const float *splat60, uint64_t first, uint64_t count) {
     if (!c || (!splat60 && count)) return GSR_ERR_INVALID;
-    if (first + count > c->max_splats) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
+    if (count > c->max_splats || first > c->max_splats - count) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
     int rc = use_device(c->device);
     if (rc) return rc;
     uint64_t done = 0;
@@ -262,7 +262,7 @@ GSR_API int gsr_upload_splats_aos(gsr_ctx *c, const float *splat60, uint64_t fir
 GSR_API int gsr_upload_ply_raw(gsr_ctx *c, const float *ply, uint32_t nprops, uint64_t first, uint64_t count, float creation_time) {
     if (!c || (!ply && count)) return GSR_ERR_INVALID;
     if (nprops < 62 || nprops > 256) { set_last_error("gsr_upload_ply_raw: %u properties; need the 62 standard 3DGS floats (x..rot_3) first", nprops); return GSR_ERR_INVALID; }
-    if (first + count > c->max_splats) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
+    if (count > c->max_splats || first > c->max_splats - count) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
     int rc = use_device(c->device);
     if (rc) return rc;
     const uint64_t staging_floats = c->staging_splats * 60ull;  // the AoS staging buffer, reused for raw vertices
@@ -290,6 +290,7 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     int rc = use_device(c->device);
     if (rc) return rc;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->width = c->height = c->tiles_x = c->tiles_y = 0;  // a failure below leaves the context in the "before gsr_resize" state
     cudaFree(c->bounds); c->bounds = nullptr;
     cudaFree(c->comp_state); c->comp_state = nullptr;
     cudaFree(c->comp_chunk); c->comp_chunk = nullptr;
@@ -587,6 +588,7 @@ GSR_API int gsr_set_framebuffer_external(gsr_ctx *c, void *device_ptr) {
 GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float out_xyzn[4]) {
     if (!c || !out_xyzn) return GSR_ERR_INVALID;
     if (c->width == 0) { set_last_error("gsr_pick before gsr_resize"); return GSR_ERR_STATE; }
+    if (c->frame_counter == 0 || !c->fb_last) { set_last_error("gsr_pick before the first gsr_render at this size"); return GSR_ERR_STATE; }
     int rc = use_device(c->device);
     if (rc) return rc;
     const uint32_t T = (uint32_t)(c->tiles_x * c->tiles_y);

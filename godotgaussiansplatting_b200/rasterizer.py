@@ -235,7 +235,10 @@ class GaussianSplattingRasterizer:
         tile = (int(screen_position[0] * s) // TILE_SIZE, int(screen_position[1] * s) // TILE_SIZE)
         tile_id = tile[1] * self.tile_dims[0] + tile[0]
         out = (C.c_float * 4)()
-        _lib.check(_lib.lib().gsr_pick(self._ctx, tile_id & 0xFFFFFFFF, float(self.should_enable_heatmap[0]), out), "gsr_pick")
+        rc = _lib.lib().gsr_pick(self._ctx, tile_id & 0xFFFFFFFF, float(self.should_enable_heatmap[0]), out)
+        if rc == _lib.GSR_ERR_STATE:   # no frame rasterized yet: the reference reads its zero-initialised buffer -> Vector3.INF
+            return VECTOR3_INF.copy()
+        _lib.check(rc, "gsr_pick")
         if out[3] == 0:
             return VECTOR3_INF.copy()
         v = np.array([-out[0], -out[1], out[2]], dtype=np.float32)

@@ -178,7 +178,8 @@ GSR_API int gsr_set_framebuffer_external(gsr_ctx *ctx, void *device_ptr);
 
 /* ---- get_splat_position() (rasterizer.gd:162-171): re-dispatches the compositor for `tile_id` and reads the
  *      16-byte tile_splat_pos buffer (gsplat_render.glsl:33-36,105-110).  out_xyzn = splat_pos.xyz,
- *      num_tile_splats -- persistent across calls exactly like the reference's storage buffer. ---- */
+ *      num_tile_splats -- persistent across calls exactly like the reference's storage buffer.
+ *      GSR_ERR_STATE before the first gsr_render at the current size (no tile ranges exist yet). ---- */
 GSR_API int gsr_pick(gsr_ctx *ctx, uint32_t tile_id, float heatmap_factor, float out_xyzn[4]);
 
 /* ---- update_debug_info() (main.gd:93-119): M, overflow, per-stage GPU ms.  Synchronises the stream. ---- */

@@ -77,6 +77,9 @@ def test_tile_id_limit_and_argument_errors():
         s = np.zeros((10, 60), dtype=np.float32)
         fp = s.ctypes.data_as(C.POINTER(C.c_float))
         assert L.gsr_upload_splats_aos(c.h, fp, 95, 10) == _lib.GSR_ERR_INVALID      # past max_splats
+        assert L.gsr_upload_splats_aos(c.h, fp, 2**64 - 1, 2) == _lib.GSR_ERR_INVALID  # first + count wraps around
+        out4 = (C.c_float * 4)()
+        assert L.gsr_pick(c.h, 0, 0.0, out4) == _lib.GSR_ERR_STATE                    # no frame rendered at this size yet
         assert L.gsr_upload_ply_raw(c.h, fp, 61, 0, 5, 0.0) == _lib.GSR_ERR_INVALID   # fewer than the 62 standard properties
         vp = np.zeros(32, dtype=np.float32)
         ub = bytearray(32)
