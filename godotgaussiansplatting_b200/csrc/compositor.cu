@@ -105,6 +105,10 @@ __device__ __forceinline__ BlendK make_blend_k() {
 //      two pixels, written stage by stage so that the GU ~25-instruction dependency chains can be interleaved (a lone
 //      warp otherwise runs this at IPC 0.23: measured 25 us per chunk for a tile that owns its SM).  No dependence on
 //      the transmittance: this part of gsplat_render.glsl:84-88 can run ahead of the sequential blend.
+//      HWEXP (experiment, GSR_COMP_HWEXP=1): exp() through the SFU (MUFU.EX2 on the XU pipe) instead of the det_exp()
+//      polynomial: 10 of the 28 FMA-pipe operations per splat and pixel pair disappear, but the result is no longer
+//      bit-reproducible on a CPU (pixels within 1e-4 except where a `t > 1/255` exit or a tile-stop vote flips).
+template <bool HWEXP>
 __device__ __forceinline__ void phase_a(const float4 *s_a, const float4 *s_b, int j, u64 npx2, float fpy, const BlendK &K, u64 al2[GU]) {
     float4 A[GU];
     float bx[GU], by[GU], oy[GU];
@@ -127,6 +131,17 @@ __device__ __forceinline__ void phase_a(const float4 *s_a, const float4 *s_b, in
     // exp(power): det_exp(), two lanes at a time
 #pragma unroll
     for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], K.L2E2);
+    if (HWEXP) {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float tl, th;
+            upk(pw2[u], tl, th);
+            asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(tl));  // one MUFU.EX2; results below 2^-126 flush to 0
+            asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(th));
+            al2[u] = mul2(bc(by[u]), pk(tl, th));
+        }
+        return;
+    }
 #pragma unroll
     for (int u = 0; u < GU; ++u) {
         float tl, th;
@@ -189,6 +204,7 @@ __device__ __forceinline__ void phase_b(const float4 *s_b, const float *s_c, int
 #ifndef GSR_COMP_MIN_BLOCKS
 #define GSR_COMP_MIN_BLOCKS 4  // lets ptxas spend registers on interleaving the per-splat dependency chains
 #endif
+template <bool HWEXP>
 __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel(const __grid_constant__ CompositeArgs p) {
     __shared__ float4 s_a[CHUNK];
     __shared__ float4 s_b[CHUNK];
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
             for (int j = 0; j < chunk4; j += GU) {
                 if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
                 u64 al2[GU];
-                phase_a(s_a, s_b, j, npx2, fpy, K, al2);
+                phase_a<HWEXP>(s_a, s_b, j, npx2, fpy, K, al2);
                 phase_b(s_b, s_c, j, al2, K, cr2, cg2, cb2, t0, t1);
             }
 
@@ -457,7 +473,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
                     }
                     u64 al2[GU];
                     if (k % 3 == 0) {
-                        phase_a(s_a, s_b, k * GU, npx2, fpy, K, al2);
+                        phase_a<false>(s_a, s_b, k * GU, npx2, fpy, K, al2);
                     } else {
                         if (lane == 0) { while (*(volatile uint32_t *)&s_prod[g] <= jq) {} }
                         __syncwarp();
@@ -481,7 +497,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
                     stop = __shfl_sync(0xffffffffu, stop, 0);
                     if (stop) break;
                     u64 al2[GU];
-                    phase_a(s_a, s_b, k * GU, npx2, fpy, K, al2);
+                    phase_a<false>(s_a, s_b, k * GU, npx2, fpy, K, al2);
 #pragma unroll
                     for (int u = 0; u < GU; ++u) s_ring[g][jq % RING_D][u][lane] = al2[u];
                     __syncwarp();
@@ -553,7 +569,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, cfg_dev = -1;
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, cfg_dev = -1;
     int dev = 0;
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     if (cfg_dev != dev) {
@@ -561,15 +577,19 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         GSR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const char *w = getenv("GSR_COMP_WS");  // experiment knob: 1 = warp-specialised kernel, 0 = plain
         if (w) use_ws = atoi(w) != 0;
+        const char *h = getenv("GSR_COMP_HWEXP");  // experiment knob: 1 = exp() on the SFU (not bit-reproducible; see phase_a)
+        use_hwexp = (h && atoi(h) != 0) ? 1 : 0;
         if (use_ws) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_ws_kernel, WS_THREADS, 0));
-        else GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel, THREADS, 0));
+        else if (use_hwexp) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel<true>, THREADS, 0));
+        else GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel<false>, THREADS, 0));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         const char *e = getenv("GSR_COMP_CTAS_PER_SM");  // experiment knob
         if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
     const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
     if (use_ws) composite_ws_kernel<<<grid, WS_THREADS, 0, stream>>>(a);
-    else composite_kernel<<<grid, THREADS, 0, stream>>>(a);
+    else if (use_hwexp) composite_kernel<true><<<grid, THREADS, 0, stream>>>(a);
+    else composite_kernel<false><<<grid, THREADS, 0, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
