@@ -160,6 +160,89 @@ def test_degenerate_splats():
     assert (ref.values == 8).sum() <= 1          # radius 0 still rounds out to the one tile under the centre
 
 
+def adversarial_splats(n, seed, w, h, frame):
+    """Random splats far outside the synthetic generator's envelope: positions over four decades (also behind the camera),
+    scales from 1e-5 to 6 with random orientation, opacities at the ends of [0, 1], every phase of the load-in animation,
+    large SH coefficients."""
+    rng = np.random.default_rng(seed)
+    splat60, vp, ub = make_scene(n, seed, w, h, frame=frame)
+    splat60[:, 0:3] = rng.normal(0, 1, (n, 3)).astype(np.float32) * rng.choice([0.1, 1, 3, 10, 100], size=(n, 1)).astype(np.float32)
+    splat60[:, 3] = rng.choice([0.0, 9.2, 9.7, 9.99, 10.0, 12.0], size=n).astype(np.float32)     # uniforms.time is 10
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    qw, qx, qy, qz = q.T
+    R = np.stack([1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                  2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                  2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)], axis=1).reshape(n, 3, 3)
+    sc = np.exp(rng.uniform(np.log(1e-5), np.log(6), (n, 3)))
+    S = np.einsum("nij,nj,nkj->nik", R, sc ** 2, R).astype(np.float32)
+    splat60[:, 4], splat60[:, 5], splat60[:, 6] = S[:, 0, 0], S[:, 0, 1], S[:, 0, 2]
+    splat60[:, 7], splat60[:, 8], splat60[:, 9] = S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]
+    splat60[:, 10] = rng.choice([0.0, 1e-6, 0.01, 0.5, 0.999, 1.0], size=n).astype(np.float32)
+    splat60[:, 12:60] = rng.normal(0, 1.5, (n, 48)).astype(np.float32)
+    return splat60, vp, ub
+
+
+@pytest.mark.parametrize("seed,frame", [(123, 11), (321, 200)])
+def test_projection_fuzz(seed, frame):
+    """gsplat_projection.glsl alone on adversarial splats: M, every emitted pair and every record bit for bit."""
+    n, w, h = 100000, 640, 360
+    splat60, vp, ub = adversarial_splats(n, seed, w, h, frame)
+    splat60[30000:, 0:3] = 1e9        # 70 000 culled fillers: the reference sizes the pair buffers as 10 x point count (Q12)
+    u = orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8))
+    pr = orc.project(splat60, vp, u, cap=10 * n)
+    assert 0 < pr.duplicates <= 10 * n and pr.visible > 500
+    P = refshaders.ReferencePipeline(splat60, w, h)
+    P.uniforms[:] = np.frombuffer(bytes(ub), dtype=np.float32)
+    P.histogram[: 1 + 4 * refshaders.RADIX] = 0
+    P._dispatch("gsplat_projection", ((n + 255) // 256, 1, 1),
+                [P.splats, P.culled, P.histogram, P.sort_keys, P.sort_values, P.grid_dims, P.uniforms], np.asarray(vp, dtype=np.float32).tobytes())
+    assert int(P.histogram[0]) == pr.duplicates
+    np.testing.assert_array_equal(P.sort_keys[: pr.duplicates], pr.keys)
+    np.testing.assert_array_equal(P.sort_values[: pr.duplicates], pr.values)
+    vis = np.unique(pr.values)
+    for f in orc.RECORD_DTYPE.names:
+        np.testing.assert_array_equal(bits(P.culled[f][vis]), bits(pr.records[f][vis]), err_msg=f"record field {f}")
+
+
+def test_render_fuzz():
+    """gsplat_render.glsl alone on synthetic records and ranges: indefinite conics (positive power, alpha > 1, negative
+    transmittance -- Q8: nothing is clamped), ranges that run past their chunk, the heat-map term."""
+    rng = np.random.default_rng(77)
+    w, h, nrec = 96, 64, 5000
+    gx, gy = (w + 15) // 16, (h + 15) // 16
+    T = gx * gy
+    rec = np.zeros(nrec, dtype=orc.RECORD_DTYPE)
+    rec["image_pos"] = rng.uniform(-20, [w + 20, h + 20], (nrec, 2)).astype(np.float32)
+    rec["conic"] = np.stack([rng.uniform(-0.002, 0.05, nrec), rng.uniform(-0.03, 0.03, nrec), rng.uniform(-0.002, 0.05, nrec)], axis=1).astype(np.float32)
+    rec["color"] = np.concatenate([rng.uniform(0, 1.5, (nrec, 3)), rng.choice([0.0, 0.02, 0.3, 0.9, 1.0, 1.7], size=(nrec, 1))], axis=1).astype(np.float32)
+    rec["pos_xy"] = rng.normal(size=(nrec, 2)).astype(np.float32)
+    rec["pos_z"] = rng.normal(size=nrec).astype(np.float32)
+    lens = rng.choice([0, 1, 3, 255, 256, 257, 700], size=T)
+    M = int(lens.sum())
+    values = rng.integers(0, nrec, M + 300, dtype=np.uint32)           # entries past a range are read too (:72)
+    bounds = np.zeros((T, 2), dtype=np.uint32)
+    bounds[:, 0] = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    bounds[:, 1] = bounds[:, 0] + lens
+    bounds[3] = (50, 10)                                                # end < start: max(0, int(y - x)) = 0 splats (:61)
+    orc.set_blend_contraction(False)
+    try:
+        want, _, _ = orc.render(rec, values, bounds, w, h, heatmap=1.0)
+    finally:
+        orc.set_blend_contraction(True)
+    refshaders.set_shared_fill(0)
+    L = refshaders._lib(False)
+    tex = np.zeros((h, w, 4), dtype=np.float32)
+    pick = np.zeros(4, dtype=np.float32)
+    bufs = [rec, values, bounds, pick, tex]
+    import ctypes as C
+    ptrs = (C.c_void_p * 5)(*[b.ctypes.data for b in bufs])
+    sizes = (C.c_size_t * 5)(*[b.nbytes for b in bufs])
+    push = C.create_string_buffer(refshaders.create_push_constant([1.0, -1]), 16)
+    assert L.refshader_gsplat_render_dispatch(gx, gy, 1, ptrs, sizes, C.cast(push, C.c_void_p), w, h) == 0
+    np.testing.assert_array_equal(bits(tex), bits(want))
+
+
 REF_PLY = "/root/reference/resources/demo.ply"
 
 
