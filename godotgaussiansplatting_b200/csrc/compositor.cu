@@ -364,6 +364,206 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
 }
 
 // ==============================================================================================================
+// EXPERIMENTAL "v2" staging (GSR_COMP_V2=1; off by default, NOT yet run on a GPU -- written at the end of round 1 from the
+// ncu stall profile of composite_kernel: barrier 2.68 and math_pipe_throttle 1.57 warps per issue, FMA pipe 53 % busy,
+// 106 registers => 4 CTAs/SM).  Same tiles, same queue, same arithmetic, same results; what changes is the staging:
+//   * the records of chunk i+1 travel global -> shared with cp.async (LDGSTS) into per-thread private raw slots while
+//     chunk i is blended, instead of living in 18 registers across the blend loop (the register budget decides how many
+//     CTAs share an SM, and co-resident CTAs are what fills the barrier stalls);
+//   * each thread then rescales its own two records into the OTHER half of a double-buffered staging area, so the
+//     "staged data visible" barrier and the tile-stop-vote barrier of the reference (:70,:77,:98) become ONE
+//     __syncthreads per chunk (vote words double-buffered by chunk parity for the same reason).
+#ifndef GSR_COMP_V2_MIN_BLOCKS
+#define GSR_COMP_V2_MIN_BLOCKS 5
+#endif
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_kernel(const __grid_constant__ CompositeArgs p) {
+    __shared__ float4 s_a[2][CHUNK];
+    __shared__ float4 s_b[2][CHUNK];
+    __shared__ float s_c[2][CHUNK];
+    __shared__ float4 s_raw[CHUNK * 3];   // slot k (splat k of the chunk in flight) = floats [3k, 3k+3); written and read by one thread
+    __shared__ uint32_t s_vote[2][THREADS / 32];
+    __shared__ uint32_t s_tile, s_resume;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const BlendK K = make_blend_k();
+    uint32_t staged = 0;
+    unsigned long long t_start = 0;
+
+    for (;;) {
+        if (tid == 0) {
+            const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
+            if (ticket < (uint32_t)p.num_tiles) {
+                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                s_resume = 0u;
+            } else {
+                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                volatile uint32_t *done = &p.frame->comp_done;
+                uint32_t v;
+                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (v == 0u) v = *slot;
+                s_tile = v ? v - 1u : EXIT_TILE;
+                s_resume = 1u;
+                __threadfence();
+            }
+            if (p.trace) t_start = globaltimer_ns();
+        }
+        __syncthreads();
+        const uint32_t tile_id = s_tile;
+        const bool resume = s_resume != 0u;
+        if (tile_id == EXIT_TILE) break;
+
+        const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
+        const int px0 = (int)(tx * TILE + 2u * (tid & 7u)), py = (int)(ty * TILE + (tid >> 3));
+        const u64 npx2 = pk(-(float)px0, -(float)(px0 + 1));
+        const float fpy = (float)py;
+
+        const uint2 bounds = p.bounds[tile_id];
+        const int32_t diff = (int32_t)(bounds.y - bounds.x);
+        const int num_splats = diff > 0 ? diff : 0;
+        const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);
+
+        u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;
+        float t0 = 1.0f, t1 = 1.0f;
+        int i0 = 0;
+        const uint32_t rel = tile_id - (uint32_t)p.tile_begin;
+        const uint32_t local_tile = (rel / (uint32_t)(p.row_step * p.tiles_x)) * (uint32_t)p.tiles_x + rel % (uint32_t)p.tiles_x;
+        float4 *st = p.state + (uint64_t)local_tile * (2u * THREADS);
+        if (resume) {
+            const float4 sa = __ldcg(st + tid), sb = __ldcg(st + THREADS + tid);
+            cr2 = pk(sa.x, sa.y); cg2 = pk(sa.z, sa.w); cb2 = pk(sb.x, sb.y);
+            t0 = sb.z; t1 = sb.w;
+            i0 = (int)__ldcg(p.state_chunk + local_tile);
+        }
+
+        // splat ids of this thread's two slots of a chunk (one chunk ahead of the records, two ahead of the blend)
+        auto load_ids = [&](int ci, uint32_t &v0, uint32_t &v1) {
+            const int k0 = CHUNK * ci + (int)tid, k1 = k0 + THREADS;
+            v0 = (ci < num_iterations && k0 < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)k0) : 0xFFFFFFFFu;
+            v1 = (ci < num_iterations && k1 < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)k1) : 0xFFFFFFFFu;
+        };
+        auto issue = [&](uint32_t v0, uint32_t v1) {   // records of the two splats -> this thread's raw slots
+            if (v0 != 0xFFFFFFFFu) {
+                const float4 *r = p.records + (uint64_t)v0 * 3u;
+                cp_async16(&s_raw[3 * tid + 0], r + 0); cp_async16(&s_raw[3 * tid + 1], r + 1); cp_async16(&s_raw[3 * tid + 2], r + 2);
+            }
+            if (v1 != 0xFFFFFFFFu) {
+                const float4 *r = p.records + (uint64_t)v1 * 3u;
+                cp_async16(&s_raw[3 * (tid + THREADS) + 0], r + 0); cp_async16(&s_raw[3 * (tid + THREADS) + 1], r + 1);
+                cp_async16(&s_raw[3 * (tid + THREADS) + 2], r + 2);
+            }
+        };
+        auto finalize = [&](uint32_t v0, uint32_t v1, int b) {   // wait for the own copies, pre-scale like gather()
+            cp_async_commit_wait_all();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t slot = tid + (uint32_t)hh * THREADS;
+                Staged sgd = null_splat();
+                if ((hh ? v1 : v0) != 0xFFFFFFFFu) {
+                    const float4 r0 = s_raw[3 * slot + 0], r1 = s_raw[3 * slot + 1], r2 = s_raw[3 * slot + 2];
+                    sgd.a = make_float4(r0.x, r0.y, -0.5f * r1.x, -0.5f * r1.z);
+                    sgd.b = make_float4(-r1.y, r2.w, r2.x, r2.y);
+                    sgd.c = r2.z;
+                }
+                s_a[b][slot] = sgd.a; s_b[b][slot] = sgd.b; s_c[b][slot] = sgd.c;
+            }
+        };
+
+        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int i_begin = i0;
+        bool finished = true;
+        int b = 0;
+        uint32_t va0, va1, vb0 = 0xFFFFFFFFu, vb1 = 0xFFFFFFFFu;   // ids of the chunk being fetched / of the one after it
+        if (i0 < num_iterations) {
+            load_ids(i0, va0, va1);
+            issue(va0, va1);
+            load_ids(i0 + 1, vb0, vb1);
+            finalize(va0, va1, 0);
+        }
+        __syncthreads();   // staging half 0 visible (also orders the previous tile's last reads before this tile's writes)
+        for (int i = i_begin; i < num_iterations; ++i) {
+            const int sort_offset = CHUNK * i;
+            const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
+            staged += (uint32_t)chunk;
+            const bool fetch_next = (i + 1 < num_iterations) && (i + 1 - i_begin < quantum);
+            if (fetch_next) {   // chunk i+1: records in flight during this blend, ids of chunk i+2 behind them
+                va0 = vb0; va1 = vb1;
+                issue(va0, va1);
+                load_ids(i + 2, vb0, vb1);
+            }
+
+            const int chunk4 = (chunk + GU - 1) & ~(GU - 1);
+            for (int j = 0; j < chunk4; j += GU) {
+                if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
+                u64 al2[GU];
+                phase_a<false>(s_a[b], s_b[b], j, npx2, fpy, K, al2);
+                phase_b(s_b[b], s_c[b], j, al2, K, cr2, cg2, cb2, t0, t1);
+            }
+            if (fetch_next) finalize(va0, va1, b ^ 1);   // nobody reads half b^1 before the barrier below
+
+            const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t0 * 255.0f) + (uint32_t)(t1 * 255.0f));
+            if (lane == 0) s_vote[i & 1][warp] = wsum;
+            __syncthreads();   // the ONE barrier of the chunk: votes of chunk i and staging half b^1 (chunk i+1) visible
+            uint32_t shared_t = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) shared_t += s_vote[i & 1][w];
+            if (!(shared_t > 255u)) break;
+            if (i + 1 < num_iterations && i + 1 - i_begin >= quantum) {
+                finished = false;
+                i0 = i + 1;
+                break;
+            }
+            b ^= 1;
+        }
+
+        float r0, r1, g0, g1, b0, b1;
+        upk(cr2, r0, r1); upk(cg2, g0, g1); upk(cb2, b0, b1);
+        if (!finished) {
+            __stcg(st + tid, make_float4(r0, r1, g0, g1));
+            __stcg(st + THREADS + tid, make_float4(b0, b1, t0, t1));
+            if (tid == 0) __stcg(p.state_chunk + local_tile, (uint32_t)i0);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t slot = atomicAdd(&p.frame->comp_tail, 1u);
+                __threadfence();
+                *(volatile uint32_t *)(p.queue + slot) = tile_id + 1u;
+            }
+        } else {
+            const float hx = (float)num_splats * 5e-4f;  // :100-101
+            const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
+            if (py < p.height) {
+                float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
+                const float k0 = 1.0f - t0, k1 = 1.0f - t1;
+                if (px0 < p.width)
+                    row[px0] = make_float4(r0 + h0 * k0 * p.heatmap_factor, g0 + h1 * k0 * p.heatmap_factor, b0 + h2c * k0 * p.heatmap_factor, 1.0f);
+                if (px0 + 1 < p.width)
+                    row[px0 + 1] = make_float4(r1 + h0 * k1 * p.heatmap_factor, g1 + h1 * k1 * p.heatmap_factor, b1 + h2c * k1 * p.heatmap_factor, 1.0f);
+            }
+            if ((tid & 15u) == 0u && tile_id == p.target_tile_id && t0 != 1.0f) {  // :105-110 pick
+                const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
+                const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
+                *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
+            }
+            if (tid == 0) atomicAdd(&p.frame->comp_done, 1u);
+        }
+        if (p.trace && tid == 0) {
+            const uint32_t k = atomicAdd(p.trace_count, 1u);
+            if (k < p.trace_cap) p.trace[k] = make_ulonglong4(((unsigned long long)tile_id << 32) | smid(), t_start, globaltimer_ns(), ((unsigned long long)(uint32_t)i_begin << 32) | (uint32_t)(finished ? 1u : 0u) | ((uint32_t)num_iterations << 1));
+        }
+        __syncthreads();  // s_tile / staging buffers are reused by the next item
+    }
+    if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
+}
+
+// ==============================================================================================================
 // EXPERIMENTAL warp-specialised variant (GSR_COMP_WS=1; off by default).  Measured on B200 (c3): 0.77 ms vs 0.54 ms for
 // composite_kernel -- the per-4-splat hand-off through shared memory (poll, 4 x 64-bit loads, two warp syncs) costs more
 // than the instruction-level parallelism it buys, both in the saturated phase (-30 % throughput) and for a lone tile
@@ -569,7 +769,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, cfg_dev = -1;
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, cfg_dev = -1;
     int dev = 0;
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     if (cfg_dev != dev) {
@@ -579,7 +779,10 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         if (w) use_ws = atoi(w) != 0;
         const char *h = getenv("GSR_COMP_HWEXP");  // experiment knob: 1 = exp() on the SFU (not bit-reproducible; see phase_a)
         use_hwexp = (h && atoi(h) != 0) ? 1 : 0;
-        if (use_ws) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_ws_kernel, WS_THREADS, 0));
+        const char *v2e = getenv("GSR_COMP_V2");  // experiment knob: 1 = cp.async staging, one barrier per chunk (bit-identical results)
+        use_v2 = (v2e && atoi(v2e) != 0 && !use_ws && !use_hwexp) ? 1 : 0;
+        if (use_v2) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel, THREADS, 0));
+        else if (use_ws) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_ws_kernel, WS_THREADS, 0));
         else if (use_hwexp) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel<true>, THREADS, 0));
         else GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel<false>, THREADS, 0));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -587,7 +790,8 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
     const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
-    if (use_ws) composite_ws_kernel<<<grid, WS_THREADS, 0, stream>>>(a);
+    if (use_v2) composite_v2_kernel<<<grid, THREADS, 0, stream>>>(a);
+    else if (use_ws) composite_ws_kernel<<<grid, WS_THREADS, 0, stream>>>(a);
     else if (use_hwexp) composite_kernel<true><<<grid, THREADS, 0, stream>>>(a);
     else composite_kernel<false><<<grid, THREADS, 0, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());
