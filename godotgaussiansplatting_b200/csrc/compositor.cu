@@ -24,6 +24,7 @@
 // Arithmetic contract: "gsr deterministic math" (common.cuh): the GLSL-legal contractions of :84 and :89 are
 // explicit fma, exp() is the det_exp() polynomial (evaluated here two lanes at a time).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -37,12 +38,22 @@ constexpr float MIN_ALPHA = 1.0f / 255.0f;
 
 typedef unsigned long long u64;
 
+#ifndef GSR_CPU_EMU
 __device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#else  // tests/kernel_emu: the kernels of this file compiled for the CPU (test infrastructure; libgsr never defines GSR_CPU_EMU).
+       // A packed op is two independent IEEE binary32 operations -- exactly what the PTX f32x2 instructions are.
+inline u64 pk(float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (u64)a | ((u64)b << 32); }
+inline void upk(u64 v, float &lo, float &hi) { const uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4); }
+inline u64 fma2(u64 a, u64 b, u64 c) { float al, ah, bl, bh, cl, ch; upk(a, al, ah); upk(b, bl, bh); upk(c, cl, ch); return pk(fmaf(al, bl, cl), fmaf(ah, bh, ch)); }
+inline u64 mul2(u64 a, u64 b) { float al, ah, bl, bh; upk(a, al, ah); upk(b, bl, bh); return pk(al * bl, ah * bh); }
+inline u64 add2(u64 a, u64 b) { float al, ah, bl, bh; upk(a, al, ah); upk(b, bl, bh); return pk(al + bl, ah + bh); }
+inline u64 sub2(u64 a, u64 b) { float al, ah, bl, bh; upk(a, al, ah); upk(b, bl, bh); return pk(al - bl, ah - bh); }
+#endif
 __device__ __forceinline__ u64 bc(float x) { return pk(x, x); }
 
 struct Staged {  // one gathered record, pre-scaled for the inner loop
@@ -83,8 +94,13 @@ constexpr int GU = GSR_COMP_GROUP;
 #define GSR_COMP_WS_DEFAULT 0
 #endif
 
+#ifndef GSR_CPU_EMU
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#else
+inline unsigned long long globaltimer_ns() { return 0ull; }
+inline uint32_t smid() { return 0u; }
+#endif
 
 // Persistent CTAs + re-queueable tiles.  Work item = (tile, first chunk).  Tickets [0, num_tiles) are the tiles
 // themselves in natural order; an unfinished tile spills its per-pixel state (t, rgb of 256 pixels = 4 KB) and is
@@ -136,8 +152,12 @@ __device__ __forceinline__ void phase_a(const float4 *s_a, const float4 *s_b, in
         for (int u = 0; u < GU; ++u) {
             float tl, th;
             upk(pw2[u], tl, th);
+#ifndef GSR_CPU_EMU
             asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(tl));  // one MUFU.EX2; results below 2^-126 flush to 0
             asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(th));
+#else
+            tl = exp2f(tl); th = exp2f(th);
+#endif
             al2[u] = mul2(bc(by[u]), pk(tl, th));
         }
         return;
@@ -376,12 +396,17 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
 #ifndef GSR_COMP_V2_MIN_BLOCKS
 #define GSR_COMP_V2_MIN_BLOCKS 5
 #endif
+#ifndef GSR_CPU_EMU
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+#else
+inline void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+inline void cp_async_commit_wait_all() {}
+#endif
 
 __global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_kernel(const __grid_constant__ CompositeArgs p) {
     __shared__ float4 s_a[2][CHUNK];
@@ -767,6 +792,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 
 }  // namespace
 
+#ifndef GSR_CPU_EMU
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
     static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, cfg_dev = -1;
@@ -797,5 +823,6 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
+#endif  // GSR_CPU_EMU
 
 }  // namespace gsr

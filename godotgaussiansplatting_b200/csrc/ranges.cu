@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) band_fixup_kernel(const int32_t *__restri
 
 }  // namespace
 
+#ifndef GSR_CPU_EMU  // tests/kernel_emu compiles the kernels above for the CPU; the launchers are CUDA only
 int launch_band_fixup(const int32_t *global_last_plus1, float4 *out, int32_t width, int32_t height, int32_t tiles_x, int32_t num_tiles_total,
                       int32_t band_y0, int32_t band_y1, int32_t row_mod, int32_t row_rem, cudaStream_t stream) {
     band_fixup_kernel<<<1, 256, 0, stream>>>(global_last_plus1, out, width, height, tiles_x, num_tiles_total, band_y0, band_y1, row_mod, row_rem);
@@ -78,5 +79,6 @@ int launch_tile_ranges(const uint32_t *sorted_keys, const FrameState *frame, uin
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
+#endif  // GSR_CPU_EMU
 
 }  // namespace gsr

@@ -373,6 +373,7 @@ struct invocation {
     uint local_index, sg_invocation, sg_id, num_subgroups;
     /* subgroup collective exchange */
     uint sg_in, sg_sum, sg_excl, sg_ballot;
+    uint sg_vals[32]; /* every participant's sg_in (0 for non-participants): lane shuffles of the CUDA shim */
     bool sg_first;
 };
 
@@ -470,11 +471,13 @@ inline void run_workgroup(uvec3 group, uvec3 local_size, void (*body)(void*), vo
                     if (s.inv[i].state == INV_READY) resume(s, s.inv[i]);
                 /* everyone in the subgroup is now blocked or done: resolve a pending collective */
                 uint sum = 0, ballot = 0; bool any_waiting = false, first_seen = false;
+                uint vals[32] = {0};
                 for (size_t i = lo; i < hi; ++i) {
                     invocation& v = s.inv[i];
                     if (v.state != INV_AT_SUBGROUP) continue;
                     any_waiting = true;
                     v.sg_excl = sum;
+                    vals[i - lo] = v.sg_in;
                     sum += v.sg_in;
                     if (v.sg_in) ballot |= 1u << (i - lo);
                     v.sg_first = !first_seen;
@@ -485,6 +488,7 @@ inline void run_workgroup(uvec3 group, uvec3 local_size, void (*body)(void*), vo
                     invocation& v = s.inv[i];
                     if (v.state != INV_AT_SUBGROUP) continue;
                     v.sg_sum = sum; v.sg_ballot = ballot; v.state = INV_READY;
+                    std::memcpy(v.sg_vals, vals, sizeof vals);
                 }
             }
         }

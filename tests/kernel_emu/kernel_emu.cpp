@@ -1,0 +1,93 @@
+// kernel_emu.cpp -- libgsr's tile-range and compositor kernels (csrc/ranges.cu, csrc/compositor.cu) compiled for the CPU.
+// TEST INFRASTRUCTURE: see cuda_shim.h.  Built by tests/kernel_emu/build.py into tests/kernel_emu/libkernel_emu.so.
+#define GSR_CPU_EMU 1
+#include "cuda_shim.h"
+
+namespace cuda_emu { dim g_block_dim{128, 1, 1}, g_grid_dim{1, 1, 1}; }
+namespace gsr { void set_last_error(const char *, ...) {} }
+
+#include "../../godotgaussiansplatting_b200/csrc/compositor.cu"
+#include "../../godotgaussiansplatting_b200/csrc/ranges.cu"
+
+namespace {
+struct Launch { const gsr::CompositeArgs *args; int variant; };
+void body(void *p) {
+    const Launch *l = static_cast<const Launch *>(p);
+    switch (l->variant) {
+        case 0: gsr::composite_kernel<false>(*l->args); break;   // the shipped kernel
+        case 1: gsr::composite_v2_kernel(*l->args); break;       // GSR_COMP_V2
+        default: gsr::composite_kernel<true>(*l->args); break;   // GSR_COMP_HWEXP (exp2f stands in for MUFU.EX2)
+    }
+}
+}  // namespace
+
+// One persistent block works through every tile of the launch (fresh tickets first, then its own hand-backs in FIFO order),
+// which exercises the whole item logic: staging, blend, vote, quantum, spill, re-queue, resume.
+extern "C" int emu_composite(int variant, const void *records, const uint32_t *values, const uint32_t *bounds, float *out_rgba, int width,
+                             int height, int tile_begin, int row_step, int num_tiles, float heatmap_factor, uint32_t target_tile_id,
+                             float *pick4, unsigned long long *staged_out, unsigned *pushes_out) {
+    const int tiles_x = (width + 15) / 16;
+    gsr::FrameState frame;
+    memset(&frame, 0, sizeof frame);
+    const size_t nt = (size_t)(num_tiles > 0 ? num_tiles : 1);
+    uint32_t *queue = static_cast<uint32_t *>(calloc(nt * GSR_COMP_MAX_PUSHES, sizeof(uint32_t)));
+    float4 *state = static_cast<float4 *>(calloc(nt * 256, sizeof(float4)));
+    uint32_t *state_chunk = static_cast<uint32_t *>(calloc(nt, sizeof(uint32_t)));
+    gsr::CompositeArgs a;
+    memset(&a, 0, sizeof a);
+    a.records = static_cast<const float4 *>(records);
+    a.values = values;
+    a.bounds = reinterpret_cast<const uint2 *>(bounds);
+    a.out = reinterpret_cast<float4 *>(out_rgba);
+    a.width = width; a.height = height; a.tiles_x = tiles_x;
+    a.tile_begin = tile_begin; a.row_step = row_step; a.num_tiles = num_tiles;
+    a.heatmap_factor = heatmap_factor; a.target_tile_id = target_tile_id;
+    a.pick = reinterpret_cast<float4 *>(pick4);
+    a.frame = &frame; a.count_staged = 1;
+    a.queue = queue; a.state = state; a.state_chunk = state_chunk;
+    Launch l{&a, variant};
+    if (num_tiles > 0) glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(128, 1, 1), &body, &l);
+    if (staged_out) *staged_out = frame.staged;
+    if (pushes_out) *pushes_out = frame.comp_tail;
+    const int ok = (int)frame.comp_done == num_tiles ? 0 : 1;
+    free(queue); free(state); free(state_chunk);
+    return ok;
+}
+
+// ---- csrc/ranges.cu: `grid` blocks of 256 threads, run one after another (the kernel has no inter-block dependence) ----
+namespace {
+struct RangesLaunch { const uint32_t *keys; const gsr::FrameState *frame; uint2 *bounds; uint32_t num_tiles; int quirks, sharded; int32_t *sync_word; };
+void ranges_body(void *p) {
+    const RangesLaunch *l = static_cast<const RangesLaunch *>(p);
+    gsr::tile_ranges_kernel(l->keys, l->frame, l->bounds, l->num_tiles, l->quirks, l->sharded, l->sync_word);
+}
+struct FixupLaunch { const int32_t *last; float4 *out; int32_t w, h, tiles_x, T, y0, y1, mod, rem; };
+void fixup_body(void *p) {
+    const FixupLaunch *l = static_cast<const FixupLaunch *>(p);
+    gsr::band_fixup_kernel(l->last, l->out, l->w, l->h, l->tiles_x, l->T, l->y0, l->y1, l->mod, l->rem);
+}
+}  // namespace
+
+extern "C" int emu_tile_ranges(const uint32_t *sorted_keys, uint32_t m, uint32_t *bounds, uint32_t num_tiles, int quirks, int sharded,
+                               int32_t global_last_tile, int32_t *sync_word, int grid) {
+    gsr::FrameState frame;
+    memset(&frame, 0, sizeof frame);
+    frame.dup_total = m; frame.dup_sorted = m; frame.last_tile_plus1 = global_last_tile + 1;
+    memset(bounds, 0, sizeof(uint32_t) * 2 * (size_t)num_tiles);   // rasterizer.gd:128
+    RangesLaunch l{sorted_keys, &frame, reinterpret_cast<uint2 *>(bounds), num_tiles, quirks, sharded, sync_word};
+    cuda_emu::g_block_dim = cuda_emu::dim{256, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{(unsigned)grid, 1, 1};
+    for (int b = 0; b < grid; ++b) glsl::run_workgroup(glsl::uvec3((unsigned)b, 0, 0), glsl::uvec3(256, 1, 1), &ranges_body, &l);
+    cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
+    return 0;
+}
+
+extern "C" int emu_band_fixup(int32_t global_last_plus1, float *out_rgba, int width, int height, int band_y0, int band_y1, int row_mod, int row_rem) {
+    const int tiles_x = (width + 15) / 16, tiles_y = (height + 15) / 16;
+    FixupLaunch l{&global_last_plus1, reinterpret_cast<float4 *>(out_rgba), width, height, tiles_x, tiles_x * tiles_y, band_y0, band_y1, row_mod, row_rem};
+    cuda_emu::g_block_dim = cuda_emu::dim{256, 1, 1};
+    glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(256, 1, 1), &fixup_body, &l);
+    cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    return 0;
+}

@@ -73,3 +73,16 @@ def test_product_code_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 code = "\n".join(l for l in text.splitlines() if not l.strip().startswith(("#", "//", "*", "/*")))
                 assert "from oracle" not in code and "import oracle" not in code and "gsr_oracle" not in code, f
+
+
+def test_library_is_not_the_cpu_emulation_build():
+    """tests/kernel_emu compiles two kernel files for the CPU behind -DGSR_CPU_EMU (a logic pre-flight, test infrastructure).
+    libgsr itself must never be built that way, must not export the harness, and must carry sm_100a device code."""
+    from godotgaussiansplatting_b200 import build as gsr_build
+    src = open(gsr_build.__file__).read()
+    assert "GSR_CPU_EMU" not in src
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in ("emu_composite", "emu_tile_ranges", "emu_band_fixup"):
+        assert not hasattr(L, name), name
+    raw = open(_lib.LIB_PATH, "rb").read()
+    assert b"sm_100a" in raw and b"composite_kernel" in raw
