@@ -390,12 +390,91 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
 //   * the records of chunk i+1 travel global -> shared with cp.async (LDGSTS) into per-thread private raw slots while
 //     chunk i is blended, instead of living in 18 registers across the blend loop (the register budget decides how many
 //     CTAs share an SM, and co-resident CTAs are what fills the barrier stalls);
-//   * each thread then rescales its own two records into the OTHER half of a double-buffered staging area, so the
+//   * the copies land directly in the OTHER half of a double-buffered staging area (24 KB in all), where each thread
+//     then pre-scales its own two records in place, so the
 //     "staged data visible" barrier and the tile-stop-vote barrier of the reference (:70,:77,:98) become ONE
 //     __syncthreads per chunk (vote words double-buffered by chunk parity for the same reason).
-#ifndef GSR_COMP_V2_MIN_BLOCKS
-#define GSR_COMP_V2_MIN_BLOCKS 5
-#endif
+// phase A / phase B of composite_kernel over the one-array staging layout of the v2 / p4 kernels (slot k = float4[3k..3k+2])
+__device__ __forceinline__ void phase_a_st(const float4 *s, int j, u64 npx2, float fpy, const BlendK &K, u64 al2[GU]) {
+    float4 A[GU];
+    float bx[GU], by[GU], oy[GU];
+    u64 ox2[GU], pw2[GU], tm2[GU], e2[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) { A[u] = s[3 * (j + u)]; const float4 b = s[3 * (j + u) + 1]; bx[u] = b.x; by[u] = b.y; }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
+    // power = -0.5*(cx*ox*ox + cz*oy*oy) - cy*ox*oy  with q = fma(cz*oy, oy, cx*ox*ox), power = fma(-(cy*ox), oy, -0.5*q)
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = mul2(bc(bx[u]), ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
+    // exp(power): det_exp(), two lanes at a time
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], K.L2E2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        float tl, th;
+        upk(pw2[u], tl, th);
+        tl = g_min(g_max(tl, -127.0f), 128.0f);
+        th = g_min(g_max(th, -127.0f), 128.0f);
+        pw2[u] = pk(tl, th);
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) tm2[u] = add2(pw2[u], K.MAGIC2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) al2[u] = sub2(tm2[u], K.MAGIC2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(K.C6, pw2[u], K.C5);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C4);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C3);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C1);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.ONE2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        float ml, mh;
+        upk(tm2[u], ml, mh);
+        tm2[u] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u),
+                    __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = mul2(e2[u], tm2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) al2[u] = mul2(bc(by[u]), e2[u]);
+}
+
+__device__ __forceinline__ void phase_b_st(const float4 *s, int j, const u64 al2[GU], const BlendK &K, u64 &cr2, u64 &cg2,
+                                        u64 &cb2, float &t0, float &t1) {
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        const float4 b = s[3 * (j + u) + 1];
+        const float cbl = s[3 * (j + u) + 2].x;
+        float al, ah;
+        upk(al2[u], al, ah);
+        al = (t0 > MIN_ALPHA) ? al : 0.0f;
+        ah = (t1 > MIN_ALPHA) ? ah : 0.0f;
+        const u64 m2 = pk(al, ah);
+        const u64 t2 = pk(t0, t1);
+        cr2 = fma2(mul2(bc(b.z), m2), t2, cr2);
+        cg2 = fma2(mul2(bc(b.w), m2), t2, cg2);
+        cb2 = fma2(mul2(bc(cbl), m2), t2, cb2);
+        upk(mul2(t2, sub2(K.ONE2, m2)), t0, t1);
+    }
+}
+
 #ifndef GSR_CPU_EMU
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -408,11 +487,10 @@ inline void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, 
 inline void cp_async_commit_wait_all() {}
 #endif
 
-__global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_kernel(const __grid_constant__ CompositeArgs p) {
-    __shared__ float4 s_a[2][CHUNK];
-    __shared__ float4 s_b[2][CHUNK];
-    __shared__ float s_c[2][CHUNK];
-    __shared__ float4 s_raw[CHUNK * 3];   // slot k (splat k of the chunk in flight) = floats [3k, 3k+3); written and read by one thread
+template <int MIN_BLOCKS>   // CTAs per SM the register allocation targets: 5 -> 82 registers, 6 -> 70, 8 -> 62 (ptxas, no spills)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v2_kernel(const __grid_constant__ CompositeArgs p) {
+    __shared__ float4 s_st[2][CHUNK * 3];   // two staging halves; slot k = float4[3k] (a), [3k+1] (b), [3k+2].x (c): the 48-byte
+                                            // record lands there raw (cp.async) and is pre-scaled in place by the thread that fetched it
     __shared__ uint32_t s_vote[2][THREADS / 32];
     __shared__ uint32_t s_tile, s_resume;
 
@@ -473,30 +551,31 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_
             v0 = (ci < num_iterations && k0 < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)k0) : 0xFFFFFFFFu;
             v1 = (ci < num_iterations && k1 < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)k1) : 0xFFFFFFFFu;
         };
-        auto issue = [&](uint32_t v0, uint32_t v1) {   // records of the two splats -> this thread's raw slots
+        auto issue = [&](uint32_t v0, uint32_t v1, int b) {   // raw records of the two splats -> this thread's slots of half b
             if (v0 != 0xFFFFFFFFu) {
                 const float4 *r = p.records + (uint64_t)v0 * 3u;
-                cp_async16(&s_raw[3 * tid + 0], r + 0); cp_async16(&s_raw[3 * tid + 1], r + 1); cp_async16(&s_raw[3 * tid + 2], r + 2);
+                float4 *d = &s_st[b][3 * tid];
+                cp_async16(d + 0, r + 0); cp_async16(d + 1, r + 1); cp_async16(d + 2, r + 2);
             }
             if (v1 != 0xFFFFFFFFu) {
                 const float4 *r = p.records + (uint64_t)v1 * 3u;
-                cp_async16(&s_raw[3 * (tid + THREADS) + 0], r + 0); cp_async16(&s_raw[3 * (tid + THREADS) + 1], r + 1);
-                cp_async16(&s_raw[3 * (tid + THREADS) + 2], r + 2);
+                float4 *d = &s_st[b][3 * (tid + THREADS)];
+                cp_async16(d + 0, r + 0); cp_async16(d + 1, r + 1); cp_async16(d + 2, r + 2);
             }
         };
-        auto finalize = [&](uint32_t v0, uint32_t v1, int b) {   // wait for the own copies, pre-scale like gather()
+        auto finalize = [&](uint32_t v0, uint32_t v1, int b) {   // wait for the own copies, pre-scale in place like gather()
             cp_async_commit_wait_all();
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t slot = tid + (uint32_t)hh * THREADS;
+                float4 *d = &s_st[b][3 * (tid + (uint32_t)hh * THREADS)];
                 Staged sgd = null_splat();
                 if ((hh ? v1 : v0) != 0xFFFFFFFFu) {
-                    const float4 r0 = s_raw[3 * slot + 0], r1 = s_raw[3 * slot + 1], r2 = s_raw[3 * slot + 2];
+                    const float4 r0 = d[0], r1 = d[1], r2 = d[2];
                     sgd.a = make_float4(r0.x, r0.y, -0.5f * r1.x, -0.5f * r1.z);
                     sgd.b = make_float4(-r1.y, r2.w, r2.x, r2.y);
                     sgd.c = r2.z;
                 }
-                s_a[b][slot] = sgd.a; s_b[b][slot] = sgd.b; s_c[b][slot] = sgd.c;
+                d[0] = sgd.a; d[1] = sgd.b; d[2] = make_float4(sgd.c, 0.f, 0.f, 0.f);
             }
         };
 
@@ -508,7 +587,7 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_
         uint32_t va0, va1, vb0 = 0xFFFFFFFFu, vb1 = 0xFFFFFFFFu;   // ids of the chunk being fetched / of the one after it
         if (i0 < num_iterations) {
             load_ids(i0, va0, va1);
-            issue(va0, va1);
+            issue(va0, va1, 0);
             load_ids(i0 + 1, vb0, vb1);
             finalize(va0, va1, 0);
         }
@@ -520,7 +599,7 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_
             const bool fetch_next = (i + 1 < num_iterations) && (i + 1 - i_begin < quantum);
             if (fetch_next) {   // chunk i+1: records in flight during this blend, ids of chunk i+2 behind them
                 va0 = vb0; va1 = vb1;
-                issue(va0, va1);
+                issue(va0, va1, b ^ 1);   // half b^1 was last read in blend(i-1): everybody is past that barrier
                 load_ids(i + 2, vb0, vb1);
             }
 
@@ -528,8 +607,8 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_
             for (int j = 0; j < chunk4; j += GU) {
                 if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
                 u64 al2[GU];
-                phase_a<false>(s_a[b], s_b[b], j, npx2, fpy, K, al2);
-                phase_b(s_b[b], s_c[b], j, al2, K, cr2, cg2, cb2, t0, t1);
+                phase_a_st(s_st[b], j, npx2, fpy, K, al2);
+                phase_b_st(s_st[b], j, al2, K, cr2, cg2, cb2, t0, t1);
             }
             if (fetch_next) finalize(va0, va1, b ^ 1);   // nobody reads half b^1 before the barrier below
 
@@ -584,6 +663,295 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_V2_MIN_BLOCKS) composite_v2_
             if (k < p.trace_cap) p.trace[k] = make_ulonglong4(((unsigned long long)tile_id << 32) | smid(), t_start, globaltimer_ns(), ((unsigned long long)(uint32_t)i_begin << 32) | (uint32_t)(finished ? 1u : 0u) | ((uint32_t)num_iterations << 1));
         }
         __syncthreads();  // s_tile / staging buffers are reused by the next item
+    }
+    if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
+}
+
+// ==============================================================================================================
+// EXPERIMENTAL "p4" variant (GSR_COMP_P4=1; off by default, NOT yet run on a GPU; logic checked by tests/test_kernel_emu.py).
+// v2 staging, but 64 threads per tile and FOUR horizontally adjacent pixels (two packed pairs) per thread: the shared-memory
+// loads and the row terms (oy, cz*oy) of a splat are shared by both pairs, and every splat offers two independent
+// dependency chains, so a group of two splats gives ptxas the four chains the 2-pixel kernel needs four splats for.
+// Same arithmetic per pixel, same vote, same queue => same results.
+constexpr int P4_THREADS = 64;
+constexpr int P4_GU = 2;
+#ifndef GSR_COMP_P4_MIN_BLOCKS
+#define GSR_COMP_P4_MIN_BLOCKS 8
+#endif
+
+// phase A for two pixel pairs (pixels px0,px0+1 | px0+2,px0+3 of one row) and P4_GU splats, stage by stage
+// staging layout of the p4 kernel: ONE array per half, slot k = float4[3k] (a), float4[3k+1] (b), float4[3k+2].x (c) -- the
+// 48-byte record lands there raw (cp.async) and is pre-scaled in place by the thread that fetched it
+__device__ __forceinline__ void phase_a_p4(const float4 *s, int j, u64 npxA, u64 npxB, float fpy, const BlendK &K, u64 al2[P4_GU][2]) {
+    float4 A[P4_GU];
+    float bx[P4_GU], by[P4_GU], oy[P4_GU], czoy[P4_GU];
+    u64 ox2[P4_GU][2], pw2[P4_GU][2], tm2[P4_GU][2], e2[P4_GU][2];
+#pragma unroll
+    for (int u = 0; u < P4_GU; ++u) { A[u] = s[3 * (j + u)]; const float4 b = s[3 * (j + u) + 1]; bx[u] = b.x; by[u] = b.y; }
+#pragma unroll
+    for (int u = 0; u < P4_GU; ++u) {
+        ox2[u][0] = add2(bc(A[u].x), npxA); ox2[u][1] = add2(bc(A[u].x), npxB);
+        oy[u] = A[u].y - fpy; czoy[u] = A[u].w * oy[u];
+    }
+#define P4_EACH for (int u = 0; u < P4_GU; ++u) for (int q = 0; q < 2; ++q)
+#pragma unroll
+    P4_EACH pw2[u][q] = mul2(bc(A[u].z), ox2[u][q]);
+#pragma unroll
+    P4_EACH pw2[u][q] = mul2(pw2[u][q], ox2[u][q]);
+#pragma unroll
+    P4_EACH pw2[u][q] = fma2(bc(czoy[u]), bc(oy[u]), pw2[u][q]);
+#pragma unroll
+    P4_EACH e2[u][q] = mul2(bc(bx[u]), ox2[u][q]);
+#pragma unroll
+    P4_EACH pw2[u][q] = fma2(e2[u][q], bc(oy[u]), pw2[u][q]);
+#pragma unroll
+    P4_EACH pw2[u][q] = mul2(pw2[u][q], K.L2E2);
+#pragma unroll
+    P4_EACH {
+        float tl, th;
+        upk(pw2[u][q], tl, th);
+        tl = g_min(g_max(tl, -127.0f), 128.0f);
+        th = g_min(g_max(th, -127.0f), 128.0f);
+        pw2[u][q] = pk(tl, th);
+    }
+#pragma unroll
+    P4_EACH tm2[u][q] = add2(pw2[u][q], K.MAGIC2);
+#pragma unroll
+    P4_EACH al2[u][q] = sub2(tm2[u][q], K.MAGIC2);
+#pragma unroll
+    P4_EACH pw2[u][q] = sub2(pw2[u][q], al2[u][q]);  // f
+#pragma unroll
+    P4_EACH e2[u][q] = fma2(K.C6, pw2[u][q], K.C5);
+#pragma unroll
+    P4_EACH e2[u][q] = fma2(e2[u][q], pw2[u][q], K.C4);
+#pragma unroll
+    P4_EACH e2[u][q] = fma2(e2[u][q], pw2[u][q], K.C3);
+#pragma unroll
+    P4_EACH e2[u][q] = fma2(e2[u][q], pw2[u][q], K.C2);
+#pragma unroll
+    P4_EACH e2[u][q] = fma2(e2[u][q], pw2[u][q], K.C1);
+#pragma unroll
+    P4_EACH e2[u][q] = fma2(e2[u][q], pw2[u][q], K.ONE2);
+#pragma unroll
+    P4_EACH {
+        float ml, mh;
+        upk(tm2[u][q], ml, mh);
+        tm2[u][q] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u), __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
+    }
+#pragma unroll
+    P4_EACH e2[u][q] = mul2(e2[u][q], tm2[u][q]);
+#pragma unroll
+    P4_EACH al2[u][q] = mul2(bc(by[u]), e2[u][q]);
+#undef P4_EACH
+}
+
+__device__ __forceinline__ void phase_b_p4(const float4 *s, int j, const u64 al2[P4_GU][2], const BlendK &K, u64 cr2[2], u64 cg2[2], u64 cb2[2],
+                                           float t[4]) {
+#pragma unroll
+    for (int u = 0; u < P4_GU; ++u) {
+        const float4 b = s[3 * (j + u) + 1];
+        const float cbl = s[3 * (j + u) + 2].x;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float al, ah;
+            upk(al2[u][q], al, ah);
+            al = (t[2 * q] > MIN_ALPHA) ? al : 0.0f;
+            ah = (t[2 * q + 1] > MIN_ALPHA) ? ah : 0.0f;
+            const u64 m2 = pk(al, ah);
+            const u64 t2 = pk(t[2 * q], t[2 * q + 1]);
+            cr2[q] = fma2(mul2(bc(b.z), m2), t2, cr2[q]);
+            cg2[q] = fma2(mul2(bc(b.w), m2), t2, cg2[q]);
+            cb2[q] = fma2(mul2(bc(cbl), m2), t2, cb2[q]);
+            upk(mul2(t2, sub2(K.ONE2, m2)), t[2 * q], t[2 * q + 1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(P4_THREADS, GSR_COMP_P4_MIN_BLOCKS) composite_p4_kernel(const __grid_constant__ CompositeArgs p) {
+    __shared__ float4 s_st[2][CHUNK * 3];   // two staging halves, 12 KB each (see phase_a_p4)
+    __shared__ uint32_t s_vote[2][P4_THREADS / 32];
+    __shared__ uint32_t s_tile, s_resume;
+    constexpr int SL = CHUNK / P4_THREADS;   // staging slots per thread (4): slot tid + k*64
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const BlendK K = make_blend_k();
+    uint32_t staged = 0;
+    unsigned long long t_start = 0;
+
+    for (;;) {
+        if (tid == 0) {
+            const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
+            if (ticket < (uint32_t)p.num_tiles) {
+                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                s_resume = 0u;
+            } else {
+                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                volatile uint32_t *done = &p.frame->comp_done;
+                uint32_t v;
+                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (v == 0u) v = *slot;
+                s_tile = v ? v - 1u : EXIT_TILE;
+                s_resume = 1u;
+                __threadfence();
+            }
+            if (p.trace) t_start = globaltimer_ns();
+        }
+        __syncthreads();
+        const uint32_t tile_id = s_tile;
+        const bool resume = s_resume != 0u;
+        if (tile_id == EXIT_TILE) break;
+
+        const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
+        const int px0 = (int)(tx * TILE + 4u * (tid & 3u)), py = (int)(ty * TILE + (tid >> 2));
+        const u64 npxA = pk(-(float)px0, -(float)(px0 + 1)), npxB = pk(-(float)(px0 + 2), -(float)(px0 + 3));
+        const float fpy = (float)py;
+
+        const uint2 bounds = p.bounds[tile_id];
+        const int32_t diff = (int32_t)(bounds.y - bounds.x);
+        const int num_splats = diff > 0 ? diff : 0;
+        const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);
+
+        u64 cr2[2] = {pk(0.f, 0.f), pk(0.f, 0.f)}, cg2[2] = {cr2[0], cr2[0]}, cb2[2] = {cr2[0], cr2[0]};
+        float t[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        int i0 = 0;
+        const uint32_t rel = tile_id - (uint32_t)p.tile_begin;
+        const uint32_t local_tile = (rel / (uint32_t)(p.row_step * p.tiles_x)) * (uint32_t)p.tiles_x + rel % (uint32_t)p.tiles_x;
+        float4 *st = p.state + (uint64_t)local_tile * 256u;   // 4 float4 per thread: r[4], g[4], b[4], t[4]
+        if (resume) {
+            const float4 sr = __ldcg(st + tid), sg = __ldcg(st + 64 + tid), sb = __ldcg(st + 128 + tid), stt = __ldcg(st + 192 + tid);
+            cr2[0] = pk(sr.x, sr.y); cr2[1] = pk(sr.z, sr.w);
+            cg2[0] = pk(sg.x, sg.y); cg2[1] = pk(sg.z, sg.w);
+            cb2[0] = pk(sb.x, sb.y); cb2[1] = pk(sb.z, sb.w);
+            t[0] = stt.x; t[1] = stt.y; t[2] = stt.z; t[3] = stt.w;
+            i0 = (int)__ldcg(p.state_chunk + local_tile);
+        }
+
+        auto load_ids = [&](int ci, uint32_t v[SL]) {
+#pragma unroll
+            for (int k = 0; k < SL; ++k) {
+                const int idx = CHUNK * ci + (int)tid + k * P4_THREADS;
+                v[k] = (ci < num_iterations && idx < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)idx) : 0xFFFFFFFFu;
+            }
+        };
+        auto issue = [&](const uint32_t v[SL], int b) {   // raw records straight into the half that is not being blended
+#pragma unroll
+            for (int k = 0; k < SL; ++k)
+                if (v[k] != 0xFFFFFFFFu) {
+                    const float4 *r = p.records + (uint64_t)v[k] * 3u;
+                    float4 *d = &s_st[b][3 * (tid + (uint32_t)k * P4_THREADS)];
+                    cp_async16(d + 0, r + 0); cp_async16(d + 1, r + 1); cp_async16(d + 2, r + 2);
+                }
+        };
+        auto finalize = [&](const uint32_t v[SL], int b) {   // own slots: wait, pre-scale in place (gather()'s layout)
+            cp_async_commit_wait_all();
+#pragma unroll
+            for (int k = 0; k < SL; ++k) {
+                float4 *d = &s_st[b][3 * (tid + (uint32_t)k * P4_THREADS)];
+                Staged sgd = null_splat();
+                if (v[k] != 0xFFFFFFFFu) {
+                    const float4 r0 = d[0], r1 = d[1], r2 = d[2];
+                    sgd.a = make_float4(r0.x, r0.y, -0.5f * r1.x, -0.5f * r1.z);
+                    sgd.b = make_float4(-r1.y, r2.w, r2.x, r2.y);
+                    sgd.c = r2.z;
+                }
+                d[0] = sgd.a; d[1] = sgd.b; d[2] = make_float4(sgd.c, 0.f, 0.f, 0.f);
+            }
+        };
+
+        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int i_begin = i0;
+        bool finished = true;
+        int b = 0;
+        uint32_t va[SL], vb[SL];
+#pragma unroll
+        for (int k = 0; k < SL; ++k) va[k] = vb[k] = 0xFFFFFFFFu;
+        if (i0 < num_iterations) {
+            load_ids(i0, va);
+            issue(va, 0);
+            load_ids(i0 + 1, vb);
+            finalize(va, 0);
+        }
+        __syncthreads();
+        for (int i = i_begin; i < num_iterations; ++i) {
+            const int sort_offset = CHUNK * i;
+            const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
+            staged += (uint32_t)chunk;
+            const bool fetch_next = (i + 1 < num_iterations) && (i + 1 - i_begin < quantum);
+            if (fetch_next) {
+#pragma unroll
+                for (int k = 0; k < SL; ++k) va[k] = vb[k];
+                issue(va, b ^ 1);   // half b^1 was last read in blend(i-1): everybody is past that barrier
+                load_ids(i + 2, vb);
+            }
+
+            const int chunkg = (chunk + P4_GU - 1) & ~(P4_GU - 1);   // null splats (opacity 0) pad the group: exact no-ops
+            for (int j = 0; j < chunkg; j += P4_GU) {
+                if (!__any_sync(0xffffffffu, (t[0] > MIN_ALPHA) || (t[1] > MIN_ALPHA) || (t[2] > MIN_ALPHA) || (t[3] > MIN_ALPHA))) break;
+                u64 al2[P4_GU][2];
+                phase_a_p4(s_st[b], j, npxA, npxB, fpy, K, al2);
+                phase_b_p4(s_st[b], j, al2, K, cr2, cg2, cb2, t);
+            }
+            if (fetch_next) finalize(va, b ^ 1);
+
+            const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t[0] * 255.0f) + (uint32_t)(t[1] * 255.0f) +
+                                                                    (uint32_t)(t[2] * 255.0f) + (uint32_t)(t[3] * 255.0f));
+            if (lane == 0) s_vote[i & 1][warp] = wsum;
+            __syncthreads();
+            uint32_t shared_t = 0;
+#pragma unroll
+            for (int w = 0; w < P4_THREADS / 32; ++w) shared_t += s_vote[i & 1][w];
+            if (!(shared_t > 255u)) break;
+            if (i + 1 < num_iterations && i + 1 - i_begin >= quantum) {
+                finished = false;
+                i0 = i + 1;
+                break;
+            }
+            b ^= 1;
+        }
+
+        float r[4], g[4], bl[4];
+        upk(cr2[0], r[0], r[1]); upk(cr2[1], r[2], r[3]);
+        upk(cg2[0], g[0], g[1]); upk(cg2[1], g[2], g[3]);
+        upk(cb2[0], bl[0], bl[1]); upk(cb2[1], bl[2], bl[3]);
+        if (!finished) {
+            __stcg(st + tid, make_float4(r[0], r[1], r[2], r[3]));
+            __stcg(st + 64 + tid, make_float4(g[0], g[1], g[2], g[3]));
+            __stcg(st + 128 + tid, make_float4(bl[0], bl[1], bl[2], bl[3]));
+            __stcg(st + 192 + tid, make_float4(t[0], t[1], t[2], t[3]));
+            if (tid == 0) __stcg(p.state_chunk + local_tile, (uint32_t)i0);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t slot = atomicAdd(&p.frame->comp_tail, 1u);
+                __threadfence();
+                *(volatile uint32_t *)(p.queue + slot) = tile_id + 1u;
+            }
+        } else {
+            const float hx = (float)num_splats * 5e-4f;  // :100-101
+            const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
+            if (py < p.height) {
+                float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float kk = 1.0f - t[k];
+                    if (px0 + k < p.width)
+                        row[px0 + k] = make_float4(r[k] + h0 * kk * p.heatmap_factor, g[k] + h1 * kk * p.heatmap_factor, bl[k] + h2c * kk * p.heatmap_factor, 1.0f);
+                }
+            }
+            // :105-110 pick: the elected lanes of the reference's 8 subgroups are the pixels (0, 2s): even rows, first column
+            if ((tid & 7u) == 0u && tile_id == p.target_tile_id && t[0] != 1.0f) {
+                const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
+                const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
+                *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
+            }
+            if (tid == 0) atomicAdd(&p.frame->comp_done, 1u);
+        }
+        if (p.trace && tid == 0) {
+            const uint32_t k = atomicAdd(p.trace_count, 1u);
+            if (k < p.trace_cap) p.trace[k] = make_ulonglong4(((unsigned long long)tile_id << 32) | smid(), t_start, globaltimer_ns(), ((unsigned long long)(uint32_t)i_begin << 32) | (uint32_t)(finished ? 1u : 0u) | ((uint32_t)num_iterations << 1));
+        }
+        __syncthreads();
     }
     if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
 }
@@ -795,7 +1163,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 #ifndef GSR_CPU_EMU
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, cfg_dev = -1;
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, use_p4 = 0, cfg_dev = -1;
     int dev = 0;
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     if (cfg_dev != dev) {
@@ -805,9 +1173,15 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         if (w) use_ws = atoi(w) != 0;
         const char *h = getenv("GSR_COMP_HWEXP");  // experiment knob: 1 = exp() on the SFU (not bit-reproducible; see phase_a)
         use_hwexp = (h && atoi(h) != 0) ? 1 : 0;
-        const char *v2e = getenv("GSR_COMP_V2");  // experiment knob: 1 = cp.async staging, one barrier per chunk (bit-identical results)
-        use_v2 = (v2e && atoi(v2e) != 0 && !use_ws && !use_hwexp) ? 1 : 0;
-        if (use_v2) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel, THREADS, 0));
+        const char *v2e = getenv("GSR_COMP_V2");  // experiment knob: cp.async staging, one barrier per chunk (bit-identical results);
+        use_v2 = (v2e && atoi(v2e) != 0 && !use_ws && !use_hwexp) ? atoi(v2e) : 0;   // value = CTAs/SM target: 1|5 -> 5, 6, 8
+        const char *p4e = getenv("GSR_COMP_P4");  // experiment knob: 1 = four pixels per thread on top of the v2 staging (bit-identical results)
+        use_p4 = (p4e && atoi(p4e) != 0 && !use_ws && !use_hwexp) ? 1 : 0;
+        if (use_p4) use_v2 = 0;
+        if (use_p4) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_p4_kernel, P4_THREADS, 0));
+        else if (use_v2 >= 8) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<8>, THREADS, 0));
+        else if (use_v2 >= 6) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<6>, THREADS, 0));
+        else if (use_v2) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<5>, THREADS, 0));
         else if (use_ws) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_ws_kernel, WS_THREADS, 0));
         else if (use_hwexp) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel<true>, THREADS, 0));
         else GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_kernel<false>, THREADS, 0));
@@ -816,7 +1190,10 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
     const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
-    if (use_v2) composite_v2_kernel<<<grid, THREADS, 0, stream>>>(a);
+    if (use_p4) composite_p4_kernel<<<grid, P4_THREADS, 0, stream>>>(a);
+    else if (use_v2 >= 8) composite_v2_kernel<8><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v2 >= 6) composite_v2_kernel<6><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v2) composite_v2_kernel<5><<<grid, THREADS, 0, stream>>>(a);
     else if (use_ws) composite_ws_kernel<<<grid, WS_THREADS, 0, stream>>>(a);
     else if (use_hwexp) composite_kernel<true><<<grid, THREADS, 0, stream>>>(a);
     else composite_kernel<false><<<grid, THREADS, 0, stream>>>(a);

@@ -15,7 +15,8 @@ void body(void *p) {
     const Launch *l = static_cast<const Launch *>(p);
     switch (l->variant) {
         case 0: gsr::composite_kernel<false>(*l->args); break;   // the shipped kernel
-        case 1: gsr::composite_v2_kernel(*l->args); break;       // GSR_COMP_V2
+        case 1: gsr::composite_v2_kernel<5>(*l->args); break;       // GSR_COMP_V2
+        case 3: gsr::composite_p4_kernel(*l->args); break;       // GSR_COMP_P4 (64 threads)
         default: gsr::composite_kernel<true>(*l->args); break;   // GSR_COMP_HWEXP (exp2f stands in for MUFU.EX2)
     }
 }
@@ -46,7 +47,10 @@ extern "C" int emu_composite(int variant, const void *records, const uint32_t *v
     a.frame = &frame; a.count_staged = 1;
     a.queue = queue; a.state = state; a.state_chunk = state_chunk;
     Launch l{&a, variant};
-    if (num_tiles > 0) glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(128, 1, 1), &body, &l);
+    const unsigned threads = variant == 3 ? 64u : 128u;
+    cuda_emu::g_block_dim = cuda_emu::dim{threads, 1, 1};
+    if (num_tiles > 0) glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(threads, 1, 1), &body, &l);
+    cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
     if (staged_out) *staged_out = frame.staged;
     if (pushes_out) *pushes_out = frame.comp_tail;
     const int ok = (int)frame.comp_done == num_tiles ? 0 : 1;
