@@ -109,7 +109,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) onesweep_kernel(const
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "need one thread per digit");
     constexpr int WARPS = THREADS / 32;
     constexpr uint32_t TILE_KEYS = THREADS * ITEMS;
+#ifndef GSR_CPU_EMU
     extern __shared__ uint32_t smem[];
+#else  // tests/kernel_emu (CPU logic pre-flight): dynamic shared memory becomes a block-shared array of the same size
+    __shared__ uint32_t smem[WARPS * RADIX + 2 * TILE_KEYS];
+#endif
     uint32_t *s_whist = smem;                    // [WARPS][256] warp-private digit counters
     uint32_t *s_keys = s_whist + WARPS * RADIX;  // [TILE_KEYS]
     uint32_t *s_vals = s_keys + TILE_KEYS;       // [TILE_KEYS] (PAIRS)
@@ -313,6 +317,8 @@ int g_sm_count = 0;
 
 }  // namespace
 
+#ifndef GSR_CPU_EMU  // host side: CUDA only (tests/kernel_emu drives the kernels above itself)
+
 size_t SortWorkspace::bytes() const {
     return sizeof(uint32_t) * (4 * RADIX + 8) + sizeof(uint32_t) * 4ull * max_tiles * RADIX + (alt_keys ? 8ull * max_n : 0);
 }
@@ -387,5 +393,6 @@ int sort_pairs_device(SortWorkspace &ws, uint32_t *keys, uint32_t *vals, const u
 }
 
 uint32_t sort_tile_keys() { return SWEEP_TILE; }
+#endif  // GSR_CPU_EMU
 
 }  // namespace gsr

@@ -54,6 +54,13 @@ inline unsigned long long __shfl_sync(unsigned m, unsigned long long v, int src)
     const unsigned lo = __shfl_sync(m, (unsigned)v, src), hi = __shfl_sync(m, (unsigned)(v >> 32), src);
     return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
+inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned delta) {
+    ::glsl::subgroup_collective(v);
+    auto *c = ::glsl::sched().cur;
+    return c->sg_invocation >= delta ? c->sg_vals[c->sg_invocation - delta] : v;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline void __nanosleep(unsigned) {

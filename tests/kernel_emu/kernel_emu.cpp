@@ -1,4 +1,4 @@
-// kernel_emu.cpp -- libgsr's tile-range and compositor kernels (csrc/ranges.cu, csrc/compositor.cu) compiled for the CPU.
+// kernel_emu.cpp -- libgsr's sort, tile-range and compositor kernels (csrc/radix_sort.cu, ranges.cu, compositor.cu) compiled for the CPU.
 // TEST INFRASTRUCTURE: see cuda_shim.h.  Built by tests/kernel_emu/build.py into tests/kernel_emu/libkernel_emu.so.
 #define GSR_CPU_EMU 1
 #include "cuda_shim.h"
@@ -8,6 +8,7 @@ namespace gsr { void set_last_error(const char *, ...) {} }
 
 #include "../../godotgaussiansplatting_b200/csrc/compositor.cu"
 #include "../../godotgaussiansplatting_b200/csrc/ranges.cu"
+#include "../../godotgaussiansplatting_b200/csrc/radix_sort.cu"
 
 namespace {
 struct Launch { const gsr::CompositeArgs *args; int variant; };
@@ -93,5 +94,52 @@ extern "C" int emu_band_fixup(int32_t global_last_plus1, float *out_rgba, int wi
     cuda_emu::g_block_dim = cuda_emu::dim{256, 1, 1};
     glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(256, 1, 1), &fixup_body, &l);
     cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    return 0;
+}
+
+// ---- csrc/radix_sort.cu: the histogram kernel on `hist_grid` blocks, then four onesweep passes, each by ONE persistent block that
+//      pulls every tile in ticket order (so a look-back always finds its predecessors published) ----
+namespace {
+struct HistLaunch { const uint32_t *keys, *n_ptr; uint32_t n_max; uint32_t *hist, *status; uint32_t tile_keys, max_tiles; };
+void hist_body(void *p) {
+    const HistLaunch *l = static_cast<const HistLaunch *>(p);
+    gsr::sort_hist_kernel(l->keys, l->n_ptr, l->n_max, l->hist, l->status, l->tile_keys, l->max_tiles);
+}
+struct SweepLaunch { const uint32_t *kin; uint32_t *kout; const uint32_t *vin; uint32_t *vout; const uint32_t *n_ptr; uint32_t n_max; const uint32_t *hist; uint32_t *status, *ticket; int shift; };
+void sweep_pairs_body(void *p) {
+    const SweepLaunch *l = static_cast<const SweepLaunch *>(p);
+    gsr::onesweep_kernel<gsr::SWEEP_THREADS, gsr::SWEEP_ITEMS, true>(l->kin, l->kout, l->vin, l->vout, l->n_ptr, l->n_max, l->hist, l->status, l->ticket, l->shift);
+}
+void sweep_keys_body(void *p) {
+    const SweepLaunch *l = static_cast<const SweepLaunch *>(p);
+    gsr::onesweep_kernel<gsr::SWEEP_THREADS, gsr::SWEEP_ITEMS, false>(l->kin, l->kout, nullptr, nullptr, l->n_ptr, l->n_max, l->hist, l->status, l->ticket, l->shift);
+}
+}  // namespace
+
+// keys/values: n_max entries each, sorted in place (values may be null: keys only).  n <= n_max is read "from the device".
+extern "C" int emu_sort_pairs(uint32_t *keys, uint32_t *values, uint32_t n, uint32_t n_max, int hist_grid) {
+    const uint32_t tile = gsr::SWEEP_TILE, max_tiles = (n_max + tile - 1) / tile;
+    uint32_t *hist = static_cast<uint32_t *>(calloc(4 * 256 + 8, sizeof(uint32_t)));
+    uint32_t *status = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * 4ull * max_tiles * 256));
+    memset(status, 0xCD, sizeof(uint32_t) * 4ull * max_tiles * 256);   // the histogram kernel must clear what the passes use
+    uint32_t *alt_k = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * (size_t)n_max));
+    uint32_t *alt_v = values ? static_cast<uint32_t *>(malloc(sizeof(uint32_t) * (size_t)n_max)) : nullptr;
+    uint32_t *tickets = hist + 4 * 256;
+    const uint32_t n_dev = n;
+    HistLaunch h{keys, &n_dev, n_max, hist, status, tile, max_tiles};
+    cuda_emu::g_block_dim = cuda_emu::dim{512, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{(unsigned)hist_grid, 1, 1};
+    for (int b = 0; b < hist_grid; ++b) glsl::run_workgroup(glsl::uvec3((unsigned)b, 0, 0), glsl::uvec3(512, 1, 1), &hist_body, &h);
+    cuda_emu::g_block_dim = cuda_emu::dim{(unsigned)gsr::SWEEP_THREADS, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
+    uint32_t *kin = keys, *kout = alt_k, *vin = values, *vout = alt_v;
+    for (int pass = 0; pass < 4; ++pass) {
+        SweepLaunch l{kin, kout, vin, vout, &n_dev, n_max, hist + pass * 256, status + (size_t)pass * max_tiles * 256, tickets + pass, 8 * pass};
+        glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3((unsigned)gsr::SWEEP_THREADS, 1, 1), values ? &sweep_pairs_body : &sweep_keys_body, &l);
+        uint32_t *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    free(hist); free(status); free(alt_k); free(alt_v);
     return 0;
 }

@@ -1,7 +1,7 @@
-"""libgsr's tile-range and compositor kernels, compiled for the CPU (tests/kernel_emu), against the oracle -- bit for bit.
+"""libgsr's sort, tile-range and compositor kernels, compiled for the CPU (tests/kernel_emu), against the oracle -- bit for bit.
 
 This is NOT a CPU path of the product (libgsr has none; see tests/test_abi.py): it is a pre-flight check of kernel LOGIC.
-csrc/ranges.cu and csrc/compositor.cu are compiled by g++ under a thin shim of the CUDA execution model (threads = fibers,
+csrc/radix_sort.cu, csrc/ranges.cu and csrc/compositor.cu are compiled by g++ under a thin shim of the CUDA execution model (threads = fibers,
 __syncthreads / warp collectives real, __shared__ = block-shared, packed f32x2 PTX = two IEEE binary32 operations), and one
 persistent block works through every tile: staging, blend, tile-stop vote, quantum, spill, re-queue, resume.
 It lets a kernel variant that has never seen a GPU (GSR_COMP_V2) prove its indexing and buffering before GPU minutes are spent.
@@ -36,6 +36,8 @@ def lib():
                                     C.c_float, C.c_uint32, C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint)]
         L.emu_tile_ranges.restype = C.c_int
         L.emu_tile_ranges.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int32, C.c_void_p, C.c_int]
+        L.emu_sort_pairs.restype = C.c_int
+        L.emu_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.emu_band_fixup.restype = C.c_int
         L.emu_band_fixup.argtypes = [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _L = L
@@ -156,3 +158,46 @@ def test_band_fixup_kernel_blanks_only_the_owned_last_tile():
     img[:] = 1
     lib().emu_band_fixup(T, img.ctypes.data, w, h, 0, 5, 1, 0)         # last occupied tile == T-1: the other rule applies, nothing blanked
     assert (img == 1).all()
+
+
+@pytest.mark.parametrize("n", [1, 31, 100, 6143, 6144, 6145, 20000, 100000])
+@pytest.mark.parametrize("pairs", [True, False], ids=["pairs", "keys"])
+def test_onesweep_kernels_are_a_stable_sort(n, pairs):
+    """sort_hist_kernel + 4 x onesweep_kernel<512, 12>: tile = 6144 keys, ragged last tile, padding keys, look-back chain."""
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 2] &= np.uint32(0x00FF00FF)                      # heavy ties and two constant digits
+        keys[n // 2: n // 2 + 50] = 0xFFFFFFFF                        # real keys equal to the padding key
+    n_max = n + 777
+    k = np.zeros(n_max, dtype=np.uint32)
+    k[:n] = keys
+    k[n:] = 0x12345678                                               # beyond n: must not be touched or read as data
+    v = np.arange(n_max, dtype=np.uint32) if pairs else None
+    assert lib().emu_sort_pairs(k.ctypes.data, v.ctypes.data if pairs else None, n, n_max, 5) == 0
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(k[:n], keys[order])
+    assert (k[n:] == 0x12345678).all()
+    if pairs:
+        np.testing.assert_array_equal(v[:n], order.astype(np.uint32))
+
+
+def test_sorted_frame_through_the_emulated_kernels():
+    """oracle projection -> emulated sort -> emulated ranges -> emulated compositor == the oracle frame."""
+    n, w, h = 15000, 256, 144
+    splat60, vp, ub = make_scene(n, 21, w, h, scale_boost=1.0)
+    u = orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8))
+    fr = orc.frame(splat60, vp, u)
+    pr = orc.project(splat60, vp, u)
+    cap = 10 * n
+    k = np.zeros(cap, dtype=np.uint32)
+    v = np.zeros(cap, dtype=np.uint32)
+    k[: pr.duplicates], v[: pr.duplicates] = pr.keys, pr.values
+    assert lib().emu_sort_pairs(k.ctypes.data, v.ctypes.data, pr.duplicates, cap, 3) == 0
+    np.testing.assert_array_equal(k[: pr.duplicates], fr.keys)
+    np.testing.assert_array_equal(v[: pr.duplicates], fr.values)
+    bounds, _ = emu_ranges(k[: pr.duplicates], fr.bounds.shape[0])
+    np.testing.assert_array_equal(bounds, fr.bounds)
+    out, staged, _, _ = emu_composite(SHIPPED, pr.records, v[: pr.duplicates], bounds, w, h)
+    np.testing.assert_array_equal(bits(out), bits(fr.rgba))
+    assert staged == fr.staged
