@@ -43,7 +43,11 @@ __device__ __forceinline__ void godot_basis_mul(const float a[3][3], const float
 
 __global__ void __launch_bounds__(INGEST_SPLATS) ply_to_soa_kernel(const float *__restrict__ ply, uint32_t nprops, uint64_t count, float creation_time,
                                                                   float4 *__restrict__ soa, uint64_t plane_stride, uint64_t first) {
+#ifndef GSR_CPU_EMU
     extern __shared__ float s_v[];  // [INGEST_SPLATS][nprops]
+#else  // tests/kernel_emu (CPU logic pre-flight): nprops <= 256 (gsr_upload_ply_raw rejects more)
+    __shared__ float s_v[INGEST_SPLATS * 256];
+#endif
     const uint64_t s0 = (uint64_t)blockIdx.x * INGEST_SPLATS;
     const uint32_t here = (uint32_t)((count - s0) < (uint64_t)INGEST_SPLATS ? (count - s0) : INGEST_SPLATS);
     const float *src = ply + s0 * nprops;
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(256) pack_rgb_kernel(const float4 *__restrict_
 
 }  // namespace
 
+#ifndef GSR_CPU_EMU  // host side: CUDA only
 int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
                       cudaStream_t stream) {
     if (count == 0) return GSR_OK;
@@ -132,5 +137,6 @@ int launch_aos_to_soa(const float4 *aos, uint64_t count, float4 *soa, uint64_t p
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
+#endif  // GSR_CPU_EMU
 
 }  // namespace gsr

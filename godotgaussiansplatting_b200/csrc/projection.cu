@@ -13,6 +13,8 @@
 //     feeds it to indirect dispatches (:210-214).
 // The arithmetic follows the "gsr deterministic math" contract (common.cuh): this file is compiled with
 // -fmad=false, every operator below is one IEEE binary32 operation in GLSL parse order.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -81,6 +83,7 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsign
 }
 
 // ---- TMA (bulk async copy) + mbarrier helpers: SASS UBLKCP / SYNCS ----
+#ifndef GSR_CPU_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -103,6 +106,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      : "memory");
     } while (!ok);
 }
+#else  // tests/kernel_emu (CPU logic pre-flight): a bulk copy completes at once, so the barrier protocol is a no-op
+inline void mbar_init(uint64_t *, uint32_t) {}
+inline void fence_mbar_init() {}
+inline void mbar_expect_tx(uint64_t *, uint32_t) {}
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+inline void mbar_wait(uint64_t *, uint32_t) {}
+#endif
 
 // SH colour (gsplat_projection.glsl:94-121), streamed six planes (= 8 coefficients x RGB) at a time so that at
 // most 24 coefficient registers are live.  `src[k * stride]` is SH plane k of this splat (shared slab or global).
@@ -315,7 +325,11 @@ constexpr size_t PROJ_SLAB_BYTES = sizeof(float4) * NUM_PLANES * 32;            
 constexpr size_t PROJ_SMEM_BYTES = PROJ_SLAB_BYTES * PROJ_WARPS;                // 61440 B per CTA
 
 __global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_kernel(const __grid_constant__ ProjectionArgs a) {
+#ifndef GSR_CPU_EMU
     extern __shared__ __align__(128) unsigned char proj_smem[];
+#else
+    __shared__ __align__(128) unsigned char proj_smem[PROJ_SMEM_BYTES];
+#endif
     __shared__ uint32_t s_bid;
     __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS][2];
     __shared__ uint32_t s_wtotal[PROJ_WARPS];   // duplicate count of each warp
@@ -533,7 +547,11 @@ constexpr int SH_SPLATS = SH_GROUPS * PROJ_THREADS;  // 1024 splats per CTA = on
 constexpr size_t SH_SLAB_BYTES = sizeof(float4) * 3 * SH_SPLATS;  // planes 0..2 of the CTA's splats: [group][warp][plane][lane]
 
 __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(const __grid_constant__ ProjectionArgs a) {
+#ifndef GSR_CPU_EMU
     extern __shared__ __align__(128) unsigned char proj_smem[];
+#else
+    __shared__ __align__(128) unsigned char proj_smem[SH_SLAB_BYTES];
+#endif
     __shared__ uint4 s_res[SH_SPLATS];      // (n, x0|y0<<16, w|depth<<16, last_tile) per splat slot
     __shared__ uint16_t s_list[SH_SPLATS];  // slots of the surviving splats
     __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS];
@@ -698,6 +716,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
 
 uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_THREADS - 1) / PROJ_THREADS; }
 
+#ifndef GSR_CPU_EMU  // host side: CUDA only
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     const uint32_t blocks = projection_num_blocks(a.num_splats);
     if (blocks == 0) return GSR_OK;
@@ -725,5 +744,6 @@ int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
+#endif  // GSR_CPU_EMU
 
 }  // namespace gsr

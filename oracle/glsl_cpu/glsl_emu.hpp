@@ -348,7 +348,7 @@ template <> struct layout_of<mat4> { static constexpr size_t align = 16, size = 
 /* invocation scheduler                                                                           */
 /* ---------------------------------------------------------------------------------------------- */
 enum { EMU_SUBGROUP_WIDTH = 32 };
-enum inv_state { INV_READY, INV_AT_BARRIER, INV_AT_SUBGROUP, INV_DONE };
+enum inv_state { INV_READY, INV_AT_BARRIER, INV_AT_SUBGROUP, INV_DONE, INV_YIELD };
 
 #if defined(__x86_64__) && !defined(GLSL_EMU_UCONTEXT)
 #define GLSL_EMU_FAST_SWITCH 1
@@ -374,6 +374,7 @@ struct invocation {
     /* subgroup collective exchange */
     uint sg_in, sg_sum, sg_excl, sg_ballot;
     uint sg_vals[32]; /* every participant's sg_in (0 for non-participants): lane shuffles of the CUDA shim */
+    uint sg_part;     /* participation mask of the last collective */
     bool sg_first;
 };
 
@@ -402,6 +403,8 @@ inline void yield_to_scheduler() { scheduler& s = sched(); swapcontext(&s.cur->c
 inline void resume(scheduler& s, invocation& v) { s.cur = &v; swapcontext(&s.main_ctx, &v.ctx); }
 #endif
 inline void barrier() { sched().cur->state = INV_AT_BARRIER; yield_to_scheduler(); }
+/* a spin-wait iteration (CUDA shim: __nanosleep): the invocation stays runnable, everybody else gets a turn first */
+inline void spin_yield() { sched().cur->state = INV_YIELD; yield_to_scheduler(); }
 inline void subgroup_collective(uint v) {
     invocation* me = sched().cur;
     me->sg_in = v;
@@ -463,14 +466,22 @@ inline void run_workgroup(uvec3 group, uvec3 local_size, void (*body)(void*), vo
         makecontext(&v.ctx, fiber_entry, 0);
 #endif
     }
+    unsigned long stuck = 0;
     for (;;) {
+        bool progressed = false;
         for (uint sg = 0; sg < nsub; ++sg) {
             const size_t lo = size_t(sg) * EMU_SUBGROUP_WIDTH, hi = (lo + EMU_SUBGROUP_WIDTH < n) ? lo + EMU_SUBGROUP_WIDTH : n;
             for (;;) {
+                bool spinning = false;
                 for (size_t i = lo; i < hi; ++i)
-                    if (s.inv[i].state == INV_READY) resume(s, s.inv[i]);
+                    if (s.inv[i].state == INV_READY) {
+                        resume(s, s.inv[i]);
+                        if (s.inv[i].state == INV_YIELD) spinning = true; else progressed = true;
+                    }
+                /* a spinning invocation may still join the collective its subgroup is waiting in: come back later */
+                if (spinning) break;
                 /* everyone in the subgroup is now blocked or done: resolve a pending collective */
-                uint sum = 0, ballot = 0; bool any_waiting = false, first_seen = false;
+                uint sum = 0, ballot = 0, part = 0; bool any_waiting = false, first_seen = false;
                 uint vals[32] = {0};
                 for (size_t i = lo; i < hi; ++i) {
                     invocation& v = s.inv[i];
@@ -478,24 +489,36 @@ inline void run_workgroup(uvec3 group, uvec3 local_size, void (*body)(void*), vo
                     any_waiting = true;
                     v.sg_excl = sum;
                     vals[i - lo] = v.sg_in;
+                    part |= 1u << (i - lo);
                     sum += v.sg_in;
                     if (v.sg_in) ballot |= 1u << (i - lo);
                     v.sg_first = !first_seen;
                     first_seen = true;
                 }
                 if (!any_waiting) break;
+                progressed = true;
                 for (size_t i = lo; i < hi; ++i) {
                     invocation& v = s.inv[i];
                     if (v.state != INV_AT_SUBGROUP) continue;
-                    v.sg_sum = sum; v.sg_ballot = ballot; v.state = INV_READY;
+                    v.sg_sum = sum; v.sg_ballot = ballot; v.sg_part = part; v.state = INV_READY;
                     std::memcpy(v.sg_vals, vals, sizeof vals);
                 }
             }
         }
-        bool all_done = true;
-        for (size_t i = 0; i < n; ++i)
-            if (s.inv[i].state == INV_AT_BARRIER) { s.inv[i].state = INV_READY; all_done = false; }
-        if (all_done) break;
+        bool runnable = false, at_barrier = false;
+        for (size_t i = 0; i < n; ++i) {
+            if (s.inv[i].state == INV_YIELD) { s.inv[i].state = INV_READY; runnable = true; }
+            else if (s.inv[i].state == INV_READY || s.inv[i].state == INV_AT_SUBGROUP) runnable = true;
+            else if (s.inv[i].state == INV_AT_BARRIER) at_barrier = true;
+        }
+        if (!runnable) {
+            if (!at_barrier) break; /* everybody is done */
+            for (size_t i = 0; i < n; ++i)
+                if (s.inv[i].state == INV_AT_BARRIER) s.inv[i].state = INV_READY;
+            progressed = true;
+        }
+        if (progressed) stuck = 0;
+        else if (++stuck > 1000000ul) { std::fprintf(stderr, "glsl_emu: no invocation makes progress (a spin-wait that nobody satisfies)\n"); std::abort(); }
     }
     s.cur = nullptr;
 }

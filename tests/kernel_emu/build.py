@@ -1,4 +1,4 @@
-"""Build tests/kernel_emu/libkernel_emu.so: csrc/radix_sort.cu, csrc/ranges.cu and csrc/compositor.cu compiled by g++ for the CPU (see cuda_shim.h).
+"""Build tests/kernel_emu/libkernel_emu.so: every kernel file of csrc/ (ingest, projection, radix_sort, ranges, compositor) compiled by g++ for the CPU (see cuda_shim.h).
 TEST INFRASTRUCTURE; needs only the CUDA headers (no GPU, no nvcc)."""
 from __future__ import annotations
 
@@ -15,6 +15,8 @@ DEPS = [os.path.join(HERE, f) for f in ("kernel_emu.cpp", "cuda_shim.h", "build.
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "compositor.cu"),
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "ranges.cu"),
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "radix_sort.cu"),
+    os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "projection.cu"),
+    os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "ingest.cu"),
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "common.cuh"),
 ]
 

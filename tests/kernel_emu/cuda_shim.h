@@ -59,14 +59,24 @@ inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned delta) {
     auto *c = ::glsl::sched().cur;
     return c->sg_invocation >= delta ? c->sg_vals[c->sg_invocation - delta] : v;
 }
+inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { ::glsl::subgroup_collective(v); auto *c = ::glsl::sched().cur; return c->sg_vals[(c->sg_invocation ^ (unsigned)m) & 31]; }
+inline unsigned long long __shfl_xor_sync(unsigned mk, unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(mk, (unsigned)v, m), hi = __shfl_xor_sync(mk, (unsigned)(v >> 32), m);
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+inline int __reduce_max_sync(unsigned, int v) {
+    ::glsl::subgroup_collective((unsigned)v);
+    auto *c = ::glsl::sched().cur;
+    int m = v;
+    for (int i = 0; i < 32; ++i) if (c->sg_part & (1u << i)) { const int x = (int)c->sg_vals[i]; m = x > m ? x : m; }
+    return m;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
-inline void __nanosleep(unsigned) {
-    fprintf(stderr, "kernel_emu: a thread waits for another block -- impossible with the single block this harness runs\n");
-    abort();
-}
+inline void __nanosleep(unsigned) { ::glsl::spin_yield(); }   /* a spin-wait iteration: let everybody else run first (the scheduler
+                                                                  aborts if nobody ever satisfies the wait) */
 
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }

@@ -1,4 +1,5 @@
-// kernel_emu.cpp -- libgsr's sort, tile-range and compositor kernels (csrc/radix_sort.cu, ranges.cu, compositor.cu) compiled for the CPU.
+// kernel_emu.cpp -- libgsr's projection, sort, tile-range and compositor kernels (csrc/projection.cu, radix_sort.cu, ranges.cu,
+// compositor.cu) compiled for the CPU.
 // TEST INFRASTRUCTURE: see cuda_shim.h.  Built by tests/kernel_emu/build.py into tests/kernel_emu/libkernel_emu.so.
 #define GSR_CPU_EMU 1
 #include "cuda_shim.h"
@@ -9,6 +10,8 @@ namespace gsr { void set_last_error(const char *, ...) {} }
 #include "../../godotgaussiansplatting_b200/csrc/compositor.cu"
 #include "../../godotgaussiansplatting_b200/csrc/ranges.cu"
 #include "../../godotgaussiansplatting_b200/csrc/radix_sort.cu"
+#include "../../godotgaussiansplatting_b200/csrc/projection.cu"
+#include "../../godotgaussiansplatting_b200/csrc/ingest.cu"
 
 namespace {
 struct Launch { const gsr::CompositeArgs *args; int variant; };
@@ -141,5 +144,101 @@ extern "C" int emu_sort_pairs(uint32_t *keys, uint32_t *values, uint32_t n, uint
     }
     cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
     free(hist); free(status); free(alt_k); free(alt_v);
+    return 0;
+}
+
+// ---- csrc/projection.cu: blocks run one after another; each takes its scan position from the ticket, so a look-back always finds
+//      its predecessors published.  Inside a block the warps meet through shared-memory flags (spin-waits yield to the scheduler). ----
+namespace {
+void projection_body(void *p) { gsr::projection_kernel(*static_cast<const gsr::ProjectionArgs *>(p)); }
+void projection_sharded_body(void *p) { gsr::projection_sharded_kernel(*static_cast<const gsr::ProjectionArgs *>(p)); }
+}  // namespace
+
+// soa: 15 planes x plane_stride float4 (the library's SoA layout); vp: 32 floats; uniforms32: the 32-byte block.
+// Per-frame constants are derived exactly like render_enqueue() in gsr_api.cu.  Returns M; outputs like the library's buffers.
+extern "C" long long emu_projection(const void *soa, unsigned long long plane_stride, unsigned num_splats, const float *vp, const void *uniforms32,
+                                    int band_y0, int band_y1, int row_mod, int row_rem, int fast_reject, int sh_bulk_min, void *records,
+                                    uint32_t *keys, uint32_t *values, unsigned capacity, unsigned *visible_out, int *last_tile_out, unsigned *overflow_out) {
+    gsr::ProjectionArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.soa = static_cast<const float4 *>(soa); pa.plane_stride = plane_stride; pa.num_splats = num_splats;
+    memcpy(pa.vp, vp, sizeof pa.vp);
+    memcpy(&pa.u, uniforms32, sizeof pa.u);
+    {
+        const float tfi0 = vp[16 + 0], tfi1 = vp[16 + 5];
+        const volatile float hw = (float)pa.u.dims[0] * 0.5f, hh = (float)pa.u.dims[1] * 0.5f;
+        const volatile float f0 = hw * tfi0, f1 = hh * tfi1;
+        const volatile float t0 = 1.0f / tfi0, t1 = 1.0f / tfi1;
+        const volatile float n0 = -t0, n1 = -t1;
+        pa.focal_base[0] = f0; pa.focal_base[1] = f1;
+        pa.lim_lo[0] = n0 * 1.3f; pa.lim_lo[1] = n1 * 1.3f;
+        pa.lim_hi[0] = t0 * 1.3f; pa.lim_hi[1] = t1 * 1.3f;
+    }
+    const bool fast = row_mod > 1;
+    pa.band_y0 = band_y0; pa.band_y1 = band_y1; pa.row_mod = row_mod; pa.row_rem = row_rem;
+    pa.fast_reject = (fast_reject && fast) ? 1 : 0;
+    pa.fast_mode = fast ? 1 : 0;
+    pa.sh_bulk_min = sh_bulk_min > 0 ? sh_bulk_min : (fast ? 1 : 12);
+    {
+        float g[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) { g[i][j] = 0.0f; for (int r = 0; r < 3; ++r) g[i][j] += vp[4 * i + r] * vp[4 * j + r]; }
+        float nrm = 0.0f;
+        for (int i = 0; i < 3; ++i) { float row = 0.0f; for (int j = 0; j < 3; ++j) row += g[i][j] < 0.0f ? -g[i][j] : g[i][j]; nrm = row > nrm ? row : nrm; }
+        pa.w_frob2 = nrm * 1.0001f;
+    }
+    gsr::FrameState frame;
+    memset(&frame, 0, sizeof frame);
+    const unsigned per_block = pa.fast_reject ? (unsigned)gsr::SH_SPLATS : (unsigned)gsr::PROJ_THREADS;
+    const unsigned blocks = (num_splats + per_block - 1) / per_block;
+    unsigned long long *lookback = static_cast<unsigned long long *>(calloc(blocks ? blocks : 1, sizeof(unsigned long long)));
+    pa.records = static_cast<float4 *>(records); pa.keys = keys; pa.values = values; pa.capacity = capacity;
+    pa.lookback = lookback; pa.frame = &frame;
+    cuda_emu::g_block_dim = cuda_emu::dim{(unsigned)gsr::PROJ_THREADS, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{blocks, 1, 1};
+    for (unsigned b = 0; b < blocks; ++b)
+        glsl::run_workgroup(glsl::uvec3(b, 0, 0), glsl::uvec3((unsigned)gsr::PROJ_THREADS, 1, 1), pa.fast_reject ? &projection_sharded_body : &projection_body, &pa);
+    cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
+    free(lookback);
+    if (visible_out) *visible_out = frame.visible;
+    if (last_tile_out) *last_tile_out = frame.last_tile_plus1 - 1;
+    if (overflow_out) *overflow_out = frame.overflow;
+    return (long long)frame.dup_total;
+}
+
+// ---- csrc/ingest.cu ----
+namespace {
+struct AosLaunch { const float4 *aos; uint64_t count; float4 *soa; uint64_t stride, first; };
+void aos_body(void *p) { const AosLaunch *l = static_cast<const AosLaunch *>(p); gsr::aos_to_soa_kernel(l->aos, l->count, l->soa, l->stride, l->first); }
+struct PlyLaunch { const float *ply; uint32_t nprops; uint64_t count; float creation; float4 *soa; uint64_t stride, first; };
+void ply_body(void *p) { const PlyLaunch *l = static_cast<const PlyLaunch *>(p); gsr::ply_to_soa_kernel(l->ply, l->nprops, l->count, l->creation, l->soa, l->stride, l->first); }
+struct PackLaunch { const float4 *rgba; float4 *rgb; uint64_t quads, pixels; };
+void pack_body(void *p) { const PackLaunch *l = static_cast<const PackLaunch *>(p); gsr::pack_rgb_kernel(l->rgba, l->rgb, l->quads, l->pixels); }
+void run_blocks(unsigned blocks, unsigned threads, void (*body)(void *), void *arg) {
+    cuda_emu::g_block_dim = cuda_emu::dim{threads, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{blocks, 1, 1};
+    for (unsigned b = 0; b < blocks; ++b) glsl::run_workgroup(glsl::uvec3(b, 0, 0), glsl::uvec3(threads, 1, 1), body, arg);
+    cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
+}
+}  // namespace
+
+extern "C" int emu_aos_to_soa(const void *aos60, unsigned long long count, void *soa, unsigned long long plane_stride, unsigned long long first) {
+    AosLaunch l{static_cast<const float4 *>(aos60), count, static_cast<float4 *>(soa), plane_stride, first};
+    run_blocks((unsigned)((count + gsr::SPLATS_PER_BLOCK - 1) / gsr::SPLATS_PER_BLOCK), 256, &aos_body, &l);
+    return 0;
+}
+extern "C" int emu_ply_to_soa(const float *ply, unsigned nprops, unsigned long long count, float creation_time, void *soa,
+                              unsigned long long plane_stride, unsigned long long first) {
+    if (nprops > 256) return 1;
+    PlyLaunch l{ply, nprops, count, creation_time, static_cast<float4 *>(soa), plane_stride, first};
+    run_blocks((unsigned)((count + gsr::INGEST_SPLATS - 1) / gsr::INGEST_SPLATS), (unsigned)gsr::INGEST_SPLATS, &ply_body, &l);
+    return 0;
+}
+extern "C" int emu_pack_rgb(const void *rgba, void *rgb, unsigned long long pixels) {
+    const unsigned long long quads = (pixels + 3) / 4;
+    PackLaunch l{static_cast<const float4 *>(rgba), static_cast<float4 *>(rgb), quads, pixels};
+    run_blocks((unsigned)((quads + 255) / 256), 256, &pack_body, &l);
     return 0;
 }

@@ -1,7 +1,8 @@
-"""libgsr's sort, tile-range and compositor kernels, compiled for the CPU (tests/kernel_emu), against the oracle -- bit for bit.
+"""Every kernel of libgsr (ingest, projection, Onesweep sort, tile ranges, compositor), compiled for the CPU (tests/kernel_emu),
+against the oracle -- bit for bit.
 
 This is NOT a CPU path of the product (libgsr has none; see tests/test_abi.py): it is a pre-flight check of kernel LOGIC.
-csrc/radix_sort.cu, csrc/ranges.cu and csrc/compositor.cu are compiled by g++ under a thin shim of the CUDA execution model (threads = fibers,
+the five kernel files of csrc/ are compiled by g++ under a thin shim of the CUDA execution model (threads = fibers,
 __syncthreads / warp collectives real, __shared__ = block-shared, packed f32x2 PTX = two IEEE binary32 operations), and one
 persistent block works through every tile: staging, blend, tile-stop vote, quantum, spill, re-queue, resume.
 It lets a kernel variant that has never seen a GPU (GSR_COMP_V2) prove its indexing and buffering before GPU minutes are spent.
@@ -38,6 +39,12 @@ def lib():
         L.emu_tile_ranges.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int32, C.c_void_p, C.c_int]
         L.emu_sort_pairs.restype = C.c_int
         L.emu_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.emu_projection.restype = C.c_longlong
+        L.emu_projection.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_uint)]
+        L.emu_aos_to_soa.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong, C.c_ulonglong]
+        L.emu_ply_to_soa.argtypes = [C.c_void_p, C.c_uint, C.c_ulonglong, C.c_float, C.c_void_p, C.c_ulonglong, C.c_ulonglong]
+        L.emu_pack_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong]
         L.emu_band_fixup.restype = C.c_int
         L.emu_band_fixup.argtypes = [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _L = L
@@ -201,3 +208,148 @@ def test_sorted_frame_through_the_emulated_kernels():
     out, staged, _, _ = emu_composite(SHIPPED, pr.records, v[: pr.duplicates], bounds, w, h)
     np.testing.assert_array_equal(bits(out), bits(fr.rgba))
     assert staged == fr.staged
+
+
+# ---------------------------------------------------------------------------------------------------------------- ingest + projection
+def emu_upload(splat60, chunk=None):
+    """gsr_upload_splats_aos: AoS -> 15 SoA planes (stride = n rounded up to 256), optionally in chunks like ply_file.gd:36-71."""
+    splat60 = np.ascontiguousarray(splat60, dtype=np.float32)
+    n = splat60.shape[0]
+    stride = (n + 255) // 256 * 256
+    soa = np.zeros((15, stride, 4), dtype=np.float32)
+    step = chunk or n
+    for first in range(0, n, step):
+        part = np.ascontiguousarray(splat60[first:first + step])
+        lib().emu_aos_to_soa(part.ctypes.data, part.shape[0], soa.ctypes.data, stride, first)
+    return soa, stride
+
+
+def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, fast_reject=0, sh_bulk_min=0, cap=None):
+    gy = (h + 15) // 16
+    y0, y1 = (0, gy) if band is None else band
+    cap = cap or 10 * n
+    rec = np.zeros(n, dtype=orc.RECORD_DTYPE)
+    keys = np.zeros(cap, dtype=np.uint32)
+    vals = np.zeros(cap, dtype=np.uint32)
+    vis, last, ovf = C.c_uint(0), C.c_int(0), C.c_uint(0)
+    vp = np.ascontiguousarray(vp, dtype=np.float32)
+    m = lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, y0, y1, row_mod, row_rem, fast_reject, sh_bulk_min, rec.ctypes.data,
+                             keys.ctypes.data, vals.ctypes.data, cap, C.byref(vis), C.byref(last), C.byref(ovf))
+    return dict(m=int(m), keys=keys[:min(m, cap)], values=vals[:min(m, cap)], records=rec, visible=int(vis.value), last_tile=int(last.value),
+                overflow=bool(ovf.value))
+
+
+def assert_projection_equal(got, pr):
+    assert got["m"] == pr.duplicates and got["visible"] == pr.visible and not got["overflow"]
+    np.testing.assert_array_equal(got["keys"], pr.keys)
+    np.testing.assert_array_equal(got["values"], pr.values)
+    vis = np.unique(pr.values)
+    for f in orc.RECORD_DTYPE.names:
+        np.testing.assert_array_equal(bits(got["records"][f][vis]), bits(pr.records[f][vis]), err_msg=f"record field {f}")
+
+
+@pytest.mark.parametrize("sh_bulk_min", [1, 12, 33], ids=["always_bulk", "default", "never_bulk"])
+def test_projection_kernel(sh_bulk_min):
+    """projection_kernel: TMA-staged planes, chained scan over the CTA links (closer warp + look-back), both SH paths, hybrid emit."""
+    n, w, h = 20000, 320, 208
+    splat60, vp, ub = make_scene(n, 3, w, h, scale_boost=1.0)
+    pr = orc.project(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+    soa, stride = emu_upload(splat60, chunk=777)
+    got = emu_project(soa, stride, n, vp, ub, w, h, sh_bulk_min=sh_bulk_min)
+    assert_projection_equal(got, pr)
+    assert got["last_tile"] == pr.last_tile
+
+
+def test_projection_kernel_edge_sizes_and_overflow():
+    for n in (1, 31, 257, 1000):
+        splat60, vp, ub = make_scene(n, 60 + n, 320, 240, scale_boost=-1.5)
+        pr = orc.project(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+        soa, stride = emu_upload(splat60)
+        assert_projection_equal(emu_project(soa, stride, n, vp, ub, 320, 240), pr)
+    # huge splats: M exceeds the capacity -> overflow flagged, the true M still counted, nothing written past the capacity
+    n = 300
+    splat60, vp, ub = make_scene(n, 5, 640, 480, scale_boost=3.0)
+    pr = orc.project(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=10 * n)
+    assert pr.duplicates > 10 * n
+    soa, stride = emu_upload(splat60)
+    got = emu_project(soa, stride, n, vp, ub, 640, 480, cap=10 * n)
+    assert got["overflow"] and got["m"] == pr.duplicates
+    np.testing.assert_array_equal(got["keys"], pr.keys[: 10 * n])
+
+
+def test_projection_kernel_band_and_cyclic_rows():
+    n, w, h = 12000, 320, 240
+    gx, gy = (w + 15) // 16, (h + 15) // 16
+    splat60, vp, ub = make_scene(n, 8, w, h, scale_boost=1.0)
+    u = orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8))
+    soa, stride = emu_upload(splat60)
+    # contiguous band (gsr_set_band): the oracle's band mode
+    pr = orc.project(splat60, vp, u, band=(4, 9))
+    got = emu_project(soa, stride, n, vp, ub, w, h, band=(4, 9))
+    assert_projection_equal(got, pr)
+    assert got["last_tile"] == pr.last_tile                      # exact sharded mode: the frame-global last tile
+    # cyclic rows (gsr_set_row_interleave), plain and with the conservative reject + 1024-splat compaction kernel:
+    # every rank emits exactly the full frame's pairs of its own rows, in the same (splat-id, row-major) order
+    full = orc.project(splat60, vp, u)
+    rows = (full.keys >> 16) // gx
+    for fast_reject in (0, 1):
+        seen = 0
+        for rem in range(3):
+            got = emu_project(soa, stride, n, vp, ub, w, h, row_mod=3, row_rem=rem, fast_reject=fast_reject)
+            own = rows % 3 == rem
+            np.testing.assert_array_equal(got["keys"], full.keys[own])
+            np.testing.assert_array_equal(got["values"], full.values[own])
+            assert got["last_tile"] == (int((full.keys[own] >> 16).max()) if own.any() else -1)   # LOCAL last tile
+            seen += got["m"]
+        assert seen == full.duplicates
+
+
+def test_ingest_kernels():
+    from godotgaussiansplatting_b200.synthetic import synthetic_ply_table
+    n = 1000
+    table = np.ascontiguousarray(synthetic_ply_table(n, 4), dtype=np.float32)
+    want = orc.preprocess_ply(table, 2.5)                                            # (n, 60): util/ply_file.gd:44-69
+    stride = (n + 255) // 256 * 256
+    soa = np.zeros((15, stride, 4), dtype=np.float32)
+    assert lib().emu_ply_to_soa(table.ctypes.data, table.shape[1], n, 2.5, soa.ctypes.data, stride, 0) == 0
+    got = soa[:, :n, :].transpose(1, 0, 2).reshape(n, 60)
+    np.testing.assert_array_equal(bits(got), bits(want))
+    soa2, _ = emu_upload(want, chunk=130)
+    np.testing.assert_array_equal(bits(soa2), bits(soa))
+    for pixels in (1, 4, 1023, 4096):                                                # RGB32F packing incl. the ragged tail
+        rgba = np.random.default_rng(pixels).random((pixels, 4), dtype=np.float32)
+        rgb = np.zeros(3 * ((pixels + 3) // 4 * 4) + 4, dtype=np.float32)
+        lib().emu_pack_rgb(rgba.ctypes.data, rgb.ctypes.data, pixels)
+        np.testing.assert_array_equal(rgb[: 3 * pixels].reshape(pixels, 3), rgba[:, :3])
+
+
+def test_whole_pipeline_through_the_emulated_kernels():
+    """PLY vertices -> ingest -> projection -> sort -> ranges -> compositor -> RGB packing, every stage the product's kernel code."""
+    from godotgaussiansplatting_b200.synthetic import synthetic_ply_table
+    from godotgaussiansplatting_b200 import camera as cam
+    from tests.scenes import uniforms_bytes
+    n, w, h = 9000, 256, 144
+    table = np.ascontiguousarray(synthetic_ply_table(n, 12), dtype=np.float32)
+    table[:, 55:58] += 1.0
+    c = cam.orbit_camera(40, aspect=w / h)
+    vp = cam.pack_camera_push_constants(c.get_camera_transform(), c.get_camera_projection())
+    ub = uniforms_bytes(c.global_position, 1.0, w, h, 10.0)
+    fr = orc.frame(orc.preprocess_ply(table, 0.0), vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+    stride = (n + 255) // 256 * 256
+    soa = np.zeros((15, stride, 4), dtype=np.float32)
+    lib().emu_ply_to_soa(table.ctypes.data, table.shape[1], n, 0.0, soa.ctypes.data, stride, 0)
+    pj = emu_project(soa, stride, n, vp, ub, w, h)
+    cap = 10 * n
+    k = np.zeros(cap, dtype=np.uint32)
+    v = np.zeros(cap, dtype=np.uint32)
+    k[: pj["m"]], v[: pj["m"]] = pj["keys"], pj["values"]
+    lib().emu_sort_pairs(k.ctypes.data, v.ctypes.data, pj["m"], cap, 4)
+    bounds, _ = emu_ranges(k[: pj["m"]], fr.bounds.shape[0])
+    out, staged, _, _ = emu_composite(SHIPPED, pj["records"], v[: pj["m"]], bounds, w, h)
+    assert pj["m"] == fr.duplicates and staged == fr.staged
+    np.testing.assert_array_equal(k[: pj["m"]], fr.keys)
+    np.testing.assert_array_equal(bounds, fr.bounds)
+    np.testing.assert_array_equal(bits(out), bits(fr.rgba))
+    rgb = np.zeros((h * w * 3 + 4,), dtype=np.float32)
+    lib().emu_pack_rgb(out.ctypes.data, rgb.ctypes.data, w * h)
+    np.testing.assert_array_equal(bits(rgb[: 3 * w * h].reshape(h, w, 3)), bits(fr.rgba[..., :3]))
