@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--splats", type=int, default=int(os.environ.get("GSR_BENCH_SPLATS", "0")), help="debug: override N (marks the line reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-radix", action="store_true")
-    ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["peer", "nccl"],
+    ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["peer", "peerx", "nccl"],
                     help="N>1: 'peer' = compositor stores bands into the root's frame over NVLink peer memory + 4-byte NCCL sync; "
                          "'nccl' = NCCL gather of the band framebuffers")
     return ap.parse_args()
@@ -376,7 +376,8 @@ def main():
             host_chunks.append(blk)
     t_gen = time.perf_counter() - t_gen
     fb = None
-    peer = world > 1 and args.mgpu == "peer"
+    peer = world > 1 and args.mgpu in ("peer", "peerx")
+    peerx = world > 1 and args.mgpu == "peerx"   # EXPERIMENTAL: the per-frame cull is split across the ranks (gsr_shard_*), see below
     sync_flag = torch.zeros(1, dtype=torch.int32, device="cuda") if world > 1 else None
     if peer:
         # fused compositor + gather: the root exports CUDA-IPC handles of its two frames; every rank's compositor then
@@ -392,6 +393,17 @@ def main():
         class _Word:  # the library's int32 "local last occupied tile + 1" word as a torch tensor (all-reduced in place)
             __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (rast.band_sync_word_ptr(), False), "version": 2}
         sync_flag = torch.as_tensor(_Word(), device="cuda")
+        if peerx:
+            # every rank computes the tile-row extents of ITS slice of the splats, one in-place all-gather shares them, and the
+            # projection then only does the maths for the splats whose rows the rank owns (instead of culling all N on every rank)
+            ext_ptr, ext_cap = rast.shard_extents_ptr()
+            ext_slice = ((wl["n"] + world - 1) // world + 255) // 256 * 256
+            assert ext_slice * world <= ext_cap
+
+            class _Ext:
+                __cuda_array_interface__ = {"shape": (ext_slice * world,), "typestr": "<i4", "data": (ext_ptr, False), "version": 2}
+            ext_table = torch.as_tensor(_Ext(), device="cuda")   # the library's uint32 table, viewed as int32 for NCCL
+            rast.shard_use_extents(True)
     elif world > 1:  # NCCL gather needs a torch-visible frame
         fb = torch.zeros((h_pad, W, 4), dtype=torch.float32, device="cuda")
         rast.set_framebuffer_external(fb.data_ptr())
@@ -408,6 +420,9 @@ def main():
         if world == 1:
             rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=e2e and rgb_readback)
         elif peer:
+            if peerx:
+                rast.shard_extents_compute(vp, ub, rank * ext_slice, ext_slice)
+                dist.all_gather_into_tensor(ext_table, ext_table[rank * ext_slice:(rank + 1) * ext_slice])
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # band lands in the root's frame (slot i & 1) over NVLink
             if e2e and rank == 0:
                 rast.stream_join()                                 # previous read-backs done before peers may reuse a slot
@@ -517,7 +532,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": fps,
             "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": N, "width": W, "height": H, "sh_degree": 3,
-                       "parallelism": "single GPU" if world == 1 else (f"cyclic tile rows x{world} (row % {world} == rank), early-reject projection, compositor stores into the root frame over NVLink peer memory + 4-byte NCCL all-reduce" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
+                       "parallelism": "single GPU" if world == 1 else (f"cyclic tile rows x{world} (row % {world} == rank), " + ("cull split across the ranks + all-gathered row extents (experimental)" if peerx else "early-reject projection") + ", compositor stores into the root frame over NVLink peer memory + 4-byte NCCL all-reduce" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
                        "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * N / 1e6),
                        "duplicates_M": M, "visible_V": V, "staged_C": Cc, "reduced": reduced, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),

@@ -157,8 +157,14 @@ struct ProjectionArgs {
     uint32_t capacity;
     unsigned long long *lookback;  // one word per projection CTA (256 splats)
     FrameState *frame;
+    // EXPERIMENTAL (multi-GPU, opt-in, gsr_shard_*): tile-row extent of every splat's un-banded rect, y0 | y1 << 16 (0 = not
+    // visible), computed once per frame by ONE rank per splat slice (launch_extents) and all-gathered by the host; a rank then
+    // runs the projection maths only for the splats whose rows it owns instead of culling all N itself.  nullptr = off.
+    const uint32_t *extents;
 };
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
+// extents[first .. first+count) of the frame described by `a` (band / row ownership fields of `a` are ignored)
+int launch_extents(const ProjectionArgs &a, uint32_t first, uint32_t count, uint32_t *extents, cudaStream_t stream);
 uint32_t projection_num_blocks(uint32_t num_splats);
 
 // sharded: 0 = full frame, 1 = exact sharded mode (global last tile known from the projection), 2 = fast sharded mode

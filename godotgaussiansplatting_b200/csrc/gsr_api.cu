@@ -71,6 +71,8 @@ struct gsr_ctx {
     bool band_set = false;
     int row_mod = 1, row_rem = 0;   // cyclic tile-row ownership (gsr_set_row_interleave): fast sharded mode when row_mod > 1
     int32_t *sync_word = nullptr;   // local (then all-reduced) last occupied tile + 1
+    uint32_t *extents = nullptr;    // EXPERIMENTAL gsr_shard_*: per-splat tile-row extents of the current frame (all ranks' slices)
+    bool use_extents = false;
     cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
     bool ev_valid = false;
     uint32_t last_launches = 0;
@@ -126,6 +128,7 @@ void free_ctx(gsr_ctx *c) {
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->sync_word);
+    cudaFree(c->extents);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); cudaFree(c->trace); cudaFree(c->trace_count);
     if (c->ev) {
         for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -341,6 +344,35 @@ GSR_API int gsr_set_band(gsr_ctx *c, int32_t row_begin, int32_t row_end) {
     return GSR_OK;
 }
 
+// Per-frame constants of the projection (shared by gsr_render and the experimental gsr_shard_extents_compute).
+static void frame_constants(const float *view_proj, const Uniforms &u, ProjectionArgs &pa) {
+    {   // per-frame constants of project_covariance, same IEEE binary32 operations as gsplat_projection.glsl:127-133
+        const float tfi0 = view_proj[16 + 0], tfi1 = view_proj[16 + 5];
+        const volatile float hw = (float)u.dims[0] * 0.5f, hh = (float)u.dims[1] * 0.5f;
+        const volatile float f0 = hw * tfi0, f1 = hh * tfi1;
+        const volatile float t0 = 1.0f / tfi0, t1 = 1.0f / tfi1;
+        const volatile float n0 = -t0, n1 = -t1;
+        pa.focal_base[0] = f0; pa.focal_base[1] = f1;
+        pa.lim_lo[0] = n0 * 1.3f; pa.lim_lo[1] = n1 * 1.3f;
+        pa.lim_hi[0] = t0 * 1.3f; pa.lim_hi[1] = t1 * 1.3f;
+    }
+    {   // |W|_2^2 <= |W^T W|_inf (largest absolute row sum of the Gram matrix); exactly 1 for a rigid camera
+        float g[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                g[i][j] = 0.0f;
+                for (int r = 0; r < 3; ++r) g[i][j] += view_proj[4 * i + r] * view_proj[4 * j + r];
+            }
+        float nrm = 0.0f;
+        for (int i = 0; i < 3; ++i) {
+            float row = 0.0f;
+            for (int j = 0; j < 3; ++j) row += g[i][j] < 0.0f ? -g[i][j] : g[i][j];
+            nrm = row > nrm ? row : nrm;
+        }
+        pa.w_frob2 = nrm * 1.0001f;
+    }
+}
+
 static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float4 *target = nullptr) {
     if (!c || !view_proj || !uniforms32) return GSR_ERR_INVALID;
     if (c->width == 0) { set_last_error("gsr_render before gsr_resize"); return GSR_ERR_STATE; }
@@ -367,16 +399,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
     memcpy(pa.vp, view_proj, sizeof pa.vp);
     pa.u = u;
-    {   // per-frame constants of project_covariance, same IEEE binary32 operations as gsplat_projection.glsl:127-133
-        const float tfi0 = view_proj[16 + 0], tfi1 = view_proj[16 + 5];
-        const volatile float hw = (float)u.dims[0] * 0.5f, hh = (float)u.dims[1] * 0.5f;
-        const volatile float f0 = hw * tfi0, f1 = hh * tfi1;
-        const volatile float t0 = 1.0f / tfi0, t1 = 1.0f / tfi1;
-        const volatile float n0 = -t0, n1 = -t1;
-        pa.focal_base[0] = f0; pa.focal_base[1] = f1;
-        pa.lim_lo[0] = n0 * 1.3f; pa.lim_lo[1] = n1 * 1.3f;
-        pa.lim_hi[0] = t0 * 1.3f; pa.lim_hi[1] = t1 * 1.3f;
-    }
+    frame_constants(view_proj, u, pa);
     const bool fast = c->row_mod > 1;
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
     pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
@@ -391,23 +414,9 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     // this rank's rows and the latency-bound gather path was measured slower than fetching the whole 6 KB slice (0.60 vs 0.46 ms)
     static const int bulk_env = getenv("GSR_SH_BULK_MIN") ? atoi(getenv("GSR_SH_BULK_MIN")) : 0;
     pa.sh_bulk_min = bulk_env > 0 ? bulk_env : (fast ? 1 : 12);
-    {   // |W|_2^2 <= |W^T W|_inf (largest absolute row sum of the Gram matrix); exactly 1 for a rigid camera
-        float g[3][3];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                g[i][j] = 0.0f;
-                for (int r = 0; r < 3; ++r) g[i][j] += view_proj[4 * i + r] * view_proj[4 * j + r];
-            }
-        float nrm = 0.0f;
-        for (int i = 0; i < 3; ++i) {
-            float row = 0.0f;
-            for (int j = 0; j < 3; ++j) row += g[i][j] < 0.0f ? -g[i][j] : g[i][j];
-            nrm = row > nrm ? row : nrm;
-        }
-        pa.w_frob2 = nrm * 1.0001f;
-    }
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
+    pa.extents = (c->use_extents && fast && c->extents) ? c->extents : nullptr;
     if ((rc = launch_projection(pa, s))) return rc;
     launches += pa.num_splats ? 1 : 0;
     GSR_CUDA_TRY(cudaEventRecord(ev[1], s));  // 'Projection'
@@ -556,6 +565,50 @@ GSR_API int gsr_peer_import_framebuffers(gsr_ctx *c, const void *handles128) {
     GSR_CUDA_TRY(cudaIpcOpenMemHandle((void **)&c->peer_fb[0], h[0], cudaIpcMemLazyEnablePeerAccess));
     GSR_CUDA_TRY(cudaIpcOpenMemHandle((void **)&c->peer_fb[1], h[1], cudaIpcMemLazyEnablePeerAccess));
     c->peer_mode = true; c->peer_opened = true;
+    return GSR_OK;
+}
+
+// ---- EXPERIMENTAL (multi-GPU, opt-in): split the per-frame cull across the ranks.  Every rank computes the tile-row extents of
+//      ITS slice of the splats (gsr_shard_extents_compute), the host all-gathers the slices in place (NCCL on
+//      gsr_shard_extents_ptr), and gsr_render then runs the projection maths only for the splats whose rows this rank owns
+//      (gsr_shard_use_extents(1); needs gsr_set_row_interleave).  Exact: same rects, same emission order.
+GSR_API void *gsr_shard_extents_ptr(gsr_ctx *c, uint64_t *capacity_out) {
+    if (!c) return nullptr;
+    const uint64_t cap = ((c->max_splats + 255ull) / 256ull + 64ull) * 256ull;   // room for up to 64 ranks' 256-aligned slices
+    if (!c->extents) {
+        if (use_device(c->device)) return nullptr;
+        if (cudaMalloc((void **)&c->extents, sizeof(uint32_t) * cap) != cudaSuccess) { set_last_error("cudaMalloc(extents) failed"); c->extents = nullptr; return nullptr; }
+        cudaMemsetAsync(c->extents, 0, sizeof(uint32_t) * cap, c->stream);
+    }
+    if (capacity_out) *capacity_out = cap;
+    return c->extents;
+}
+
+GSR_API int gsr_shard_extents_compute(gsr_ctx *c, const float view_proj[32], const void *uniforms32, uint64_t first, uint64_t count) {
+    if (!c || !view_proj || !uniforms32) return GSR_ERR_INVALID;
+    if (c->width == 0) { set_last_error("gsr_shard_extents_compute before gsr_resize"); return GSR_ERR_STATE; }
+    uint64_t cap = 0;
+    if (!gsr_shard_extents_ptr(c, &cap)) return GSR_ERR_OOM;
+    if (count > cap || first > cap - count) { set_last_error("extent slice [%llu,%llu) exceeds the table (%llu)", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)cap); return GSR_ERR_INVALID; }
+    Uniforms u;
+    memcpy(&u, uniforms32, sizeof u);
+    if (u.dims[0] != c->width || u.dims[1] != c->height) { set_last_error("uniform dims %dx%d differ from gsr_resize %dx%d", u.dims[0], u.dims[1], c->width, c->height); return GSR_ERR_INVALID; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    ProjectionArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
+    memcpy(pa.vp, view_proj, sizeof pa.vp);
+    pa.u = u;
+    frame_constants(view_proj, u, pa);
+    pa.sh_bulk_min = 12;
+    return launch_extents(pa, (uint32_t)first, (uint32_t)count, c->extents, c->stream);
+}
+
+GSR_API int gsr_shard_use_extents(gsr_ctx *c, int enable) {
+    if (!c) return GSR_ERR_INVALID;
+    if (enable && !c->extents) { set_last_error("gsr_shard_use_extents before gsr_shard_extents_ptr / _compute"); return GSR_ERR_STATE; }
+    c->use_extents = enable != 0;
     return GSR_OK;
 }
 

@@ -546,6 +546,17 @@ constexpr int SH_GROUPS = 4;
 constexpr int SH_SPLATS = SH_GROUPS * PROJ_THREADS;  // 1024 splats per CTA = one link of the chained scan
 constexpr size_t SH_SLAB_BYTES = sizeof(float4) * 3 * SH_SPLATS;  // planes 0..2 of the CTA's splats: [group][warp][plane][lane]
 
+// TABLE (experimental, a.extents != nullptr): the quick pass is a lookup in the frame's all-gathered row-extent table instead of
+// the cull + conservative test -- no plane is staged up front, the survivors' planes 0..2 are gathered in the dense pass.
+__device__ __forceinline__ bool extent_owned(uint32_t e, const ProjectionArgs &a) {   // does a row of [y0, y1) belong to this context?
+    int32_t y0 = (int32_t)(e & 0xFFFFu), y1 = (int32_t)(e >> 16);
+    if (y0 < a.band_y0) y0 = a.band_y0;
+    if (y1 > a.band_y1) y1 = a.band_y1;
+    if (y1 <= y0) return false;
+    return y0 + ((a.row_rem - y0 % a.row_mod) + a.row_mod) % a.row_mod < y1;
+}
+
+template <bool TABLE>
 __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(const __grid_constant__ ProjectionArgs a) {
 #ifndef GSR_CPU_EMU
     extern __shared__ __align__(128) unsigned char proj_smem[];
@@ -574,7 +585,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
     const uint32_t gx = (uint32_t)((a.u.dims[0] + TILE - 1) / TILE);
 
     // ---- TMA: planes 0..2 of the warp's four 32-splat slices (12 x 512 B onto the warp's mbarrier) ----
-    if (lane == 0) {
+    if (!TABLE && lane == 0) {
         mbar_expect_tx(&s_bar[warp], 12u * 512u);
 #pragma unroll
         for (int g = 0; g < SH_GROUPS; ++g)
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
                 bulk_g2s(slab + ((g * PROJ_WARPS + warp) * 3u + k) * 32u, a.soa + (uint64_t)k * a.plane_stride + base_id + g * PROJ_THREADS + warp * 32u,
                          512u, &s_bar[warp]);
     }
-    mbar_wait(&s_bar[warp], 0);
+    if (!TABLE) mbar_wait(&s_bar[warp], 0);
 
     // ---- quick pass: cull + conservative row test, CTA-wide compaction of the survivors ----
 #pragma unroll
@@ -591,6 +602,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
         const uint32_t slot = g * PROJ_THREADS + tid;
         bool live = false;
         LaneOut q;
+        if (TABLE) {
+            if (base_id + slot < a.num_splats) live = extent_owned(__ldg(a.extents + base_id + slot), a);
+        } else
         if (base_id + slot < a.num_splats) live = project_lane<true>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), q);
         const uint32_t lmask = __ballot_sync(0xffffffffu, live);
         uint32_t wbase = 0;
@@ -606,7 +620,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
         const uint32_t slot = s_list[it];
         const uint32_t gid = base_id + slot;
         LaneOut o;
-        if (project_lane<false>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), o) && o.n) {
+        bool hit;
+        if (TABLE) hit = project_lane<false>(a, __ldg(a.soa + gid), __ldg(a.soa + a.plane_stride + gid), __ldg(a.soa + 2ull * a.plane_stride + gid), o);
+        else hit = project_lane<false>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), o);
+        if (hit && o.n) {
             float col[3];
             sh_color<false>(a.soa + 3ull * a.plane_stride + gid, a.plane_stride, o.vx, o.vy, o.vz, col);
             float4 *rec = a.records + (uint64_t)gid * 3u;
@@ -712,24 +729,53 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
     }
 }
 
+// EXPERIMENTAL (gsr_shard_extents_compute): tile-row extent of the un-banded rect of splats [first, first + count) -- the exact
+// rect of gsplat_projection.glsl:144-148,191 (same project_lane), y0 | y1 << 16, 0 when the splat emits nothing.  `a` must
+// describe the FULL frame (band = all rows, row_mod = 1, no reject): launch_extents() prepares that copy.
+__global__ void __launch_bounds__(PROJ_THREADS) extent_kernel(const __grid_constant__ ProjectionArgs a, uint32_t first, uint32_t count,
+                                                              uint32_t *__restrict__ extents) {
+    const uint32_t i = blockIdx.x * PROJ_THREADS + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t id = first + i;
+    uint32_t e = 0u;
+    if (id < a.num_splats) {
+        LaneOut o;
+        if (project_lane<false>(a, __ldg(a.soa + id), __ldg(a.soa + a.plane_stride + id), __ldg(a.soa + 2ull * a.plane_stride + id), o) && o.n)
+            e = o.y0 | ((o.y0 + o.n / o.w) << 16);
+    }
+    extents[id] = e;
+}
+
 }  // namespace
 
 uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_THREADS - 1) / PROJ_THREADS; }
 
 #ifndef GSR_CPU_EMU  // host side: CUDA only
+int launch_extents(const ProjectionArgs &frame_args, uint32_t first, uint32_t count, uint32_t *extents, cudaStream_t stream) {
+    if (count == 0) return GSR_OK;
+    ProjectionArgs a = frame_args;   // the whole frame: no band, no row ownership, no reject
+    a.band_y0 = 0; a.band_y1 = (a.u.dims[1] + TILE - 1) / TILE;
+    a.row_mod = 1; a.row_rem = 0; a.fast_reject = 0; a.fast_mode = 0; a.extents = nullptr;
+    extent_kernel<<<(count + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, stream>>>(a, first, count, extents);
+    GSR_CUDA_TRY(cudaGetLastError());
+    return GSR_OK;
+}
+
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     const uint32_t blocks = projection_num_blocks(a.num_splats);
     if (blocks == 0) return GSR_OK;
-    if (a.fast_reject) {  // sharded variant: 1024 splats per CTA
+    if (a.fast_reject || a.extents) {  // sharded variant: 1024 splats per CTA
         static int sh_dev = -1;
         int d = 0;
         GSR_CUDA_TRY(cudaGetDevice(&d));
         if (sh_dev != d) {
-            GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
+            GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
+            GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
             sh_dev = d;
         }
         const uint32_t sblocks = (a.num_splats + SH_SPLATS - 1) / SH_SPLATS;
-        projection_sharded_kernel<<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
+        if (a.extents) projection_sharded_kernel<true><<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
+        else projection_sharded_kernel<false><<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
         GSR_CUDA_TRY(cudaGetLastError());
         return GSR_OK;
     }

@@ -225,6 +225,22 @@ class GaussianSplattingRasterizer:
         buf = (C.c_ubyte * 128).from_buffer_copy(handles)
         _lib.check(_lib.lib().gsr_peer_import_framebuffers(self._ctx, buf), "gsr_peer_import_framebuffers")
 
+    # ---- EXPERIMENTAL multi-GPU: split the per-frame cull across the ranks (include/gsr.h gsr_shard_*) ----
+    def shard_extents_ptr(self):
+        cap = C.c_uint64(0)
+        ptr = _lib.lib().gsr_shard_extents_ptr(self._ctx, C.byref(cap))
+        if not ptr:
+            raise RuntimeError("gsr_shard_extents_ptr: " + _lib.lib().gsr_last_error().decode())
+        return int(ptr), int(cap.value)
+
+    def shard_extents_compute(self, vp32, uniforms32: bytes, first: int, count: int) -> None:
+        vp = np.ascontiguousarray(vp32, dtype=np.float32)
+        _lib.check(_lib.lib().gsr_shard_extents_compute(self._ctx, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms32, int(first), int(count)),
+                   "gsr_shard_extents_compute")
+
+    def shard_use_extents(self, enable: bool) -> None:
+        _lib.check(_lib.lib().gsr_shard_use_extents(self._ctx, int(bool(enable))), "gsr_shard_use_extents")
+
     def stream_join(self) -> None:
         """Make the render stream wait for the pipelined read-back copies enqueued so far."""
         _lib.check(_lib.lib().gsr_stream_join(self._ctx), "gsr_stream_join")

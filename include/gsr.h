@@ -169,6 +169,16 @@ GSR_API int gsr_render_async_rgb(gsr_ctx *ctx, const float view_proj[32], const 
  * after everything enqueued on the render stream so far (multi-GPU: after the per-frame completion sync). */
 GSR_API int gsr_readback_async(gsr_ctx *ctx, float *pinned_host, int rgb_only);
 GSR_API int gsr_stream_join(gsr_ctx *ctx);
+
+/* ---- EXPERIMENTAL (multi-GPU, opt-in; no reference counterpart -- the reference is single-device): split the per-frame cull
+ *      across the ranks instead of replicating it.  Per frame: every rank computes the tile-row extents (y0 | y1 << 16 of the
+ *      exact, un-banded rect of gsplat_projection.glsl:144-148; 0 = emits nothing) of ITS slice of the splats; the host
+ *      all-gathers the slices in place over NCCL (the table lives at gsr_shard_extents_ptr, `*capacity_out` uint32 entries,
+ *      enough for 64 ranks' 256-aligned slices); gsr_render then runs the projection maths only for the splats whose rows this
+ *      rank owns (gsr_shard_use_extents(ctx, 1); requires gsr_set_row_interleave).  Same rects, same emission order. ---- */
+GSR_API void *gsr_shard_extents_ptr(gsr_ctx *ctx, uint64_t *capacity_out);
+GSR_API int gsr_shard_extents_compute(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, uint64_t first, uint64_t count);
+GSR_API int gsr_shard_use_extents(gsr_ctx *ctx, int enable);
 GSR_API int gsr_sync(gsr_ctx *ctx);
 
 /* Device pointer of the RGBA32F frame (render_texture.texture_rd_rid, rasterizer.gd:48,101); row-major W*H. */

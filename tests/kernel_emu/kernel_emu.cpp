@@ -149,16 +149,20 @@ extern "C" int emu_sort_pairs(uint32_t *keys, uint32_t *values, uint32_t n, uint
 
 // ---- csrc/projection.cu: blocks run one after another; each takes its scan position from the ticket, so a look-back always finds
 //      its predecessors published.  Inside a block the warps meet through shared-memory flags (spin-waits yield to the scheduler). ----
+namespace { void run_blocks(unsigned blocks, unsigned threads, void (*body)(void *), void *arg); }
 namespace {
 void projection_body(void *p) { gsr::projection_kernel(*static_cast<const gsr::ProjectionArgs *>(p)); }
-void projection_sharded_body(void *p) { gsr::projection_sharded_kernel(*static_cast<const gsr::ProjectionArgs *>(p)); }
+void projection_sharded_body(void *p) { gsr::projection_sharded_kernel<false>(*static_cast<const gsr::ProjectionArgs *>(p)); }
+void projection_table_body(void *p) { gsr::projection_sharded_kernel<true>(*static_cast<const gsr::ProjectionArgs *>(p)); }
 }  // namespace
 
 // soa: 15 planes x plane_stride float4 (the library's SoA layout); vp: 32 floats; uniforms32: the 32-byte block.
 // Per-frame constants are derived exactly like render_enqueue() in gsr_api.cu.  Returns M; outputs like the library's buffers.
 extern "C" long long emu_projection(const void *soa, unsigned long long plane_stride, unsigned num_splats, const float *vp, const void *uniforms32,
                                     int band_y0, int band_y1, int row_mod, int row_rem, int fast_reject, int sh_bulk_min, void *records,
-                                    uint32_t *keys, uint32_t *values, unsigned capacity, unsigned *visible_out, int *last_tile_out, unsigned *overflow_out) {
+                                    uint32_t *keys, uint32_t *values, unsigned capacity, unsigned *visible_out, int *last_tile_out, unsigned *overflow_out,
+                                    const uint32_t *extents /* nullable: gsr_shard_use_extents */, uint32_t *extents_out /* nullable: ONLY compute
+                                    the extents of [ext_first, ext_first + ext_count), like gsr_shard_extents_compute */, unsigned ext_first, unsigned ext_count) {
     gsr::ProjectionArgs pa;
     memset(&pa, 0, sizeof pa);
     pa.soa = static_cast<const float4 *>(soa); pa.plane_stride = plane_stride; pa.num_splats = num_splats;
@@ -187,9 +191,20 @@ extern "C" long long emu_projection(const void *soa, unsigned long long plane_st
         for (int i = 0; i < 3; ++i) { float row = 0.0f; for (int j = 0; j < 3; ++j) row += g[i][j] < 0.0f ? -g[i][j] : g[i][j]; nrm = row > nrm ? row : nrm; }
         pa.w_frob2 = nrm * 1.0001f;
     }
+    if (extents_out) {   // launch_extents(): the whole frame, no band / ownership / reject
+        gsr::ProjectionArgs fa = pa;
+        fa.band_y0 = 0; fa.band_y1 = (fa.u.dims[1] + gsr::TILE - 1) / gsr::TILE;
+        fa.row_mod = 1; fa.row_rem = 0; fa.fast_reject = 0; fa.fast_mode = 0; fa.extents = nullptr;
+        struct EL { gsr::ProjectionArgs a; unsigned first, count; uint32_t *out; } el{fa, ext_first, ext_count, extents_out};
+        run_blocks((ext_count + gsr::PROJ_THREADS - 1) / gsr::PROJ_THREADS, (unsigned)gsr::PROJ_THREADS,
+                   [](void *p) { EL *l = static_cast<EL *>(p); gsr::extent_kernel(l->a, l->first, l->count, l->out); }, &el);
+        return 0;
+    }
+    pa.extents = extents;
     gsr::FrameState frame;
     memset(&frame, 0, sizeof frame);
-    const unsigned per_block = pa.fast_reject ? (unsigned)gsr::SH_SPLATS : (unsigned)gsr::PROJ_THREADS;
+    const bool sharded_kernel = pa.fast_reject || pa.extents;
+    const unsigned per_block = sharded_kernel ? (unsigned)gsr::SH_SPLATS : (unsigned)gsr::PROJ_THREADS;
     const unsigned blocks = (num_splats + per_block - 1) / per_block;
     unsigned long long *lookback = static_cast<unsigned long long *>(calloc(blocks ? blocks : 1, sizeof(unsigned long long)));
     pa.records = static_cast<float4 *>(records); pa.keys = keys; pa.values = values; pa.capacity = capacity;
@@ -197,7 +212,8 @@ extern "C" long long emu_projection(const void *soa, unsigned long long plane_st
     cuda_emu::g_block_dim = cuda_emu::dim{(unsigned)gsr::PROJ_THREADS, 1, 1};
     cuda_emu::g_grid_dim = cuda_emu::dim{blocks, 1, 1};
     for (unsigned b = 0; b < blocks; ++b)
-        glsl::run_workgroup(glsl::uvec3(b, 0, 0), glsl::uvec3((unsigned)gsr::PROJ_THREADS, 1, 1), pa.fast_reject ? &projection_sharded_body : &projection_body, &pa);
+        glsl::run_workgroup(glsl::uvec3(b, 0, 0), glsl::uvec3((unsigned)gsr::PROJ_THREADS, 1, 1),
+                            pa.extents ? &projection_table_body : (pa.fast_reject ? &projection_sharded_body : &projection_body), &pa);
     cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
     cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
     free(lookback);

@@ -41,7 +41,8 @@ def lib():
         L.emu_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.emu_projection.restype = C.c_longlong
         L.emu_projection.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_uint)]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_uint),
+                                     C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         L.emu_aos_to_soa.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong, C.c_ulonglong]
         L.emu_ply_to_soa.argtypes = [C.c_void_p, C.c_uint, C.c_ulonglong, C.c_float, C.c_void_p, C.c_ulonglong, C.c_ulonglong]
         L.emu_pack_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong]
@@ -224,7 +225,14 @@ def emu_upload(splat60, chunk=None):
     return soa, stride
 
 
-def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, fast_reject=0, sh_bulk_min=0, cap=None):
+def emu_extents(soa, stride, n, vp, ub, table, first, count):
+    """gsr_shard_extents_compute: fills table[first:first+count] (y0 | y1 << 16 of the un-banded rect, 0 = emits nothing)."""
+    vp = np.ascontiguousarray(vp, dtype=np.float32)
+    lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, 0, 0, 1, 0, 0, 0, None, None, None, 0, None, None, None,
+                         None, table.ctypes.data, first, count)
+
+
+def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, fast_reject=0, sh_bulk_min=0, cap=None, extents=None):
     gy = (h + 15) // 16
     y0, y1 = (0, gy) if band is None else band
     cap = cap or 10 * n
@@ -234,7 +242,8 @@ def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, f
     vis, last, ovf = C.c_uint(0), C.c_int(0), C.c_uint(0)
     vp = np.ascontiguousarray(vp, dtype=np.float32)
     m = lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, y0, y1, row_mod, row_rem, fast_reject, sh_bulk_min, rec.ctypes.data,
-                             keys.ctypes.data, vals.ctypes.data, cap, C.byref(vis), C.byref(last), C.byref(ovf))
+                             keys.ctypes.data, vals.ctypes.data, cap, C.byref(vis), C.byref(last), C.byref(ovf),
+                             None if extents is None else extents.ctypes.data, None, 0, 0)
     return dict(m=int(m), keys=keys[:min(m, cap)], values=vals[:min(m, cap)], records=rec, visible=int(vis.value), last_tile=int(last.value),
                 overflow=bool(ovf.value))
 
@@ -353,3 +362,42 @@ def test_whole_pipeline_through_the_emulated_kernels():
     rgb = np.zeros((h * w * 3 + 4,), dtype=np.float32)
     lib().emu_pack_rgb(out.ctypes.data, rgb.ctypes.data, w * h)
     np.testing.assert_array_equal(bits(rgb[: 3 * w * h].reshape(h, w, 3)), bits(fr.rgba[..., :3]))
+
+
+@pytest.mark.parametrize("G", [2, 3, 8])
+def test_extent_table_mode_splits_the_cull_across_ranks(G):
+    """EXPERIMENTAL gsr_shard_*: every rank computes the tile-row extents of its slice of the splats, the slices are all-gathered,
+    and every rank then projects only the splats whose rows it owns -- emitting exactly what the replicated cull emits."""
+    n, w, h = 12000, 320, 240
+    gx, gy = (w + 15) // 16, (h + 15) // 16
+    splat60, vp, ub = make_scene(n, 8, w, h, scale_boost=1.0)
+    u = orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8))
+    soa, stride = emu_upload(splat60)
+    full = orc.project(splat60, vp, u)
+    # "all-gather": rank r fills its 256-aligned slice of the one table
+    slice_len = ((n + G - 1) // G + 255) // 256 * 256
+    table = np.full(G * slice_len, 0xDEADBEEF, dtype=np.uint32)
+    for r in range(G):
+        emu_extents(soa, stride, n, vp, ub, table, r * slice_len, slice_len)
+    # the table is the exact rect: rows [y0, y1) of every visible splat, 0 otherwise
+    tiles = full.keys >> 16
+    row = (tiles // gx).astype(np.int64)
+    y0 = np.full(n, 1 << 30, dtype=np.int64)
+    y1 = np.zeros(n, dtype=np.int64)
+    np.minimum.at(y0, full.values, row)
+    np.maximum.at(y1, full.values, row + 1)
+    vis = y1 > 0
+    np.testing.assert_array_equal(table[:n][vis], (y0[vis] | (y1[vis] << 16)).astype(np.uint32))
+    assert not table[:n][~vis].any() and not table[n:].any()
+    rows = row
+    seen = 0
+    for rem in range(G):
+        got = emu_project(soa, stride, n, vp, ub, w, h, row_mod=G, row_rem=rem, extents=table)
+        own = rows % G == rem
+        np.testing.assert_array_equal(got["keys"], full.keys[own])
+        np.testing.assert_array_equal(got["values"], full.values[own])
+        ids = np.unique(full.values[own])
+        for f in orc.RECORD_DTYPE.names:
+            np.testing.assert_array_equal(bits(got["records"][f][ids]), bits(full.records[f][ids]), err_msg=f"record field {f}")
+        seen += got["m"]
+    assert seen == full.duplicates
