@@ -47,9 +47,10 @@ def parse_args():
     ap.add_argument("--splats", type=int, default=int(os.environ.get("GSR_BENCH_SPLATS", "0")), help="debug: override N (marks the line reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-radix", action="store_true")
-    ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["peer", "peerx", "nccl"],
-                    help="N>1: 'peer' = compositor stores bands into the root's frame over NVLink peer memory + 4-byte NCCL sync; "
-                         "'nccl' = NCCL gather of the band framebuffers")
+    ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["group", "peer", "nccl"],
+                    help="N>1: 'group' = NCCL-free shard group (cull split across the ranks, extents exchanged and rows composited over "
+                         "NVLink peer memory, device-side flags); 'peer' = replicated cull, compositor stores bands into the root's frame over "
+                         "NVLink peer memory + 4-byte NCCL sync; 'nccl' = NCCL gather of the band framebuffers")
     return ap.parse_args()
 
 
@@ -87,6 +88,24 @@ def oracle_scene(wl):
     """CPU-baseline legs only: the oracle's own restatement of the ingest (OpenMP) builds its input."""
     from oracle import oracle as orc
     return np.concatenate([orc.preprocess_ply(blk, 0.0) for _, blk in raw_chunks(wl)])
+
+
+def make_config(args, wl):
+    """`config` of the JSON line: a function of the command line only, so that both arms (--impl gsr / reference) print the
+    SAME dict for the same workload and GPU count (the driver compares them).  Run-dependent facts (M, V, C, timings) live
+    in `run_info`."""
+    if args.gpus == 1:
+        par = "single GPU"
+    elif args.mgpu == "nccl":
+        par = f"tile-row bands x{args.gpus} + NCCL framebuffer gather"
+    else:
+        par = (f"cyclic tile rows x{args.gpus} (row % {args.gpus} == rank), " +
+               ("cull split across the ranks, row extents exchanged with peer stores, device-side flags (no NCCL on the frame path)" if args.mgpu == "group"
+                else "replicated cull with early reject, 4-byte NCCL all-reduce per frame") +
+               ", compositor stores into the root frame over NVLink peer memory")
+    return {"workload": f"{args.workload}: {wl['desc']}", "splats": wl["n"], "width": wl["w"], "height": wl["h"], "sh_degree": 3,
+            "parallelism": par, "reduced": bool(args.splats),
+            "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * wl["n"] / 1e6)}
 
 
 class ClockSampler:
@@ -176,8 +195,9 @@ def tune_cpu_threads(wl, splat60, frame):
     return best
 
 
-def cpu_reference_frames(wl, splat60, frames, max_seconds):
-    """Times the CPU restatement (oracle) on full frames of the workload; returns (ms list, stage dict, threads)."""
+def cpu_reference_frames(wl, splat60, frames, max_seconds, keep=None):
+    """Times the CPU restatement (oracle) on full frames of the workload; returns (ms list, stage dict, threads).
+    keep: optional list that receives the oracle's last Frame (pixels, keys, ranges) for the per-run parity check."""
     from oracle import oracle as orc
     ms, stages, info = [], [], None
     t_begin = time.perf_counter()
@@ -188,6 +208,8 @@ def cpu_reference_frames(wl, splat60, frames, max_seconds):
         ms.append((time.perf_counter() - t0) * 1e3)
         stages.append(fr.stage_ms)
         info = dict(duplicates=fr.duplicates, visible=fr.visible, staged=fr.staged)
+        if keep is not None:
+            keep[:] = [(vp, ub, fr)]
         if time.perf_counter() - t_begin > max_seconds:
             break
     return ms, stages, orc.num_threads(), info
@@ -211,7 +233,7 @@ def run_reference(args, wl, rank, world):
         "impl": "reference", "metric": "Msplats/s", "value": value, "unit": "Msplats/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": mean_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "fps": 1000.0 / mean_ms,
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": wl["n"], "width": wl["w"], "height": wl["h"], "parallelism": "host threads"},
+        "config": make_config(args, wl), "run_info": {"executed_on": "host threads (CPU restatement of the reference pipeline)"},
         "cpu_baseline": {"value": value, "unit": "Msplats/s", "cores": threads, "kind": "port", "sample": sample,
                          "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}, **info,
                          "reference_shaders": ref_shaders},
@@ -376,10 +398,19 @@ def main():
             host_chunks.append(blk)
     t_gen = time.perf_counter() - t_gen
     fb = None
-    peer = world > 1 and args.mgpu in ("peer", "peerx")
-    peerx = world > 1 and args.mgpu == "peerx"   # EXPERIMENTAL: the per-frame cull is split across the ranks (gsr_shard_*), see below
+    group = world > 1 and args.mgpu == "group"
+    peer = world > 1 and args.mgpu == "peer"
     sync_flag = torch.zeros(1, dtype=torch.int32, device="cuda") if world > 1 else None
-    if peer:
+    if group:
+        # NCCL-free frame path: every rank exports its arena (flag page + extent tables) and frames, the blobs are all-gathered
+        # ONCE here, and from then on the ranks talk through NVLink peer memory only (include/gsr.h gsr_group_*)
+        from godotgaussiansplatting_b200 import _lib as _gl
+        mine = torch.frombuffer(bytearray(rast.group_export()), dtype=torch.uint8).cuda()
+        blobs = torch.zeros(world * _gl.GSR_GROUP_BLOB_BYTES, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(blobs, mine)
+        rast.group_attach(rank, world, blobs.cpu().numpy().tobytes())
+        dist.barrier()
+    elif peer:
         # fused compositor + gather: the root exports CUDA-IPC handles of its two frames; every rank's compositor then
         # stores its band directly into the root's memory over NVLink
         handles = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -393,43 +424,36 @@ def main():
         class _Word:  # the library's int32 "local last occupied tile + 1" word as a torch tensor (all-reduced in place)
             __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (rast.band_sync_word_ptr(), False), "version": 2}
         sync_flag = torch.as_tensor(_Word(), device="cuda")
-        if peerx:
-            # every rank computes the tile-row extents of ITS slice of the splats, one in-place all-gather shares them, and the
-            # projection then only does the maths for the splats whose rows the rank owns (instead of culling all N on every rank)
-            ext_ptr, ext_cap = rast.shard_extents_ptr()
-            ext_slice = ((wl["n"] + world - 1) // world + 255) // 256 * 256
-            assert ext_slice * world <= ext_cap
-
-            class _Ext:
-                __cuda_array_interface__ = {"shape": (ext_slice * world,), "typestr": "<i4", "data": (ext_ptr, False), "version": 2}
-            ext_table = torch.as_tensor(_Ext(), device="cuda")   # the library's uint32 table, viewed as int32 for NCCL
-            rast.shard_use_extents(True)
     elif world > 1:  # NCCL gather needs a torch-visible frame
         fb = torch.zeros((h_pad, W, 4), dtype=torch.float32, device="cuda")
         rast.set_framebuffer_external(fb.data_ptr())
         rast.set_band(*band)
     # two page-locked host frames: the application consumes frame i while frame i+1 is being copied
     pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
-    rgb_readback = world == 1 or peer  # RGB32F read-back (alpha == 1.0 stays on the device); the NCCL-gather mode copies RGBA
+    can_pack_rgb = world == 1 or peer or group  # optional RGB32F read-back (alpha == 1.0 stays on the device), reported beside the RGBA headline
     pinned = pinned2[0] if rank == 0 else None
 
     frames = frame_params(wl, args.warmup + args.steps)
 
     def step(i, e2e):
+        """e2e: False = device-resident frame; "rgba" = the RGBA32F frame the reference's texture holds (rasterizer.gd:92) lands in
+        pinned host memory every step; "rgb" = the packed RGB32F variant (alpha is the constant 1.0)."""
         vp, ub = frames[i]
+        rgb = e2e == "rgb"
         if world == 1:
-            rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=e2e and rgb_readback)
+            rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=rgb)
+        elif group:
+            rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # extents + rows travel over NVLink; flags order the ranks on the devices
+            if e2e and rank == 0:
+                rast.readback_async(pinned2[i & 1].data_ptr(), rgb_only=rgb)
         elif peer:
-            if peerx:
-                rast.shard_extents_compute(vp, ub, rank * ext_slice, ext_slice)
-                dist.all_gather_into_tensor(ext_table, ext_table[rank * ext_slice:(rank + 1) * ext_slice])
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # band lands in the root's frame (slot i & 1) over NVLink
             if e2e and rank == 0:
                 rast.stream_join()                                 # previous read-backs done before peers may reuse a slot
             dist.all_reduce(sync_flag, op=dist.ReduceOp.MAX)       # 4-byte sync: all rows have landed + frame-global last tile
             rast.band_fixup()                                      # reference quirk Q10 on the rank that owns that tile
             if e2e and rank == 0:
-                rast.readback_async(pinned2[i & 1].data_ptr(), rgb_only=True)
+                rast.readback_async(pinned2[i & 1].data_ptr(), rgb_only=rgb)
         else:
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)
             sharding.gather_bands(fb, rank, world, dst=0)  # one NCCL gather of the band framebuffers per frame (SURVEY 8e)
@@ -447,7 +471,7 @@ def main():
         e0.record(stream)
         for i in range(args.warmup, args.warmup + args.steps):
             step(i, e2e)
-        if e2e and (world == 1 or (peer and rank == 0)):
+        if e2e and (world == 1 or ((peer or group) and rank == 0)):
             rast.stream_join()  # the timed region ends when the last frame has landed in host memory
         e1.record(stream)
         torch.cuda.synchronize()
@@ -464,7 +488,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     hist = rast.frame_history(min(args.steps, 512))
     st = rast.stats()
-    e2e_ms = timed(e2e=True)
+    e2e_ms = timed(e2e="rgba")
+    e2e_rgb_ms = timed(e2e="rgb") if can_pack_rgb else None
 
     ms_per_step = total_ms / args.steps
     stage_total = float(np.mean([r.stage_ms[4] for r in hist]))
@@ -515,13 +540,35 @@ def main():
             radix = {"error": str(e)}
 
     cpu_baseline = None
+    parity = {"checked": False, "why": "no oracle leg on this run (multi-GPU rank layout or --no-cpu-baseline)"}
     if keep_host:
         from oracle import oracle as orc
         splat60 = np.concatenate([orc.preprocess_ply(blk, 0.0) for blk in host_chunks])
         del host_chunks
         tune_cpu_threads(wl, splat60, frames[0])  # warm-up + thread-count choice
-        ms, stages, threads, info = cpu_reference_frames(wl, splat60, frames[args.warmup:args.warmup + 3], 30.0)
+        kept = []
+        ms, stages, threads, info = cpu_reference_frames(wl, splat60, frames[args.warmup:args.warmup + 3], 30.0, keep=kept)
         cpu_ms = float(np.mean(ms))
+        # ---- self-check of this very run: the last oracle frame against a GPU frame of the same camera, through the C-ABI ----
+        vp_c, ub_c, ref = kept[0]
+        got = np.empty((H, W, 4), dtype=np.float32)
+        rast.sync()
+        rast.render_raw(vp_c, ub_c, 0.0, got.ctypes.data, asynchronous=False)
+        stp = rast.stats()
+        m = int(min(stp.duplicates, stp.capacity))
+        from godotgaussiansplatting_b200 import _lib as _gl
+        gk = rast.debug_copy(_gl.GSR_BUF_KEYS, m, np.uint32); gv = rast.debug_copy(_gl.GSR_BUF_VALUES, m, np.uint32)
+        gb = rast.debug_copy(_gl.GSR_BUF_BOUNDS, 2 * T, np.uint32).reshape(T, 2)
+        parity = {"checked": True, "against": "oracle (CPU restatement pinned to the reference's shaders), same camera, full workload",
+                  "keys_equal": bool(m == ref.keys.size and np.array_equal(gk, ref.keys)),
+                  "values_equal": bool(m == ref.values.size and np.array_equal(gv, ref.values)),
+                  "ranges_equal": bool(np.array_equal(gb, ref.bounds)),
+                  "rgba_max_abs_err": float(np.abs(got - ref.rgba).max()),
+                  "rgba_bit_identical": bool(np.array_equal(got.view(np.uint32), ref.rgba.view(np.uint32))),
+                  "duplicates_M": int(stp.duplicates), "staged_C": int(stp.staged)}
+        del gk, gv, gb, got, kept
+        if not (parity["keys_equal"] and parity["values_equal"] and parity["ranges_equal"] and parity["rgba_max_abs_err"] <= 1e-4):
+            raise SystemExit(f"bench.py: PARITY FAILURE against the oracle on the benchmarked workload: {parity}")
         cpu_baseline = {"value": N / 1e6 * 1000.0 / cpu_ms, "unit": "Msplats/s", "cores": threads, "kind": "port", "ms_per_frame": cpu_ms,
                         "sample": f"{len(ms)} full orbit frame(s) of the same workload (all {N} splats, {W}x{H}); CPU restatement of the reference pipeline, Godot/lavapipe unavailable",
                         "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}}
@@ -531,14 +578,15 @@ def main():
             "metric": "Msplats/s", "value": value, "unit": "Msplats/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": fps,
-            "config": {"workload": f"{args.workload}: {wl['desc']}", "splats": N, "width": W, "height": H, "sh_degree": 3,
-                       "parallelism": "single GPU" if world == 1 else (f"cyclic tile rows x{world} (row % {world} == rank), " + ("cull split across the ranks + all-gathered row extents (experimental)" if peerx else "early-reject projection") + ", compositor stores into the root frame over NVLink peer memory + 4-byte NCCL all-reduce" if peer else f"tile-row bands x{world} + NCCL framebuffer gather"),
-                       "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * N / 1e6),
-                       "duplicates_M": M, "visible_V": V, "staged_C": Cc, "reduced": reduced, "scene_build_s": t_gen},
+            "config": make_config(args, wl),
+            "run_info": {"duplicates_M": M, "visible_V": V, "staged_C": Cc, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),
-                    "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * (12 if rgb_readback else 16),
-                    "path": "gsr_render_async_rgb(ctx, view_proj, uniforms, pinned host RGB32F; alpha is the constant 1.0 of gsplat_render.glsl:101) per frame; 160 B of camera constants in, full frame out; read-back of frame i overlaps frame i+1 (two device + two host frames); timed region ends after the last frame landed on the host"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                    "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * 16,
+                    "path": "gsr_render_async(ctx, view_proj, uniforms, pinned host RGBA32F) per frame -- the frame the reference's RGBA32F texture holds (rasterizer.gd:92); 160 B of camera constants in, full frame out; read-back of frame i overlaps frame i+1 (two device + two host frames); timed region ends after the last frame landed on the host",
+                    "rgb32f_packed": None if e2e_rgb_ms is None else {
+                        "value": N / 1e6 * 1000.0 / (e2e_rgb_ms / args.steps), "fps": 1000.0 / (e2e_rgb_ms / args.steps), "d2h_bytes_per_step": P * 12,
+                        "path": "gsr_render_async_rgb: RGB32F pack on the copy stream (alpha is the constant 1.0 of gsplat_render.glsl:101)"}},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "gpu_launches": int(st.kernel_launches) * args.steps, "kernel_launches_per_frame": int(st.kernel_launches),
             "stage_ms": stage, "radix": radix,
             "reference_published": {"fps": 108, "scene": "bicycle.ply ~6.1M splats @1080p", "hw": "RTX 3060 Ti", "source": "README.md:58 (other hardware; not comparable)"},

@@ -20,7 +20,7 @@ GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES, GSR_FLAG_FAST_REJECT = 0x1, 0x
 EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_upload_ply_raw", "gsr_resize", "gsr_set_band", "gsr_set_row_interleave", "gsr_band_sync_word", "gsr_band_fixup", "gsr_render",
     "gsr_render_async", "gsr_render_async_rgb", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
-    "gsr_stream_join", "gsr_shard_extents_ptr", "gsr_shard_extents_compute", "gsr_shard_use_extents", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
+    "gsr_stream_join", "gsr_group_export", "gsr_group_attach", "gsr_group_detach", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
     "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
     "gsr_device_count", "gsr_version",
@@ -40,6 +40,7 @@ class GsrStats(C.Structure):
 
 
 GSR_HISTORY_FRAMES = 512
+GSR_GROUP_BLOB_BYTES = 320
 
 
 class GsrFrameRecord(C.Structure):
@@ -81,10 +82,9 @@ def lib():
         L.gsr_render_async_rgb.argtypes = [vp, fp, vp, C.c_float, vp]
         L.gsr_sync.argtypes = [vp]
         L.gsr_stream_join.argtypes = [vp]
-        L.gsr_shard_extents_ptr.restype = C.c_void_p
-        L.gsr_shard_extents_ptr.argtypes = [vp, C.POINTER(C.c_uint64)]
-        L.gsr_shard_extents_compute.argtypes = [vp, fp, vp, C.c_uint64, C.c_uint64]
-        L.gsr_shard_use_extents.argtypes = [vp, C.c_int]
+        L.gsr_group_export.argtypes = [vp, vp]
+        L.gsr_group_attach.argtypes = [vp, C.c_int32, C.c_int32, vp]
+        L.gsr_group_detach.argtypes = [vp]
         L.gsr_readback_async.argtypes = [vp, vp, C.c_int]
         L.gsr_peer_export_framebuffers.argtypes = [vp, vp]
         L.gsr_peer_import_framebuffers.argtypes = [vp, vp]

@@ -157,14 +157,41 @@ struct ProjectionArgs {
     uint32_t capacity;
     unsigned long long *lookback;  // one word per projection CTA (256 splats)
     FrameState *frame;
-    // EXPERIMENTAL (multi-GPU, opt-in, gsr_shard_*): tile-row extent of every splat's un-banded rect, y0 | y1 << 16 (0 = not
-    // visible), computed once per frame by ONE rank per splat slice (launch_extents) and all-gathered by the host; a rank then
-    // runs the projection maths only for the splats whose rows it owns instead of culling all N itself.  nullptr = off.
+    // group mode (gsr_group_attach): tile-row extent of every splat's un-banded rect, y0 | y1 << 16 (0 = not visible), computed
+    // once per frame by ONE rank per splat slice (launch_extents, peer stores into every rank's table); a rank then runs the
+    // projection maths only for the splats whose rows it owns instead of culling all N itself.  nullptr = off.
     const uint32_t *extents;
 };
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
-// extents[first .. first+count) of the frame described by `a` (band / row ownership fields of `a` are ignored)
-int launch_extents(const ProjectionArgs &a, uint32_t first, uint32_t count, uint32_t *extents, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU shard group (group.cu, gsr_group_attach): flag words + extent tables in every rank's arena
+// ---------------------------------------------------------------------------------------------
+constexpr int GROUP_MAX = 16;                                   // ranks per group (one NVSwitch domain)
+#define GSR_GROUP_TIMEOUT_NS 10000000000ull                     // every device-side wait gives up after 10 s
+struct GroupFlags {                                             // offset 0 of a rank's arena; written by the peers over NVLink
+    unsigned long long meta[2][GROUP_MAX];  // [frame parity][source rank] = seq << 32 | (last tile of the source's slice + 1)
+    uint32_t done[GROUP_MAX];               // presenting rank: done[r] = seq of the newest frame whose rows from rank r have landed
+    uint32_t released;                      // set by the presenting rank: frames with seq <= released no longer need their slot
+    uint32_t error;                         // local: a wait timed out (1 = extents, 2 = done / released)
+    uint32_t ext_ticket;                    // local: CTAs of the extent kernel that have finished
+    int32_t ext_last;                       // local: atomicMax target, last tile + 1 over this rank's slice
+};
+constexpr size_t GROUP_FLAGS_BYTES = 4096;                      // the two extent tables follow the flag page
+static_assert(sizeof(GroupFlags) <= GROUP_FLAGS_BYTES, "flag page");
+struct GroupPeers {                                             // the same pointers on every rank, indexed by rank
+    GroupFlags *flags[GROUP_MAX];
+    uint32_t *table[GROUP_MAX];                                 // extent table of the CURRENT frame parity in rank r's arena
+    int world, rank;
+};
+// extents of splats [first, first+count) of the frame described by `a` (band / row ownership of `a` are ignored), stored into
+// EVERY rank's table (peer stores); the last CTA then publishes seq | last tile to every rank's meta[parity][rank].
+int launch_extents(const ProjectionArgs &a, uint32_t first, uint32_t count, const GroupPeers &peers, int parity, uint32_t seq, cudaStream_t stream);
+int launch_group_wait_extents(GroupFlags *flags, int parity, int world, uint32_t seq, FrameState *frame, cudaStream_t stream);
+int launch_group_wait_released(GroupFlags *flags, uint32_t need, cudaStream_t stream);
+int launch_group_wait_done(GroupFlags *flags, int world, uint32_t seq, cudaStream_t stream);
+int launch_group_signal_done(const GroupPeers &peers, int root, int rank, uint32_t seq, cudaStream_t stream);
+int launch_group_release(const GroupPeers &peers, int world, uint32_t value, cudaStream_t stream);
 uint32_t projection_num_blocks(uint32_t num_splats);
 
 // sharded: 0 = full frame, 1 = exact sharded mode (global last tile known from the projection), 2 = fast sharded mode

@@ -248,11 +248,14 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
                 s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
-                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
+                const uint32_t qi = ticket - (uint32_t)p.num_tiles;
+                const bool in_q = qi < (uint32_t)COMP_MAX_PUSHES * (uint32_t)p.num_tiles;
+                volatile uint32_t *slot = p.queue + (in_q ? qi : 0u);
                 volatile uint32_t *done = &p.frame->comp_done;
-                uint32_t v;
-                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
-                if (v == 0u) v = *slot;  // a push may have landed between the two reads
+                uint32_t v = 0u;
+                while (in_q && (v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (in_q && v == 0u) v = *slot;  // a push may have landed between the two reads
                 s_tile = v ? v - 1u : EXIT_TILE;
                 s_resume = 1u;
                 __threadfence();
@@ -506,11 +509,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v2_kernel(const
                 s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
-                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
+                const uint32_t qi = ticket - (uint32_t)p.num_tiles;
+                const bool in_q = qi < (uint32_t)COMP_MAX_PUSHES * (uint32_t)p.num_tiles;
+                volatile uint32_t *slot = p.queue + (in_q ? qi : 0u);
                 volatile uint32_t *done = &p.frame->comp_done;
-                uint32_t v;
-                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
-                if (v == 0u) v = *slot;
+                uint32_t v = 0u;
+                while (in_q && (v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (in_q && v == 0u) v = *slot;
                 s_tile = v ? v - 1u : EXIT_TILE;
                 s_resume = 1u;
                 __threadfence();
@@ -785,11 +791,14 @@ __global__ void __launch_bounds__(P4_THREADS, GSR_COMP_P4_MIN_BLOCKS) composite_
                 s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
-                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
+                const uint32_t qi = ticket - (uint32_t)p.num_tiles;
+                const bool in_q = qi < (uint32_t)COMP_MAX_PUSHES * (uint32_t)p.num_tiles;
+                volatile uint32_t *slot = p.queue + (in_q ? qi : 0u);
                 volatile uint32_t *done = &p.frame->comp_done;
-                uint32_t v;
-                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
-                if (v == 0u) v = *slot;
+                uint32_t v = 0u;
+                while (in_q && (v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (in_q && v == 0u) v = *slot;
                 s_tile = v ? v - 1u : EXIT_TILE;
                 s_resume = 1u;
                 __threadfence();
@@ -994,11 +1003,14 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
                 s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
-                volatile uint32_t *slot = p.queue + (ticket - (uint32_t)p.num_tiles);
+                // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
+                const uint32_t qi = ticket - (uint32_t)p.num_tiles;
+                const bool in_q = qi < (uint32_t)COMP_MAX_PUSHES * (uint32_t)p.num_tiles;
+                volatile uint32_t *slot = p.queue + (in_q ? qi : 0u);
                 volatile uint32_t *done = &p.frame->comp_done;
-                uint32_t v;
-                while ((v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
-                if (v == 0u) v = *slot;
+                uint32_t v = 0u;
+                while (in_q && (v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (in_q && v == 0u) v = *slot;
                 s_tile = v ? v - 1u : EXIT_TILE;
                 s_resume = 1u;
                 __threadfence();

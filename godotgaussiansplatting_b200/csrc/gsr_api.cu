@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <stddef.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <new>
 
@@ -71,8 +72,19 @@ struct gsr_ctx {
     bool band_set = false;
     int row_mod = 1, row_rem = 0;   // cyclic tile-row ownership (gsr_set_row_interleave): fast sharded mode when row_mod > 1
     int32_t *sync_word = nullptr;   // local (then all-reduced) last occupied tile + 1
-    uint32_t *extents = nullptr;    // EXPERIMENTAL gsr_shard_*: per-splat tile-row extents of the current frame (all ranks' slices)
-    bool use_extents = false;
+    // multi-GPU shard group (gsr_group_export / gsr_group_attach): NCCL-free frame path, see group.cu
+    struct Group {
+        void *arena = nullptr;            // this rank's arena: flag page + two extent tables
+        uint64_t table_entries = 0;       // entries per table
+        int rank = 0, world = 0;          // world > 1 <=> attached
+        GroupFlags *flags[GROUP_MAX] = {};   // every rank's flag page (peer pointers)
+        uint32_t *table[2][GROUP_MAX] = {};  // every rank's two extent tables
+        float4 *root_fb[2] = {nullptr, nullptr};  // the presenting rank's two frames
+        void *opened[3 * GROUP_MAX] = {};    // IPC mappings to close
+        int n_opened = 0;
+        uint32_t seq = 0;                 // frames rendered by the group so far (lockstep on all ranks)
+        uint64_t slice = 0;               // splats per rank (256-aligned)
+    } grp;
     cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
     bool ev_valid = false;
     uint32_t last_launches = 0;
@@ -113,6 +125,16 @@ int check_device(int device) {
     return GSR_OK;
 }
 
+void group_detach(gsr_ctx *c) {
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < c->grp.n_opened; ++i) cudaIpcCloseMemHandle(c->grp.opened[i]);
+    c->grp.n_opened = 0;
+    if (c->grp.world > 1) { c->row_mod = 1; c->row_rem = 0; }
+    c->grp.world = 0; c->grp.rank = 0; c->grp.seq = 0;
+    c->grp.root_fb[0] = c->grp.root_fb[1] = nullptr;
+}
+
 float4 *framebuffer(gsr_ctx *c) { return c->fb_ext ? c->fb_ext : (c->fb_last ? c->fb_last : c->fb); }
 
 void free_ctx(gsr_ctx *c) {
@@ -128,7 +150,8 @@ void free_ctx(gsr_ctx *c) {
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->sync_word);
-    cudaFree(c->extents);
+    for (int i = 0; i < c->grp.n_opened; ++i) cudaIpcCloseMemHandle(c->grp.opened[i]);
+    cudaFree(c->grp.arena);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); cudaFree(c->trace); cudaFree(c->trace_count);
     if (c->ev) {
         for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -302,6 +325,11 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     cudaFree(c->fb2); c->fb2 = nullptr;
     cudaFree(c->rgb[0]); cudaFree(c->rgb[1]); c->rgb[0] = c->rgb[1] = nullptr;
     c->fb_last = nullptr; c->copied_valid[0] = c->copied_valid[1] = false;
+    // peer mode refers to the frames freed above (exported) or to another process's frames of the old size (imported): drop it.
+    // The host must export / import again after a resize (every rank resizes, then the presenting rank re-exports).
+    if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); c->peer_opened = false; }
+    c->peer_mode = false; c->peer_fb[0] = c->peer_fb[1] = nullptr; c->peer_counter = 0; c->async_counter = 0;
+    group_detach(c);   // same for a shard group: every rank resizes, exports and attaches again
     GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)tx * ty));
     c->comp_queue = reinterpret_cast<uint32_t *>(c->bounds + (size_t)tx * ty);
     GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_state, sizeof(float4) * 256ull * (size_t)tx * ty));
@@ -373,7 +401,18 @@ static void frame_constants(const float *view_proj, const Uniforms &u, Projectio
     }
 }
 
-static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float4 *target = nullptr) {
+struct GroupFrame { uint32_t seq; int parity; };
+
+static GroupPeers group_peers(const gsr_ctx *c, int parity) {
+    GroupPeers p;
+    memset(&p, 0, sizeof p);
+    p.world = c->grp.world; p.rank = c->grp.rank;
+    for (int r = 0; r < c->grp.world; ++r) { p.flags[r] = c->grp.flags[r]; p.table[r] = c->grp.table[parity][r]; }
+    return p;
+}
+
+static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float4 *target = nullptr,
+                          const GroupFrame *gf = nullptr) {
     if (!c || !view_proj || !uniforms32) return GSR_ERR_INVALID;
     if (c->width == 0) { set_last_error("gsr_render before gsr_resize"); return GSR_ERR_STATE; }
     Uniforms u;
@@ -391,16 +430,18 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     c->frame = c->ring + slot;
     cudaEvent_t *ev = c->ev + 5 * slot;
     GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->num_splats), s));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->max_splats), s));
     GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)c->tiles_x * c->tiles_y, s));  // bounds + queue
     GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 
     ProjectionArgs pa;
-    pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
+    // the reference dispatches over splat_buffer.length() = point_cloud.size every frame (rasterizer.gd:83,134), i.e. also over the
+    // zero-initialised structs of splats the loader has not delivered yet: so does libgsr (the SoA planes start zeroed)
+    pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->max_splats;
     memcpy(pa.vp, view_proj, sizeof pa.vp);
     pa.u = u;
     frame_constants(view_proj, u, pa);
-    const bool fast = c->row_mod > 1;
+    const bool fast = c->row_mod > 1 && !gf;   // group mode is exact: the frame-global last tile travels with the extents
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
     pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
     // Conservative early reject + compaction of the survivors over 1024-splat CTAs (projection_sharded_kernel): exact, and
@@ -416,7 +457,19 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.sh_bulk_min = bulk_env > 0 ? bulk_env : (fast ? 1 : 12);
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
-    pa.extents = (c->use_extents && fast && c->extents) ? c->extents : nullptr;
+    pa.extents = nullptr;
+    if (gf) {
+        // group mode: this rank culls ITS slice of the splats and stores the tile-row extents into every rank's table (peer
+        // stores over NVLink), waits for the other slices, then runs the projection maths only for the splats whose rows it owns
+        const uint64_t first = (uint64_t)c->grp.rank * c->grp.slice;
+        const uint64_t count = first < c->max_splats ? ((c->max_splats - first) < c->grp.slice ? (c->max_splats - first) : c->grp.slice) : 0;
+        pa.band_y0 = 0; pa.band_y1 = c->tiles_y; pa.fast_reject = 0; pa.fast_mode = 0;
+        if ((rc = launch_extents(pa, (uint32_t)first, (uint32_t)count, group_peers(c, gf->parity), gf->parity, gf->seq, s))) return rc;
+        if ((rc = launch_group_wait_extents(c->grp.flags[c->grp.rank], gf->parity, c->grp.world, gf->seq, c->frame, s))) return rc;
+        pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
+        pa.extents = c->grp.table[gf->parity][c->grp.rank];
+        launches += 2;
+    }
     if ((rc = launch_projection(pa, s))) return rc;
     launches += pa.num_splats ? 1 : 0;
     GSR_CUDA_TRY(cudaEventRecord(ev[1], s));  // 'Projection'
@@ -429,7 +482,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     if ((rc = sort_pairs_device(c->sort, c->keys, c->vals, m_ptr, c->keys + c->capacity, c->vals + c->capacity, s, &launches))) return rc;
     GSR_CUDA_TRY(cudaEventRecord(ev[2], s));  // 'Sort'
 
-    const int sharded = fast ? 2 : (!(c->band_y0 == 0 && c->band_y1 == c->tiles_y) ? 1 : 0);
+    const int sharded = fast ? 2 : ((!(c->band_y0 == 0 && c->band_y1 == c->tiles_y) || c->row_mod > 1) ? 1 : 0);
     if (fast) GSR_CUDA_TRY(cudaMemsetAsync(c->sync_word, 0, sizeof(int32_t), s));
     const int quirks = (c->flags & GSR_FLAG_FIXED_RANGES) ? 0 : 1;
     if ((rc = launch_tile_ranges(c->keys, c->frame, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), quirks, sharded, fast ? c->sync_word : nullptr, c->sm_count * 8, s))) return rc;
@@ -438,6 +491,11 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
 
     CompositeArgs ca;
     float4 *out_fb = c->fb_ext ? c->fb_ext : (target ? target : c->fb);
+    // a pipelined read-back of this buffer may still be in flight on the copy stream (gsr_render_async followed by gsr_render)
+    for (int i = 0; i < 2; ++i) {
+        const float4 *owned = c->peer_mode ? c->peer_fb[i] : (i ? c->fb2 : c->fb);
+        if (c->copied_valid[i] && owned == out_fb) GSR_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_copied[i], 0));
+    }
     c->fb_last = out_fb;
     ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = out_fb;
     ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
@@ -455,8 +513,16 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
     ca.trace = c->trace; ca.trace_count = c->trace_count; ca.trace_cap = c->trace_cap;
     if (c->trace) GSR_CUDA_TRY(cudaMemsetAsync(c->trace_count, 0, sizeof(uint32_t), s));
+    if (gf && c->grp.rank != 0 && gf->seq >= 3u) {   // the presenting rank must have consumed the frame that used this slot
+        if ((rc = launch_group_wait_released(c->grp.flags[c->grp.rank], gf->seq - 2u, s))) return rc;
+        launches += 1;
+    }
     if ((rc = launch_composite(ca, s))) return rc;
     launches += ca.num_tiles > 0 ? 1 : 0;
+    if (gf) {   // rows have landed in the presenting rank's frame: tell it (system-scope flag store after the kernel boundary)
+        if ((rc = launch_group_signal_done(group_peers(c, gf->parity), 0, c->grp.rank, gf->seq, s))) return rc;
+        launches += 1;
+    }
     GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Render'
     c->ev_valid = true;
     c->frame_counter += 1;
@@ -465,6 +531,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
 }
 
 GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *out_host) {
+    if (c && c->grp.world > 1) { set_last_error("gsr_render: a context attached to a group renders with gsr_render_async (all ranks, same frame)"); return GSR_ERR_STATE; }
     int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
     if (rc) return rc;
     if (out_host) {
@@ -474,12 +541,14 @@ GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *unifor
     return GSR_OK;
 }
 
-static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, float *pinned_host, bool rgb_only) {
+static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, float *pinned_host, bool rgb_only, uint32_t group_seq = 0) {
     const size_t pixels = (size_t)c->width * c->height;
     int rc;
     if (rgb_only && !c->rgb[slot]) GSR_CUDA_TRY(cudaMalloc((void **)&c->rgb[slot], sizeof(float) * 3 * pixels + 64));
     GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
     GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+    // group mode: the other ranks' rows arrive over NVLink; their done flags gate the copy (device-side wait on the copy stream)
+    if (group_seq && (rc = launch_group_wait_done(c->grp.flags[c->grp.rank], c->grp.world, group_seq, c->copy_stream))) return rc;
     if (rgb_only) {
         if ((rc = launch_pack_rgb(frame, c->rgb[slot], pixels, c->copy_stream))) return rc;
         GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, c->rgb[slot], sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -493,6 +562,21 @@ static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, float *pinned_h
 
 static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float *pinned_host, bool rgb_only) {
     if (!c) return GSR_ERR_INVALID;
+    if (c->grp.world > 1) {   // shard group: every rank enqueues the same frame; rows land in the presenting rank's frames
+        if (pinned_host) { set_last_error("group mode: render with a NULL host pointer on every rank, then gsr_readback_async on rank 0"); return GSR_ERR_STATE; }
+        int rc = use_device(c->device);
+        if (rc) return rc;
+        GroupFrame gf;
+        gf.seq = c->grp.seq + 1u; gf.parity = (int)(gf.seq & 1u);
+        const int slot = (int)((gf.seq - 1u) & 1u);
+        if (c->grp.rank == 0) {
+            if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+            if (gf.seq >= 3u && (rc = launch_group_release(group_peers(c, gf.parity), c->grp.world, gf.seq - 2u, c->stream))) return rc;
+        }
+        if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, c->grp.root_fb[slot], &gf))) return rc;
+        c->grp.seq = gf.seq;
+        return GSR_OK;
+    }
     if (c->peer_mode) {  // frames alternate between the presenting rank's two frames; read-back is a separate call
         if (pinned_host) { set_last_error("peer mode: render with a NULL host pointer, then gsr_readback_async on the presenting rank"); return GSR_ERR_STATE; }
         int rc = use_device(c->device);
@@ -538,6 +622,10 @@ GSR_API int gsr_readback_async(gsr_ctx *c, float *pinned_host, int rgb_only) {
     if (!c->fb_last || c->fb_ext) { set_last_error("gsr_readback_async: no library-owned frame rendered yet"); return GSR_ERR_STATE; }
     int rc = use_device(c->device);
     if (rc) return rc;
+    if (c->grp.world > 1) {
+        if (c->grp.rank != 0) { set_last_error("gsr_readback_async: only rank 0 of a group presents the frame"); return GSR_ERR_STATE; }
+        return readback_enqueue(c, c->fb_last, (int)((c->grp.seq - 1u) & 1u), pinned_host, rgb_only != 0, c->grp.seq);
+    }
     const int slot = (c->fb_last == c->fb2 || (c->peer_mode && c->fb_last == c->peer_fb[1])) ? 1 : 0;
     return readback_enqueue(c, c->fb_last, slot, pinned_host, rgb_only != 0);
 }
@@ -568,47 +656,118 @@ GSR_API int gsr_peer_import_framebuffers(gsr_ctx *c, const void *handles128) {
     return GSR_OK;
 }
 
-// ---- EXPERIMENTAL (multi-GPU, opt-in): split the per-frame cull across the ranks.  Every rank computes the tile-row extents of
-//      ITS slice of the splats (gsr_shard_extents_compute), the host all-gathers the slices in place (NCCL on
-//      gsr_shard_extents_ptr), and gsr_render then runs the projection maths only for the splats whose rows this rank owns
-//      (gsr_shard_use_extents(1); needs gsr_set_row_interleave).  Exact: same rects, same emission order.
-GSR_API void *gsr_shard_extents_ptr(gsr_ctx *c, uint64_t *capacity_out) {
-    if (!c) return nullptr;
-    const uint64_t cap = ((c->max_splats + 255ull) / 256ull + 64ull) * 256ull;   // room for up to 64 ranks' 256-aligned slices
-    if (!c->extents) {
-        if (use_device(c->device)) return nullptr;
-        if (cudaMalloc((void **)&c->extents, sizeof(uint32_t) * cap) != cudaSuccess) { set_last_error("cudaMalloc(extents) failed"); c->extents = nullptr; return nullptr; }
-        cudaMemsetAsync(c->extents, 0, sizeof(uint32_t) * cap, c->stream);
-    }
-    if (capacity_out) *capacity_out = cap;
-    return c->extents;
-}
+// ---- multi-GPU shard group: one context per GPU (processes or threads), NCCL-free frame path (group.cu) ----
+namespace {
+struct GroupBlob {   // what gsr_group_export hands to the other ranks (any transport; 320 bytes)
+    uint32_t magic, version;
+    uint64_t pid;
+    int32_t device, width, height, pad;
+    uint64_t max_splats, table_entries;
+    void *arena, *fb[2];
+    cudaIpcMemHandle_t h_arena, h_fb[2];
+    unsigned char reserved[GSR_GROUP_BLOB_BYTES - 264];
+};
+static_assert(sizeof(GroupBlob) == GSR_GROUP_BLOB_BYTES, "blob layout");
+constexpr uint32_t GROUP_MAGIC = 0x47535247u;  // "GRSG"
 
-GSR_API int gsr_shard_extents_compute(gsr_ctx *c, const float view_proj[32], const void *uniforms32, uint64_t first, uint64_t count) {
-    if (!c || !view_proj || !uniforms32) return GSR_ERR_INVALID;
-    if (c->width == 0) { set_last_error("gsr_shard_extents_compute before gsr_resize"); return GSR_ERR_STATE; }
-    uint64_t cap = 0;
-    if (!gsr_shard_extents_ptr(c, &cap)) return GSR_ERR_OOM;
-    if (count > cap || first > cap - count) { set_last_error("extent slice [%llu,%llu) exceeds the table (%llu)", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)cap); return GSR_ERR_INVALID; }
-    Uniforms u;
-    memcpy(&u, uniforms32, sizeof u);
-    if (u.dims[0] != c->width || u.dims[1] != c->height) { set_last_error("uniform dims %dx%d differ from gsr_resize %dx%d", u.dims[0], u.dims[1], c->width, c->height); return GSR_ERR_INVALID; }
+}  // namespace
+
+GSR_API int gsr_group_export(gsr_ctx *c, void *blob) {
+    if (!c || !blob) return GSR_ERR_INVALID;
+    if (!c->fb || !c->fb2 || c->fb_ext) { set_last_error("gsr_group_export: call gsr_resize first (library-owned frames only)"); return GSR_ERR_STATE; }
     int rc = use_device(c->device);
     if (rc) return rc;
-    ProjectionArgs pa;
-    memset(&pa, 0, sizeof pa);
-    pa.soa = c->soa; pa.plane_stride = c->plane_stride; pa.num_splats = (uint32_t)c->num_splats;
-    memcpy(pa.vp, view_proj, sizeof pa.vp);
-    pa.u = u;
-    frame_constants(view_proj, u, pa);
-    pa.sh_bulk_min = 12;
-    return launch_extents(pa, (uint32_t)first, (uint32_t)count, c->extents, c->stream);
+    if (!c->grp.arena) {
+        c->grp.table_entries = ((c->max_splats + 255ull) & ~255ull) + 256ull * GROUP_MAX;   // any world's 256-aligned slices fit
+        const size_t bytes = GROUP_FLAGS_BYTES + 2ull * sizeof(uint32_t) * c->grp.table_entries;
+        cudaError_t e = cudaMalloc(&c->grp.arena, bytes);
+        if (e != cudaSuccess) { set_last_error("cudaMalloc(group arena, %zu B) -> %s", bytes, cudaGetErrorString(e)); c->grp.arena = nullptr; return GSR_ERR_OOM; }
+        GSR_CUDA_TRY(cudaMemset(c->grp.arena, 0, bytes));
+    }
+    GroupBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = GROUP_MAGIC; b.version = 1; b.pid = (uint64_t)getpid();
+    b.device = c->device; b.width = c->width; b.height = c->height;
+    b.max_splats = c->max_splats; b.table_entries = c->grp.table_entries;
+    b.arena = c->grp.arena; b.fb[0] = c->fb; b.fb[1] = c->fb2;
+    // IPC handles are needed only by ranks living in other processes; a failure here surfaces there (zero handle)
+    if (cudaIpcGetMemHandle(&b.h_arena, c->grp.arena) != cudaSuccess || cudaIpcGetMemHandle(&b.h_fb[0], c->fb) != cudaSuccess ||
+        cudaIpcGetMemHandle(&b.h_fb[1], c->fb2) != cudaSuccess) {
+        cudaGetLastError();
+        memset(&b.h_arena, 0, sizeof b.h_arena); memset(b.h_fb, 0, sizeof b.h_fb);
+    }
+    memcpy(blob, &b, sizeof b);
+    return GSR_OK;
 }
 
-GSR_API int gsr_shard_use_extents(gsr_ctx *c, int enable) {
+GSR_API int gsr_group_attach(gsr_ctx *c, int32_t rank, int32_t world, const void *blobs) {
+    if (!c || !blobs || world < 1 || world > GROUP_MAX || rank < 0 || rank >= world) { set_last_error("gsr_group_attach: need 0 <= rank < world <= %d", GROUP_MAX); return GSR_ERR_INVALID; }
+    if (!c->grp.arena || !c->fb) { set_last_error("gsr_group_attach before gsr_group_export"); return GSR_ERR_STATE; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    group_detach(c);
+    if (world == 1) return GSR_OK;
+    const GroupBlob *B = reinterpret_cast<const GroupBlob *>(blobs);
+    const uint64_t slice = (((c->max_splats + (uint64_t)world - 1) / (uint64_t)world) + 255ull) & ~255ull;
+    for (int r = 0; r < world; ++r) {
+        if (B[r].magic != GROUP_MAGIC || B[r].version != 1) { set_last_error("gsr_group_attach: blob %d is not a gsr_group_export blob", r); return GSR_ERR_INVALID; }
+        if (B[r].max_splats != c->max_splats || B[r].width != c->width || B[r].height != c->height || slice * (uint64_t)world > B[r].table_entries) {
+            set_last_error("gsr_group_attach: rank %d was created with a different scene / frame size", r);
+            return GSR_ERR_INVALID;
+        }
+    }
+    if (B[rank].arena != c->grp.arena || B[rank].pid != (uint64_t)getpid()) { set_last_error("gsr_group_attach: blob %d is not this context's export", rank); return GSR_ERR_INVALID; }
+    auto fail = [&](const char *what, int r, cudaError_t e) {
+        set_last_error("gsr_group_attach: %s of rank %d -> %s", what, r, cudaGetErrorString(e));
+        group_detach(c);
+        return GSR_ERR_CUDA;
+    };
+    for (int r = 0; r < world; ++r) {
+        char *arena = nullptr;
+        float4 *fb[2] = {nullptr, nullptr};
+        if (r == rank) {
+            arena = (char *)c->grp.arena; fb[0] = c->fb; fb[1] = c->fb2;
+        } else if (B[r].pid == (uint64_t)getpid()) {   // same process (one thread per GPU, the GDExtension case): plain peer pointers
+            if (B[r].device != c->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, c->device, B[r].device);
+                if (!can) return fail("no peer access to the device", r, cudaErrorPeerAccessUnsupported);
+                cudaError_t e = cudaDeviceEnablePeerAccess(B[r].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess", r, e);
+                cudaGetLastError();
+            }
+            arena = (char *)B[r].arena; fb[0] = (float4 *)B[r].fb[0]; fb[1] = (float4 *)B[r].fb[1];
+        } else {                                       // another process: CUDA IPC mappings
+            cudaError_t e = cudaIpcOpenMemHandle((void **)&arena, B[r].h_arena, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle(arena)", r, e);
+            c->grp.opened[c->grp.n_opened++] = arena;
+            if (r == 0) {
+                for (int k = 0; k < 2; ++k) {
+                    e = cudaIpcOpenMemHandle((void **)&fb[k], B[r].h_fb[k], cudaIpcMemLazyEnablePeerAccess);
+                    if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle(frame)", r, e);
+                    c->grp.opened[c->grp.n_opened++] = fb[k];
+                }
+            }
+        }
+        c->grp.flags[r] = reinterpret_cast<GroupFlags *>(arena);
+        c->grp.table[0][r] = reinterpret_cast<uint32_t *>(arena + GROUP_FLAGS_BYTES);
+        c->grp.table[1][r] = c->grp.table[0][r] + B[r].table_entries;
+        if (r == 0) { c->grp.root_fb[0] = fb[0]; c->grp.root_fb[1] = fb[1]; }
+    }
+    GSR_CUDA_TRY(cudaMemsetAsync(c->grp.arena, 0, GROUP_FLAGS_BYTES, c->stream));   // flags start at seq 0 (all ranks attach, then barrier)
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->grp.rank = rank; c->grp.world = world; c->grp.slice = slice; c->grp.seq = 0;
+    c->row_mod = world; c->row_rem = rank;   // cyclic tile rows: balanced by construction
+    c->band_y0 = 0; c->band_y1 = c->tiles_y; c->band_set = false;
+    c->copied_valid[0] = c->copied_valid[1] = false;
+    return GSR_OK;
+}
+
+GSR_API int gsr_group_detach(gsr_ctx *c) {
     if (!c) return GSR_ERR_INVALID;
-    if (enable && !c->extents) { set_last_error("gsr_shard_use_extents before gsr_shard_extents_ptr / _compute"); return GSR_ERR_STATE; }
-    c->use_extents = enable != 0;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    group_detach(c);
     return GSR_OK;
 }
 
@@ -627,6 +786,15 @@ GSR_API int gsr_sync(gsr_ctx *c) {
     if (rc) return rc;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    if (c->grp.world > 1) {   // a device-side wait of the group protocol gave up (peer lost / frames enqueued out of lockstep)
+        uint32_t err = 0;
+        GSR_CUDA_TRY(cudaMemcpy(&err, &c->grp.flags[c->grp.rank]->error, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) {
+            cudaMemset(&c->grp.flags[c->grp.rank]->error, 0, sizeof err);
+            set_last_error("group: a device-side wait timed out (%s)", err == 1 ? "extent slices of a peer" : "done / released flag");
+            return GSR_ERR_STATE;
+        }
+    }
     return GSR_OK;
 }
 
@@ -655,6 +823,8 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
         ca.frame = c->pick_frame; ca.count_staged = 0;  // own queue counters; slot 0 of the queue, state slot 0
         ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
         ca.trace = nullptr; ca.trace_count = nullptr; ca.trace_cap = 0;
+        for (int i = 0; i < 2; ++i)   // the re-dispatch rewrites the tile's pixels: not under a read-back in flight
+            if (c->copied_valid[i]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));
         GSR_CUDA_TRY(cudaMemsetAsync(c->pick_frame, 0, sizeof(FrameState), c->stream));
         GSR_CUDA_TRY(cudaMemsetAsync(c->comp_queue, 0, sizeof(uint32_t) * GSR_COMP_MAX_PUSHES, c->stream));  // one tile => <= 7 pushes
         if ((rc = launch_composite(ca, c->stream))) return rc;

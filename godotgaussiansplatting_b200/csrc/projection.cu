@@ -729,21 +729,44 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
     }
 }
 
-// EXPERIMENTAL (gsr_shard_extents_compute): tile-row extent of the un-banded rect of splats [first, first + count) -- the exact
-// rect of gsplat_projection.glsl:144-148,191 (same project_lane), y0 | y1 << 16, 0 when the splat emits nothing.  `a` must
-// describe the FULL frame (band = all rows, row_mod = 1, no reject): launch_extents() prepares that copy.
+// Group mode (gsr_group_attach): tile-row extent of the un-banded rect of splats [first, first + count) -- the exact rect of
+// gsplat_projection.glsl:144-148,191 (same project_lane), y0 | y1 << 16, 0 when the splat emits nothing -- stored into the
+// extent table of EVERY rank of the group: the all-gather of the cull is fused into the kernel that computes it, as 4-byte
+// peer stores over NVLink (a warp writes one 128-byte line per rank).  `a` must describe the FULL frame (band = all rows,
+// row_mod = 1, no reject): launch_extents() prepares that copy.  The CTA that finishes last publishes
+// seq << 32 | (last tile of the slice + 1) to meta[parity][rank] of every rank: data first, system fence, then the flag.
 __global__ void __launch_bounds__(PROJ_THREADS) extent_kernel(const __grid_constant__ ProjectionArgs a, uint32_t first, uint32_t count,
-                                                              uint32_t *__restrict__ extents) {
+                                                              const __grid_constant__ GroupPeers peers, int parity, uint32_t seq) {
+    __shared__ uint32_t s_is_last;
     const uint32_t i = blockIdx.x * PROJ_THREADS + threadIdx.x;
-    if (i >= count) return;
     const uint32_t id = first + i;
     uint32_t e = 0u;
-    if (id < a.num_splats) {
+    int32_t last = -1;
+    if (i < count && id < a.num_splats) {
         LaneOut o;
         if (project_lane<false>(a, __ldg(a.soa + id), __ldg(a.soa + a.plane_stride + id), __ldg(a.soa + 2ull * a.plane_stride + id), o) && o.n)
             e = o.y0 | ((o.y0 + o.n / o.w) << 16);
+        last = o.last_tile;
     }
-    extents[id] = e;
+    if (i < count) {
+#pragma unroll 4
+        for (int r = 0; r < peers.world; ++r) peers.table[r][id] = e;
+    }
+    GroupFlags *mine = peers.flags[peers.rank];
+    const int32_t wl = __reduce_max_sync(0xffffffffu, last);
+    if ((threadIdx.x & 31u) == 0u && wl >= 0) atomicMax(&mine->ext_last, wl + 1);
+    __threadfence_system();   // this thread's table stores (and the atomicMax) are ordered before the ticket below
+    __syncthreads();
+    if (threadIdx.x == 0) s_is_last = atomicAdd(&mine->ext_ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (s_is_last && threadIdx.x < 32u) {
+        __threadfence_system();
+        const int32_t lp1 = *(volatile int32_t *)&mine->ext_last;
+        const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)(uint32_t)(lp1 > 0 ? lp1 : 0);
+        if ((int)threadIdx.x < peers.world) *(volatile unsigned long long *)&peers.flags[threadIdx.x]->meta[parity][peers.rank] = word;
+        __syncwarp();
+        if (threadIdx.x == 0) { mine->ext_last = 0; mine->ext_ticket = 0u; __threadfence(); }   // ready for the next frame (stream order)
+    }
 }
 
 }  // namespace
@@ -751,12 +774,12 @@ __global__ void __launch_bounds__(PROJ_THREADS) extent_kernel(const __grid_const
 uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_THREADS - 1) / PROJ_THREADS; }
 
 #ifndef GSR_CPU_EMU  // host side: CUDA only
-int launch_extents(const ProjectionArgs &frame_args, uint32_t first, uint32_t count, uint32_t *extents, cudaStream_t stream) {
-    if (count == 0) return GSR_OK;
+int launch_extents(const ProjectionArgs &frame_args, uint32_t first, uint32_t count, const GroupPeers &peers, int parity, uint32_t seq, cudaStream_t stream) {
     ProjectionArgs a = frame_args;   // the whole frame: no band, no row ownership, no reject
     a.band_y0 = 0; a.band_y1 = (a.u.dims[1] + TILE - 1) / TILE;
     a.row_mod = 1; a.row_rem = 0; a.fast_reject = 0; a.fast_mode = 0; a.extents = nullptr;
-    extent_kernel<<<(count + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, 0, stream>>>(a, first, count, extents);
+    const uint32_t blocks = count ? (count + PROJ_THREADS - 1) / PROJ_THREADS : 1u;   // an empty slice still publishes its flag
+    extent_kernel<<<blocks, PROJ_THREADS, 0, stream>>>(a, first, count, peers, parity, seq);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

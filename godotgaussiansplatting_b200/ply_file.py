@@ -8,7 +8,7 @@ then chunked uploads through the C-ABI (`gsr_upload_splats_aos`), mirroring the 
 `buffer_update`s of the reference.  In the reference this step also runs on the host CPU.
 
 All float32 operations are written one IEEE op at a time in the order Godot's `Basis`/`Quaternion`
-code evaluates them, so the result is bit-identical to the C oracle's restatement (tests/test_ingest.py).
+code evaluates them, so the result is bit-identical to the C oracle's restatement (tests/test_oracle.py).
 """
 from __future__ import annotations
 

@@ -225,21 +225,19 @@ class GaussianSplattingRasterizer:
         buf = (C.c_ubyte * 128).from_buffer_copy(handles)
         _lib.check(_lib.lib().gsr_peer_import_framebuffers(self._ctx, buf), "gsr_peer_import_framebuffers")
 
-    # ---- EXPERIMENTAL multi-GPU: split the per-frame cull across the ranks (include/gsr.h gsr_shard_*) ----
-    def shard_extents_ptr(self):
-        cap = C.c_uint64(0)
-        ptr = _lib.lib().gsr_shard_extents_ptr(self._ctx, C.byref(cap))
-        if not ptr:
-            raise RuntimeError("gsr_shard_extents_ptr: " + _lib.lib().gsr_last_error().decode())
-        return int(ptr), int(cap.value)
+    # ---- multi-GPU shard group (include/gsr.h gsr_group_*): NCCL-free frame path over NVLink peer memory ----
+    def group_export(self) -> bytes:
+        buf = (C.c_ubyte * _lib.GSR_GROUP_BLOB_BYTES)()
+        _lib.check(_lib.lib().gsr_group_export(self._ctx, buf), "gsr_group_export")
+        return bytes(buf)
 
-    def shard_extents_compute(self, vp32, uniforms32: bytes, first: int, count: int) -> None:
-        vp = np.ascontiguousarray(vp32, dtype=np.float32)
-        _lib.check(_lib.lib().gsr_shard_extents_compute(self._ctx, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms32, int(first), int(count)),
-                   "gsr_shard_extents_compute")
+    def group_attach(self, rank: int, world: int, blobs: bytes) -> None:
+        assert len(blobs) == world * _lib.GSR_GROUP_BLOB_BYTES
+        buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
+        _lib.check(_lib.lib().gsr_group_attach(self._ctx, int(rank), int(world), buf), "gsr_group_attach")
 
-    def shard_use_extents(self, enable: bool) -> None:
-        _lib.check(_lib.lib().gsr_shard_use_extents(self._ctx, int(bool(enable))), "gsr_shard_use_extents")
+    def group_detach(self) -> None:
+        _lib.check(_lib.lib().gsr_group_detach(self._ctx), "gsr_group_detach")
 
     def stream_join(self) -> None:
         """Make the render stream wait for the pipelined read-back copies enqueued so far."""

@@ -170,15 +170,24 @@ GSR_API int gsr_render_async_rgb(gsr_ctx *ctx, const float view_proj[32], const 
 GSR_API int gsr_readback_async(gsr_ctx *ctx, float *pinned_host, int rgb_only);
 GSR_API int gsr_stream_join(gsr_ctx *ctx);
 
-/* ---- EXPERIMENTAL (multi-GPU, opt-in; no reference counterpart -- the reference is single-device): split the per-frame cull
- *      across the ranks instead of replicating it.  Per frame: every rank computes the tile-row extents (y0 | y1 << 16 of the
- *      exact, un-banded rect of gsplat_projection.glsl:144-148; 0 = emits nothing) of ITS slice of the splats; the host
- *      all-gathers the slices in place over NCCL (the table lives at gsr_shard_extents_ptr, `*capacity_out` uint32 entries,
- *      enough for 64 ranks' 256-aligned slices); gsr_render then runs the projection maths only for the splats whose rows this
- *      rank owns (gsr_shard_use_extents(ctx, 1); requires gsr_set_row_interleave).  Same rects, same emission order. ---- */
-GSR_API void *gsr_shard_extents_ptr(gsr_ctx *ctx, uint64_t *capacity_out);
-GSR_API int gsr_shard_extents_compute(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, uint64_t first, uint64_t count);
-GSR_API int gsr_shard_use_extents(gsr_ctx *ctx, int enable);
+/* ---- Multi-GPU shard group (no reference counterpart -- the reference is single-device).  One context per GPU,
+ *      in one process (a thread per GPU) or in one process per GPU.  The frame path of an attached group uses neither the
+ *      host nor NCCL: per frame every rank (1) culls ITS slice of the splats and stores their tile-row extents into every rank's
+ *      table with peer stores over NVLink/NVSwitch, (2) runs the projection maths only for the splats whose tile rows it owns
+ *      (cyclic rows: row % world == rank), sorts and scans its own pairs, (3) composites its rows straight into the presenting
+ *      rank's (rank 0) frame; sequence-numbered flag words written with system-scope stores order all of it on the devices.
+ *      Results are bit-identical to the single-GPU frame (same rects, same emission order, exact Q10 bookkeeping).
+ *        every rank:  gsr_resize; gsr_group_export(ctx, blob)            -> exchange the blobs (any transport)
+ *                     gsr_group_attach(ctx, rank, world, all_blobs)       -> barrier once (any transport)
+ *        per frame:   gsr_render_async(ctx, vp, uniforms, heat, NULL) on every rank (same frame order everywhere);
+ *                     rank 0: gsr_readback_async(ctx, pinned, rgb_only) and/or gsr_framebuffer_device_ptr
+ *      gsr_resize detaches (export / attach again).  A lost peer makes the bounded device-side waits expire: gsr_sync then
+ *      returns GSR_ERR_STATE instead of the GPU hanging. ---- */
+#define GSR_GROUP_BLOB_BYTES 320
+#define GSR_GROUP_MAX_RANKS 16
+GSR_API int gsr_group_export(gsr_ctx *ctx, void *blob /* GSR_GROUP_BLOB_BYTES */);
+GSR_API int gsr_group_attach(gsr_ctx *ctx, int32_t rank, int32_t world, const void *blobs /* world x GSR_GROUP_BLOB_BYTES, rank order */);
+GSR_API int gsr_group_detach(gsr_ctx *ctx);
 GSR_API int gsr_sync(gsr_ctx *ctx);
 
 /* Device pointer of the RGBA32F frame (render_texture.texture_rd_rid, rasterizer.gd:48,101); row-major W*H. */

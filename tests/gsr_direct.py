@@ -75,6 +75,27 @@ class Ctx:
                                      None if out is None else C.c_void_p(out.ctypes.data)), "gsr_render")
         return out
 
+    # ---- multi-GPU shard group (gsr_group_*) ----
+    def group_export(self) -> bytes:
+        buf = (C.c_ubyte * _lib.GSR_GROUP_BLOB_BYTES)()
+        _lib.check(self.L.gsr_group_export(self.h, buf), "gsr_group_export")
+        return bytes(buf)
+
+    def group_attach(self, rank, world, blobs: bytes):
+        buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
+        _lib.check(self.L.gsr_group_attach(self.h, rank, world, buf), "gsr_group_attach")
+
+    def render_async(self, vp, uniforms, heatmap=0.0, host_ptr=None):
+        vp = np.ascontiguousarray(vp, dtype=np.float32)
+        _lib.check(self.L.gsr_render_async(self.h, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms, float(heatmap),
+                                           None if host_ptr is None else C.c_void_p(host_ptr)), "gsr_render_async")
+
+    def readback_async(self, host_ptr, rgb_only=False):
+        _lib.check(self.L.gsr_readback_async(self.h, C.c_void_p(host_ptr), int(rgb_only)), "gsr_readback_async")
+
+    def sync(self):
+        _lib.check(self.L.gsr_sync(self.h), "gsr_sync")
+
     def stats(self):
         st = _lib.GsrStats()
         _lib.check(self.L.gsr_get_stats(self.h, C.byref(st)), "gsr_get_stats")

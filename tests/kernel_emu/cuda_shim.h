@@ -74,6 +74,7 @@ inline int __reduce_max_sync(unsigned, int v) {
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 inline void __threadfence_block() {}
 inline void __nanosleep(unsigned) { ::glsl::spin_yield(); }   /* a spin-wait iteration: let everybody else run first (the scheduler
                                                                   aborts if nobody ever satisfies the wait) */

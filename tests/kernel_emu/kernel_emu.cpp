@@ -195,10 +195,17 @@ extern "C" long long emu_projection(const void *soa, unsigned long long plane_st
         gsr::ProjectionArgs fa = pa;
         fa.band_y0 = 0; fa.band_y1 = (fa.u.dims[1] + gsr::TILE - 1) / gsr::TILE;
         fa.row_mod = 1; fa.row_rem = 0; fa.fast_reject = 0; fa.fast_mode = 0; fa.extents = nullptr;
-        struct EL { gsr::ProjectionArgs a; unsigned first, count; uint32_t *out; } el{fa, ext_first, ext_count, extents_out};
-        run_blocks((ext_count + gsr::PROJ_THREADS - 1) / gsr::PROJ_THREADS, (unsigned)gsr::PROJ_THREADS,
-                   [](void *p) { EL *l = static_cast<EL *>(p); gsr::extent_kernel(l->a, l->first, l->count, l->out); }, &el);
-        return 0;
+        // group of one "rank": the peer-store loop writes the single table; the last block publishes seq << 32 | last tile + 1
+        static gsr::GroupFlags flags;
+        memset(&flags, 0, sizeof flags);
+        gsr::GroupPeers peers;
+        memset(&peers, 0, sizeof peers);
+        peers.world = 1; peers.rank = 0; peers.flags[0] = &flags; peers.table[0] = extents_out;
+        struct EL { gsr::ProjectionArgs a; unsigned first, count; gsr::GroupPeers peers; } el{fa, ext_first, ext_count, peers};
+        run_blocks(ext_count ? (ext_count + gsr::PROJ_THREADS - 1) / gsr::PROJ_THREADS : 1u, (unsigned)gsr::PROJ_THREADS,
+                   [](void *p) { EL *l = static_cast<EL *>(p); gsr::extent_kernel(l->a, l->first, l->count, l->peers, 1, 77u); }, &el);
+        if (flags.ext_ticket != 0u || flags.ext_last != 0 || (uint32_t)(flags.meta[1][0] >> 32) != 77u) return -1;   // protocol words reset / published
+        return (long long)(uint32_t)flags.meta[1][0];   // last tile of the slice + 1
     }
     pa.extents = extents;
     gsr::FrameState frame;

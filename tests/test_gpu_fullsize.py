@@ -96,3 +96,59 @@ def test_full_size_frame_properties(n, seed, frame):
     for yy, xx in list(zip(ty, tx))[:200]:
         blk = img[yy * 16:(yy + 1) * 16, xx * 16:(xx + 1) * 16, :3]
         assert not blk.any()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Direct CUDA-vs-oracle parity at the sizes BASELINE.json names: the frames bench.py times are
+# compared with the oracle stage by stage -- sort keys / values / tile ranges array-equal, RGBA bit-equal (bar: 1e-4).
+# The scene goes through the device-side ingest (gsr_upload_ply_raw), exactly like bench.py builds it; the oracle gets
+# its own restatement of the ingest (orc_preprocess_ply).
+# ---------------------------------------------------------------------------------------------------------------------
+FULL = {
+    "c2": dict(n=1_000_000, seed=1, w=1920, h=1080, frames=[None]),
+    "c3": dict(n=6_000_000, seed=2, w=1920, h=1080, frames=[37, 211]),
+    "c4": dict(n=10_000_000, seed=3, w=3840, h=2160, frames=[0]),
+}
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4"])
+def test_full_size_frame_equals_oracle(name):
+    from oracle import oracle as orc
+    cfg = FULL[name]
+    n, w, h = cfg["n"], cfg["w"], cfg["h"]
+    gy = (h + 15) // 16
+    host = np.empty((n, 60), dtype=np.float32)
+    with Ctx(n, w, h) as c:
+        for lo, blk in synthetic_ply_chunks(n, cfg["seed"]):
+            c.upload_ply_raw(blk, first=lo, creation_time=0.0)
+            host[lo:lo + blk.shape[0]] = orc.preprocess_ply(blk, 0.0)
+        for frame in cfg["frames"]:
+            camera = cam.default_camera(aspect=w / h) if frame is None else cam.orbit_camera(frame, aspect=w / h)
+            vp = cam.pack_camera_push_constants(camera.get_camera_transform(), camera.get_camera_projection())
+            ub = uniforms_bytes(camera.global_position, 1.0, w, h, 10.0)
+            ref = orc.frame(host, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+            c.set_band(0, gy)
+            img = c.render(vp, ub)
+            t = c.taps()
+            st = t["stats"]
+            assert not st.overflow and not ref.overflow
+            assert st.duplicates == ref.duplicates and st.visible == ref.visible and st.last_tile == ref.last_tile
+            assert st.staged == ref.staged
+            np.testing.assert_array_equal(t["keys"], ref.keys)
+            np.testing.assert_array_equal(t["values"], ref.values)
+            np.testing.assert_array_equal(t["bounds"], ref.bounds)
+            vis = np.unique(ref.values)
+            np.testing.assert_array_equal(t["records"][vis].view(np.uint32), ref.records[vis].view(np.uint32))
+            assert float(np.abs(img - ref.rgba).max()) <= 1e-4          # the north-star bar ...
+            np.testing.assert_array_equal(img.view(np.uint32), ref.rgba.view(np.uint32))  # ... and what gsr actually delivers
+            if name == "c4":  # the multi-GPU configuration: four tile-row bands reassemble the same frame and the same sorted pairs
+                keys_b, vals_b, img_b = [], [], np.zeros_like(img)
+                for band in [(0, 34), (34, 68), (68, 102), (102, gy)]:
+                    c.set_band(*band)
+                    part = c.render(vp, ub)
+                    tb = c.taps()
+                    keys_b.append(tb["keys"]); vals_b.append(tb["values"])
+                    img_b[band[0] * 16:min(band[1] * 16, h)] = part[band[0] * 16:min(band[1] * 16, h)]
+                np.testing.assert_array_equal(np.concatenate(keys_b), ref.keys)
+                np.testing.assert_array_equal(np.concatenate(vals_b), ref.values)
+                np.testing.assert_array_equal(img_b.view(np.uint32), ref.rgba.view(np.uint32))

@@ -226,10 +226,12 @@ def emu_upload(splat60, chunk=None):
 
 
 def emu_extents(soa, stride, n, vp, ub, table, first, count):
-    """gsr_shard_extents_compute: fills table[first:first+count] (y0 | y1 << 16 of the un-banded rect, 0 = emits nothing)."""
+    """launch_extents (group mode): fills table[first:first+count] (y0 | y1 << 16 of the un-banded rect, 0 = emits nothing)."""
     vp = np.ascontiguousarray(vp, dtype=np.float32)
-    lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, 0, 0, 1, 0, 0, 0, None, None, None, 0, None, None, None,
-                         None, table.ctypes.data, first, count)
+    r = lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, 0, 0, 1, 0, 0, 0, None, None, None, 0, None, None, None,
+                             None, table.ctypes.data, first, count)
+    assert r >= 0, "extent kernel: flag protocol words not published / reset"
+    return int(r)   # last tile of the slice + 1 (what the kernel publishes next to the sequence number)
 
 
 def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, fast_reject=0, sh_bulk_min=0, cap=None, extents=None):
@@ -366,7 +368,7 @@ def test_whole_pipeline_through_the_emulated_kernels():
 
 @pytest.mark.parametrize("G", [2, 3, 8])
 def test_extent_table_mode_splits_the_cull_across_ranks(G):
-    """EXPERIMENTAL gsr_shard_*: every rank computes the tile-row extents of its slice of the splats, the slices are all-gathered,
+    """Group mode (gsr_group_*): every rank computes the tile-row extents of its slice of the splats, the slices are all-gathered,
     and every rank then projects only the splats whose rows it owns -- emitting exactly what the replicated cull emits."""
     n, w, h = 12000, 320, 240
     gx, gy = (w + 15) // 16, (h + 15) // 16
@@ -377,8 +379,8 @@ def test_extent_table_mode_splits_the_cull_across_ranks(G):
     # "all-gather": rank r fills its 256-aligned slice of the one table
     slice_len = ((n + G - 1) // G + 255) // 256 * 256
     table = np.full(G * slice_len, 0xDEADBEEF, dtype=np.uint32)
-    for r in range(G):
-        emu_extents(soa, stride, n, vp, ub, table, r * slice_len, slice_len)
+    lasts = [emu_extents(soa, stride, n, vp, ub, table, r * slice_len, slice_len) for r in range(G)]
+    assert max(lasts) == full.last_tile + 1   # the frame-global last occupied tile travels with the slices (exact Q10 bookkeeping)
     # the table is the exact rect: rows [y0, y1) of every visible splat, 0 otherwise
     tiles = full.keys >> 16
     row = (tiles // gx).astype(np.int64)
