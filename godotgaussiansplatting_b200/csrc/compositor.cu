@@ -674,6 +674,324 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v2_kernel(const
 }
 
 // ==============================================================================================================
+// "v3": the v2 structure (24 KB double-buffered staging, ONE __syncthreads per chunk, >= 6 CTAs/SM) with
+//   * TMA staging: every thread fetches the two raw 48-byte records of its slots with `cp.async.bulk` (SASS UBLKCP) onto the
+//     half's mbarrier -- no address registers held across the blend, no LDGSTS triplets; thread 0 arms the barrier with the
+//     chunk's byte count; everybody waits on it once, then pre-scales its own two records in place;
+//   * a two-instruction transmittance chain: alpha and (1 - alpha) are formed off the loop-carried path, the per-splat update is
+//     FMUL2 + FSEL (`t = alive ? t * (1 - alpha) : t`, bit-identical to multiplying by 1 - 0), instead of
+//     FSETP -> FSEL -> FADD2 -> FMUL2: a lone tile (tail of the kernel, sparse multi-GPU shards) advances faster;
+//   * CVT (experiment): round-to-nearest of the exp2 argument with F2I.RN / I2F (conversion pipe) instead of the two magic-constant
+//     FADD2s (FMA pipe) -- same integer, same fraction, same bits.
+#ifndef GSR_CPU_EMU
+__device__ __forceinline__ uint32_t comp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void comp_mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(comp_smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void comp_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void comp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void comp_mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(comp_smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void comp_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(comp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(comp_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void comp_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(comp_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+#else
+inline void comp_mbar_init(uint64_t *, uint32_t) {}
+inline void comp_fence_mbar_init() {}
+inline void comp_fence_proxy_async() {}
+inline void comp_mbar_expect_tx(uint64_t *, uint32_t) {}
+inline void comp_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+inline void comp_mbar_wait(uint64_t *, uint32_t) {}
+#endif
+
+// phase A over the one-array staging layout; also returns om2 = 1 - alpha (off the transmittance chain)
+template <bool CVT>
+__device__ __forceinline__ void phase_a_v3(const float4 *s, int j, u64 npx2, float fpy, const BlendK &K, u64 al2[GU], u64 om2[GU]) {
+    float4 A[GU];
+    float bx[GU], by[GU], oy[GU];
+    u64 ox2[GU], pw2[GU], tm2[GU], e2[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) { A[u] = s[3 * (j + u)]; const float4 b = s[3 * (j + u) + 1]; bx[u] = b.x; by[u] = b.y; }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = fma2(bc(A[u].w * oy[u]), bc(oy[u]), pw2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = mul2(bc(bx[u]), ox2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = fma2(e2[u], bc(oy[u]), pw2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], K.L2E2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        float tl, th;
+        upk(pw2[u], tl, th);
+        tl = g_min(g_max(tl, -127.0f), 128.0f);
+        th = g_min(g_max(th, -127.0f), 128.0f);
+        pw2[u] = pk(tl, th);
+    }
+    if (CVT) {
+        // n = rint(t) (ties to even, |t| <= 128): F2I.RN gives the integer the 1.5*2^23 trick leaves in the mantissa; the scale
+        // 2^n is assembled from it directly, and f = t - float(n) is the same subtraction
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float tl, th;
+            upk(pw2[u], tl, th);
+#ifndef GSR_CPU_EMU
+            const int nl = __float2int_rn(tl), nh = __float2int_rn(th);
+#else
+            const int nl = (int)nearbyintf(tl), nh = (int)nearbyintf(th);
+#endif
+            al2[u] = pk((float)nl, (float)nh);
+            tm2[u] = pk(__uint_as_float(((uint32_t)nl << 23) + 0x3F800000u), __uint_as_float(((uint32_t)nh << 23) + 0x3F800000u));
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) tm2[u] = add2(pw2[u], K.MAGIC2);
+#pragma unroll
+        for (int u = 0; u < GU; ++u) al2[u] = sub2(tm2[u], K.MAGIC2);
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) pw2[u] = sub2(pw2[u], al2[u]);  // f
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(K.C6, pw2[u], K.C5);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C4);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C3);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C2);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.C1);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = fma2(e2[u], pw2[u], K.ONE2);
+    if (!CVT) {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            float ml, mh;
+            upk(tm2[u], ml, mh);
+            tm2[u] = pk(__uint_as_float((__float_as_uint(ml) << 23) + 0x3F800000u), __uint_as_float((__float_as_uint(mh) << 23) + 0x3F800000u));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) e2[u] = mul2(e2[u], tm2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) al2[u] = mul2(bc(by[u]), e2[u]);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) om2[u] = sub2(K.ONE2, al2[u]);
+}
+
+// phase B with the short transmittance chain: per splat FMUL2 (t * (1 - alpha)) and one select per pixel
+__device__ __forceinline__ void phase_b_v3(const float4 *s, int j, const u64 al2[GU], const u64 om2[GU], u64 &cr2, u64 &cg2, u64 &cb2, float &t0, float &t1) {
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        const float4 b = s[3 * (j + u) + 1];
+        const float cbl = s[3 * (j + u) + 2].x;
+        const bool a0 = t0 > MIN_ALPHA, a1 = t1 > MIN_ALPHA;   // gsplat_render.glsl:79: a dead pixel has left the loop
+        float al, ah, pl, ph;
+        upk(al2[u], al, ah);
+        const u64 t2 = pk(t0, t1);
+        upk(mul2(t2, om2[u]), pl, ph);
+        const u64 m2 = pk(a0 ? al : 0.0f, a1 ? ah : 0.0f);
+        cr2 = fma2(mul2(bc(b.z), m2), t2, cr2);
+        cg2 = fma2(mul2(bc(b.w), m2), t2, cg2);
+        cb2 = fma2(mul2(bc(cbl), m2), t2, cb2);
+        t0 = a0 ? pl : t0;
+        t1 = a1 ? ph : t1;
+    }
+}
+
+template <int MIN_BLOCKS, bool CVT>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v3_kernel(const __grid_constant__ CompositeArgs p) {
+    __shared__ __align__(128) float4 s_st[2][CHUNK * 3];   // two staging halves; slot k = float4[3k..3k+2]: the raw 48-byte record lands
+                                                           // there (TMA) and is pre-scaled in place by the thread that fetched it
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_vote[2][THREADS / 32];
+    __shared__ uint32_t s_tile, s_resume;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const BlendK K = make_blend_k();
+    uint32_t staged = 0;
+    unsigned long long t_start = 0;
+    uint32_t phase0 = 0u, phase1 = 0u;   // mbarrier phase parity of the two halves (uniform across the CTA)
+    if (tid == 0) { comp_mbar_init(&s_bar[0], 1); comp_mbar_init(&s_bar[1], 1); comp_fence_mbar_init(); }
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) {
+            const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
+            if (ticket < (uint32_t)p.num_tiles) {
+                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                s_resume = 0u;
+            } else {
+                // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
+                const uint32_t qi = ticket - (uint32_t)p.num_tiles;
+                const bool in_q = qi < (uint32_t)COMP_MAX_PUSHES * (uint32_t)p.num_tiles;
+                volatile uint32_t *slot = p.queue + (in_q ? qi : 0u);
+                volatile uint32_t *done = &p.frame->comp_done;
+                uint32_t v = 0u;
+                while (in_q && (v = *slot) == 0u && *done < (uint32_t)p.num_tiles) __nanosleep(200);
+                if (in_q && v == 0u) v = *slot;
+                s_tile = v ? v - 1u : EXIT_TILE;
+                s_resume = 1u;
+                __threadfence();
+            }
+            if (p.trace) t_start = globaltimer_ns();
+        }
+        __syncthreads();
+        const uint32_t tile_id = s_tile;
+        const bool resume = s_resume != 0u;
+        if (tile_id == EXIT_TILE) break;
+
+        const uint32_t tx = tile_id % (uint32_t)p.tiles_x, ty = tile_id / (uint32_t)p.tiles_x;
+        const int px0 = (int)(tx * TILE + 2u * (tid & 7u)), py = (int)(ty * TILE + (tid >> 3));
+        const u64 npx2 = pk(-(float)px0, -(float)(px0 + 1));
+        const float fpy = (float)py;
+
+        const uint2 bounds = p.bounds[tile_id];
+        const int32_t diff = (int32_t)(bounds.y - bounds.x);
+        const int num_splats = diff > 0 ? diff : 0;
+        const int num_iterations = (int)ceilf((float)num_splats / (float)CHUNK);
+
+        u64 cr2 = pk(0.f, 0.f), cg2 = cr2, cb2 = cr2;
+        float t0 = 1.0f, t1 = 1.0f;
+        int i0 = 0;
+        const uint32_t rel = tile_id - (uint32_t)p.tile_begin;
+        const uint32_t local_tile = (rel / (uint32_t)(p.row_step * p.tiles_x)) * (uint32_t)p.tiles_x + rel % (uint32_t)p.tiles_x;
+        float4 *st = p.state + (uint64_t)local_tile * (2u * THREADS);
+        if (resume) {
+            const float4 sa = __ldcg(st + tid), sb = __ldcg(st + THREADS + tid);
+            cr2 = pk(sa.x, sa.y); cg2 = pk(sa.z, sa.w); cb2 = pk(sb.x, sb.y);
+            t0 = sb.z; t1 = sb.w;
+            i0 = (int)__ldcg(p.state_chunk + local_tile);
+        }
+
+        auto load_ids = [&](int ci, uint32_t &v0, uint32_t &v1) {
+            const int k0 = CHUNK * ci + (int)tid, k1 = k0 + THREADS;
+            v0 = (ci < num_iterations && k0 < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)k0) : 0xFFFFFFFFu;
+            v1 = (ci < num_iterations && k1 < num_splats) ? __ldg(p.values + bounds.x + (uint32_t)k1) : 0xFFFFFFFFu;
+        };
+        auto issue = [&](int ci, uint32_t v0, uint32_t v1, int b) {   // TMA: raw records of the two splats -> this thread's slots of half b
+            comp_fence_proxy_async();   // this thread's generic-proxy stores to its slots (pre-scale of an earlier chunk) precede the async writes
+            if (tid == 0) {
+                const int left = num_splats - CHUNK * ci;
+                comp_mbar_expect_tx(&s_bar[b], 48u * (uint32_t)(left < CHUNK ? left : CHUNK));
+            }
+            if (v0 != 0xFFFFFFFFu) comp_bulk_g2s(&s_st[b][3 * tid], p.records + (uint64_t)v0 * 3u, 48u, &s_bar[b]);
+            if (v1 != 0xFFFFFFFFu) comp_bulk_g2s(&s_st[b][3 * (tid + THREADS)], p.records + (uint64_t)v1 * 3u, 48u, &s_bar[b]);
+        };
+        auto finalize = [&](uint32_t v0, uint32_t v1, int b) {   // wait for the half, pre-scale the own two records in place like gather()
+            if (b == 0) { comp_mbar_wait(&s_bar[0], phase0); phase0 ^= 1u; } else { comp_mbar_wait(&s_bar[1], phase1); phase1 ^= 1u; }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float4 *d = &s_st[b][3 * (tid + (uint32_t)hh * THREADS)];
+                Staged sgd = null_splat();
+                if ((hh ? v1 : v0) != 0xFFFFFFFFu) {
+                    const float4 r0 = d[0], r1 = d[1], r2 = d[2];
+                    sgd.a = make_float4(r0.x, r0.y, -0.5f * r1.x, -0.5f * r1.z);
+                    sgd.b = make_float4(-r1.y, r2.w, r2.x, r2.y);
+                    sgd.c = r2.z;
+                }
+                d[0] = sgd.a; d[1] = sgd.b; d[2] = make_float4(sgd.c, 0.f, 0.f, 0.f);
+            }
+        };
+
+        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int i_begin = i0;
+        bool finished = true;
+        int b = 0;
+        uint32_t va0, va1, vb0 = 0xFFFFFFFFu, vb1 = 0xFFFFFFFFu;   // ids of the chunk being fetched / of the one after it
+        if (i0 < num_iterations) {
+            load_ids(i0, va0, va1);
+            issue(i0, va0, va1, 0);
+            load_ids(i0 + 1, vb0, vb1);
+            finalize(va0, va1, 0);
+        }
+        __syncthreads();   // staging half 0 visible (also orders the previous tile's last reads before this tile's writes)
+        for (int i = i_begin; i < num_iterations; ++i) {
+            const int sort_offset = CHUNK * i;
+            const int chunk = (num_splats - sort_offset) < CHUNK ? (num_splats - sort_offset) : CHUNK;
+            staged += (uint32_t)chunk;
+            const bool fetch_next = (i + 1 < num_iterations) && (i + 1 - i_begin < quantum);
+            if (fetch_next) {   // chunk i+1: records in flight during this blend, ids of chunk i+2 behind them
+                va0 = vb0; va1 = vb1;
+                issue(i + 1, va0, va1, b ^ 1);   // half b^1 was last read in blend(i-1): everybody is past that barrier
+                load_ids(i + 2, vb0, vb1);
+            }
+
+            const int chunk4 = (chunk + GU - 1) & ~(GU - 1);
+            for (int j = 0; j < chunk4; j += GU) {
+                if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
+                u64 al2[GU], om2[GU];
+                phase_a_v3<CVT>(s_st[b], j, npx2, fpy, K, al2, om2);
+                phase_b_v3(s_st[b], j, al2, om2, cr2, cg2, cb2, t0, t1);
+            }
+            if (fetch_next) finalize(va0, va1, b ^ 1);   // nobody reads half b^1 before the barrier below
+
+            const uint32_t wsum = __reduce_add_sync(0xffffffffu, (uint32_t)(t0 * 255.0f) + (uint32_t)(t1 * 255.0f));
+            if (lane == 0) s_vote[i & 1][warp] = wsum;
+            __syncthreads();   // the ONE barrier of the chunk: votes of chunk i and staging half b^1 (chunk i+1) visible
+            uint32_t shared_t = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) shared_t += s_vote[i & 1][w];
+            if (!(shared_t > 255u)) break;
+            if (i + 1 < num_iterations && i + 1 - i_begin >= quantum) {
+                finished = false;
+                i0 = i + 1;
+                break;
+            }
+            b ^= 1;
+        }
+
+        float r0, r1, g0, g1, b0, b1;
+        upk(cr2, r0, r1); upk(cg2, g0, g1); upk(cb2, b0, b1);
+        if (!finished) {
+            __stcg(st + tid, make_float4(r0, r1, g0, g1));
+            __stcg(st + THREADS + tid, make_float4(b0, b1, t0, t1));
+            if (tid == 0) __stcg(p.state_chunk + local_tile, (uint32_t)i0);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t slot = atomicAdd(&p.frame->comp_tail, 1u);
+                __threadfence();
+                *(volatile uint32_t *)(p.queue + slot) = tile_id + 1u;
+            }
+        } else {
+            const float hx = (float)num_splats * 5e-4f;  // :100-101
+            const float h0 = 0.0f * (1.0f - hx) + 1.0f * hx, h1 = 0.0f * (1.0f - hx) + 0.2f * hx, h2c = 1.0f * (1.0f - hx) + 0.2f * hx;
+            if (py < p.height) {
+                float4 *row = p.out + (uint64_t)py * (uint64_t)p.width;
+                const float k0 = 1.0f - t0, k1 = 1.0f - t1;
+                if (px0 < p.width)
+                    row[px0] = make_float4(r0 + h0 * k0 * p.heatmap_factor, g0 + h1 * k0 * p.heatmap_factor, b0 + h2c * k0 * p.heatmap_factor, 1.0f);
+                if (px0 + 1 < p.width)
+                    row[px0 + 1] = make_float4(r1 + h0 * k1 * p.heatmap_factor, g1 + h1 * k1 * p.heatmap_factor, b1 + h2c * k1 * p.heatmap_factor, 1.0f);
+            }
+            if ((tid & 15u) == 0u && tile_id == p.target_tile_id && t0 != 1.0f) {  // :105-110 pick
+                const uint32_t v = p.values[bounds.x + (bounds.y - bounds.x) / 10u];
+                const float4 q0 = p.records[(uint64_t)v * 3u + 0], q1 = p.records[(uint64_t)v * 3u + 1];
+                *p.pick = make_float4(q0.z, q0.w, q1.w, (float)num_splats);
+            }
+            if (tid == 0) atomicAdd(&p.frame->comp_done, 1u);
+        }
+        if (p.trace && tid == 0) {
+            const uint32_t k = atomicAdd(p.trace_count, 1u);
+            if (k < p.trace_cap) p.trace[k] = make_ulonglong4(((unsigned long long)tile_id << 32) | smid(), t_start, globaltimer_ns(), ((unsigned long long)(uint32_t)i_begin << 32) | (uint32_t)(finished ? 1u : 0u) | ((uint32_t)num_iterations << 1));
+        }
+        __syncthreads();  // s_tile / staging buffers are reused by the next item
+    }
+    if (tid == 0 && staged && p.count_staged) atomicAdd(&p.frame->staged, (unsigned long long)staged);
+}
+
+// ==============================================================================================================
 // EXPERIMENTAL "p4" variant (GSR_COMP_P4=1; off by default, NOT yet run on a GPU; logic checked by tests/test_kernel_emu.py).
 // v2 staging, but 64 threads per tile and FOUR horizontally adjacent pixels (two packed pairs) per thread: the shared-memory
 // loads and the row terms (oy, cz*oy) of a splat are shared by both pairs, and every splat offers two independent
@@ -1175,7 +1493,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 #ifndef GSR_CPU_EMU
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, use_p4 = 0, cfg_dev = -1;
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, use_p4 = 0, use_v3 = 0, use_cvt = 0, cfg_dev = -1;
     int dev = 0;
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     if (cfg_dev != dev) {
@@ -1190,7 +1508,16 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         const char *p4e = getenv("GSR_COMP_P4");  // experiment knob: 1 = four pixels per thread on top of the v2 staging (bit-identical results)
         use_p4 = (p4e && atoi(p4e) != 0 && !use_ws && !use_hwexp) ? 1 : 0;
         if (use_p4) use_v2 = 0;
-        if (use_p4) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_p4_kernel, P4_THREADS, 0));
+        const char *v3e = getenv("GSR_COMP_V3");   // experiment knob: TMA staging + short transmittance chain; value = CTAs/SM target (6 or 8)
+        use_v3 = (v3e && atoi(v3e) != 0 && !use_ws && !use_hwexp && !use_p4) ? atoi(v3e) : 0;
+        const char *cvte = getenv("GSR_COMP_CVT");
+        use_cvt = (cvte && atoi(cvte) != 0) ? 1 : 0;
+        if (use_v3) use_v2 = 0;
+        if (use_v3 >= 8 && use_cvt) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<8, true>, THREADS, 0));
+        else if (use_v3 >= 8) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<8, false>, THREADS, 0));
+        else if (use_v3 && use_cvt) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<6, true>, THREADS, 0));
+        else if (use_v3) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<6, false>, THREADS, 0));
+        else if (use_p4) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_p4_kernel, P4_THREADS, 0));
         else if (use_v2 >= 8) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<8>, THREADS, 0));
         else if (use_v2 >= 6) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<6>, THREADS, 0));
         else if (use_v2) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<5>, THREADS, 0));
@@ -1202,7 +1529,11 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
     const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
-    if (use_p4) composite_p4_kernel<<<grid, P4_THREADS, 0, stream>>>(a);
+    if (use_v3 >= 8 && use_cvt) composite_v3_kernel<8, true><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3 >= 8) composite_v3_kernel<8, false><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3 && use_cvt) composite_v3_kernel<6, true><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3) composite_v3_kernel<6, false><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_p4) composite_p4_kernel<<<grid, P4_THREADS, 0, stream>>>(a);
     else if (use_v2 >= 8) composite_v2_kernel<8><<<grid, THREADS, 0, stream>>>(a);
     else if (use_v2 >= 6) composite_v2_kernel<6><<<grid, THREADS, 0, stream>>>(a);
     else if (use_v2) composite_v2_kernel<5><<<grid, THREADS, 0, stream>>>(a);

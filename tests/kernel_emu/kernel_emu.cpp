@@ -21,6 +21,8 @@ void body(void *p) {
         case 0: gsr::composite_kernel<false>(*l->args); break;   // the shipped kernel
         case 1: gsr::composite_v2_kernel<5>(*l->args); break;       // GSR_COMP_V2
         case 3: gsr::composite_p4_kernel(*l->args); break;       // GSR_COMP_P4 (64 threads)
+        case 4: gsr::composite_v3_kernel<6, false>(*l->args); break;   // GSR_COMP_V3: TMA staging, short transmittance chain
+        case 5: gsr::composite_v3_kernel<6, true>(*l->args); break;    // ... + F2I/I2F rounding of the exp2 argument
         default: gsr::composite_kernel<true>(*l->args); break;   // GSR_COMP_HWEXP (exp2f stands in for MUFU.EX2)
     }
 }

@@ -83,6 +83,37 @@ def main():
             assert np.array_equal(got.view(np.uint32), ref.rgba.view(np.uint32)), "gathered frame differs"
             print("NCCL_GATHER_OK", flush=True)
     dist.barrier()
+    # ---- (c) shard group: NCCL-free frame path (extent slices + rows over NVLink peer memory, device-side flags) ----
+    gx = (w + 15) // 16
+    with Ctx(n, w, h, device=local) as c:
+        _lib.check(L.gsr_set_stream(c.h, C.c_void_p(stream.cuda_stream)), "stream")
+        c.upload(splat60)
+        mine = torch.frombuffer(bytearray(c.group_export()), dtype=torch.uint8).cuda()
+        blobs = torch.zeros(world * _lib.GSR_GROUP_BLOB_BYTES, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(blobs, mine)          # set-up only: NCCL is not on the frame path
+        c.group_attach(rank, world, blobs.cpu().numpy().tobytes())
+        dist.barrier()
+        seq = [frames[k % len(frames)] for k in range(7)]   # > 2 frames in flight: exercises slot release + flag parity
+        hosts = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in seq]
+        for k, (_, vp, ub) in enumerate(seq):
+            c.render_async(vp, ub)
+            if rank == 0:
+                c.readback_async(hosts[k].data_ptr())
+        c.sync()
+        t = c.taps()
+        _, vp, ub = seq[-1]
+        ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+        sel = ((ref.keys >> 16) // gx) % world == rank
+        assert np.array_equal(t["keys"], ref.keys[sel]) and np.array_equal(t["values"], ref.values[sel]), f"rank {rank}: pairs differ"
+        assert t["stats"].last_tile == ref.last_tile
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            for k, (_, vp, ub) in enumerate(seq):
+                ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+                assert np.array_equal(hosts[k].numpy().view(np.uint32), ref.rgba.view(np.uint32)), f"group frame {k} differs"
+            print("GROUP_MODE_OK", flush=True)
+        dist.barrier()
     dist.destroy_process_group()
 
 

@@ -21,4 +21,4 @@ def test_two_gpu_band_sharding_matches_oracle():
                           "--master-port", "29541", os.path.join(ROOT, "tests", "multi_gpu_worker.py")],
                          capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
-    assert "PEER_MODE_OK" in res.stdout and "NCCL_GATHER_OK" in res.stdout
+    assert "PEER_MODE_OK" in res.stdout and "NCCL_GATHER_OK" in res.stdout and "GROUP_MODE_OK" in res.stdout

@@ -92,7 +92,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("variant", [SHIPPED, V2, P4], ids=["shipped", "v2", "p4"])
+@pytest.mark.parametrize("variant", [SHIPPED, V2, P4, 4, 5], ids=["shipped", "v2", "p4", "v3", "v3cvt"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_compositor_kernels_reproduce_the_oracle(case, variant):
     n, seed, w, h, heat, kw = CASES[case]
@@ -112,7 +112,7 @@ def test_hwexp_variant_stays_inside_the_tolerance():
     assert np.abs(out - fr.rgba).max() <= 1e-4 and staged == fr.staged
 
 
-@pytest.mark.parametrize("variant", [SHIPPED, V2, P4], ids=["shipped", "v2", "p4"])
+@pytest.mark.parametrize("variant", [SHIPPED, V2, P4, 4, 5], ids=["shipped", "v2", "p4", "v3", "v3cvt"])
 def test_pick_and_row_interleave(variant):
     n, seed, w, h = 20000, 15, 320, 240
     fr = oracle_frame(n, seed, w, h, scale_boost=1.0)
