@@ -12,14 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSR_LIB_PATH") or os.path.join(HERE, "libgsr.so")  # env override: kernel-variant experiments only
 
 GSR_OK, GSR_ERR_INVALID, GSR_ERR_CUDA, GSR_ERR_OOM, GSR_ERR_STATE, GSR_ERR_OVERFLOW = range(6)
-GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES, GSR_FLAG_FAST_REJECT = 0x1, 0x2, 0x4
+GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES, GSR_FLAG_FAST_REJECT, GSR_FLAG_STATIC_CAPACITY = 0x1, 0x2, 0x4, 0x8
 (GSR_BUF_RECORDS, GSR_BUF_KEYS, GSR_BUF_VALUES, GSR_BUF_BOUNDS, GSR_BUF_KEYS_UNSORTED, GSR_BUF_VALUES_UNSORTED,
  GSR_BUF_FRAMEBUFFER, GSR_BUF_COMPOSITOR_TRACE, GSR_BUF_COMPOSITOR_TRACE_COUNT) = range(9)
 
 # every symbol include/gsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_upload_ply_raw", "gsr_resize", "gsr_set_band", "gsr_set_row_interleave", "gsr_band_sync_word", "gsr_band_fixup", "gsr_render",
-    "gsr_render_async", "gsr_render_async_rgb", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
+    "gsr_render_async", "gsr_render_async_rgb", "gsr_render_async_fmt", "gsr_output_bytes", "gsr_present_device", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
     "gsr_stream_join", "gsr_group_export", "gsr_group_attach", "gsr_group_detach", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
     "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
@@ -40,6 +40,8 @@ class GsrStats(C.Structure):
 
 
 GSR_HISTORY_FRAMES = 512
+GSR_OUT_RGBA32F, GSR_OUT_RGB32F, GSR_OUT_RGBA16F, GSR_OUT_RGBA8 = range(4)
+GSR_OUT_SRGB_TO_LINEAR = 0x100
 GSR_GROUP_BLOB_BYTES = 320
 
 
@@ -80,6 +82,10 @@ def lib():
         L.gsr_render.argtypes = [vp, fp, vp, C.c_float, vp]
         L.gsr_render_async.argtypes = [vp, fp, vp, C.c_float, vp]
         L.gsr_render_async_rgb.argtypes = [vp, fp, vp, C.c_float, vp]
+        L.gsr_render_async_fmt.argtypes = [vp, fp, vp, C.c_float, vp, C.c_int32]
+        L.gsr_output_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.gsr_output_bytes.restype = C.c_size_t
+        L.gsr_present_device.argtypes = [vp, vp, C.c_int32]
         L.gsr_sync.argtypes = [vp]
         L.gsr_stream_join.argtypes = [vp]
         L.gsr_group_export.argtypes = [vp, vp]

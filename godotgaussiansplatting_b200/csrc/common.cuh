@@ -226,7 +226,18 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream);
 
 int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
                       cudaStream_t stream);
-int launch_pack_rgb(const float4 *rgba, float4 *rgb, uint64_t pixels, cudaStream_t stream);
+// present.cu: RGBA32F frame -> GSR_OUT_* (| GSR_OUT_SRGB_TO_LINEAR)
+int launch_present(const float4 *rgba, void *out, uint64_t pixels, int format, cudaStream_t stream);
+size_t present_bytes_per_pixel(int format);
 int launch_aos_to_soa(const float4 *aos, uint64_t count, float4 *soa, uint64_t plane_stride, uint64_t first, cudaStream_t stream);
+
+// cudaFuncGetAttributes on every kernel of a file: defeats lazy module loading before the first frame
+int preload_group_kernels();
+int preload_projection_kernels();
+int preload_sort_kernels();
+int preload_ranges_kernels();
+int preload_ingest_kernels();
+int preload_present_kernels();
+int preload_composite_kernels();
 
 }  // namespace gsr

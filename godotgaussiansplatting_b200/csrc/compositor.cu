@@ -1491,6 +1491,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 }  // namespace
 
 #ifndef GSR_CPU_EMU
+int preload_composite_kernels() {
+    cudaFuncAttributes fa;
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, composite_kernel<false>));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, composite_v3_kernel<6, false>));
+    return GSR_OK;
+}
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
     static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, use_p4 = 0, use_v3 = 0, use_cvt = 0, cfg_dev = -1;

@@ -61,6 +61,15 @@ __global__ void group_store_u32_kernel(GroupPeers peers, int which, int index, i
 }  // namespace
 
 #ifndef GSR_CPU_EMU
+// Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
+// kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
+int preload_group_kernels() {
+    cudaFuncAttributes fa;
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, group_wait_extents_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, group_wait_u32_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, group_store_u32_kernel));
+    return GSR_OK;
+}
 int launch_group_wait_extents(GroupFlags *flags, int parity, int world, uint32_t seq, FrameState *frame, cudaStream_t stream) {
     group_wait_extents_kernel<<<1, 32, 0, stream>>>(flags, parity, world, seq, frame, GSR_GROUP_TIMEOUT_NS);
     GSR_CUDA_TRY(cudaGetLastError());

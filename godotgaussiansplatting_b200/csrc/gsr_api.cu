@@ -53,7 +53,7 @@ struct gsr_ctx {
     uint32_t trace_cap = 0;
     float4 *fb = nullptr, *fb_ext = nullptr;
     float4 *fb2 = nullptr;                       // second frame for pipelined read-back (gsr_render_async)
-    float4 *rgb[2] = {nullptr, nullptr};         // RGB32F staging of the two frames (gsr_render_async_rgb), lazily allocated
+    void *stage[2] = {nullptr, nullptr};         // converted copies of the two frames (GSR_OUT_* other than RGBA32F), lazily allocated (16 B/pixel)
     float4 *fb_last = nullptr;                   // frame written by the most recent render
     cudaStream_t copy_stream = nullptr;          // D2H read-back overlaps the next frame's kernels
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -86,6 +86,13 @@ struct gsr_ctx {
         uint64_t slice = 0;               // splats per rank (256-aligned)
     } grp;
     cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
+    // dynamic duplicate capacity (replaces the reference's static 10 x N, rasterizer.gd:79 "FIXME: This should not be a static
+    // value!"): every frame's M travels to a pinned host mirror without a host sync; the capacity grows ahead of need
+    FrameState *host_ring = nullptr;       // pinned mirror of `ring`
+    cudaEvent_t *ev_stat = nullptr;        // [GSR_HISTORY_FRAMES] recorded after the slot's copy
+    uint64_t stats_polled = 0;             // frames whose mirror has been examined
+    uint64_t m_high = 0;                   // high-water mark of M over the examined frames
+    uint64_t capacity_max = 0;
     bool ev_valid = false;
     uint32_t last_launches = 0;
     int sm_count = 0;
@@ -145,7 +152,7 @@ void free_ctx(gsr_ctx *c) {
     sort_workspace_destroy(c->sort);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); }
-    cudaFree(c->rgb[0]); cudaFree(c->rgb[1]);
+    cudaFree(c->stage[0]); cudaFree(c->stage[1]);
     cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -157,6 +164,11 @@ void free_ctx(gsr_ctx *c) {
         for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         delete[] c->ev;
     }
+    if (c->ev_stat) {
+        for (int i = 0; i < GSR_HISTORY_FRAMES; ++i) if (c->ev_stat[i]) cudaEventDestroy(c->ev_stat[i]);
+        delete[] c->ev_stat;
+    }
+    if (c->host_ring) cudaFreeHost(c->host_ring);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -198,8 +210,9 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     if (!(c->flags & (GSR_FLAG_REFERENCE_QUIRKS | GSR_FLAG_FIXED_RANGES))) c->flags |= GSR_FLAG_REFERENCE_QUIRKS;
     c->max_splats = cfg->max_splats;
     const uint64_t factor = cfg->dup_capacity_factor ? cfg->dup_capacity_factor : 10;  // rasterizer.gd:79
+    c->capacity_max = (1ull << 30) - 1;  // look-back words carry 30-bit counts
     c->capacity = c->max_splats * factor;
-    if (c->capacity >= (1ull << 30)) c->capacity = (1ull << 30) - 1;  // look-back words carry 30-bit counts
+    if (c->capacity > c->capacity_max) c->capacity = c->capacity_max;
     c->plane_stride = (c->max_splats + 255ull) & ~255ull;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
 
@@ -242,11 +255,24 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) {
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
     }
+    c->ev_stat = new (std::nothrow) cudaEvent_t[GSR_HISTORY_FRAMES]();
+    if (!c->ev_stat) { free_ctx(c); return GSR_ERR_OOM; }
+    for (int i = 0; i < GSR_HISTORY_FRAMES; ++i) {
+        if (cudaEventCreateWithFlags(&c->ev_stat[i], cudaEventDisableTiming) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
+    }
+    if (cudaHostAlloc((void **)&c->host_ring, sizeof(FrameState) * GSR_HISTORY_FRAMES, cudaHostAllocDefault) != cudaSuccess) {
+        set_last_error("cudaHostAlloc(frame mirror) failed"); c->host_ring = nullptr; free_ctx(c); return GSR_ERR_OOM;
+    }
+    memset(c->host_ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES);
     cudaMemsetAsync(c->soa, 0, sizeof(float4) * NUM_PLANES * c->plane_stride, c->stream);
     cudaMemsetAsync(c->records, 0, sizeof(float4) * 3ull * c->max_splats, c->stream);
     cudaMemsetAsync(c->pick, 0, sizeof(float4), c->stream);
     cudaMemsetAsync(c->sync_word, 0, sizeof(int32_t), c->stream);
     cudaMemsetAsync(c->ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES, c->stream);
+    // load every kernel now: with lazy module loading a FIRST launch may have to synchronise with the device, which must not
+    // happen on the frame path (and would deadlock a group whose ranks share one process: a wait kernel spins meanwhile)
+    if ((rc = preload_group_kernels()) || (rc = preload_projection_kernels()) || (rc = preload_sort_kernels()) || (rc = preload_ranges_kernels()) ||
+        (rc = preload_ingest_kernels()) || (rc = preload_present_kernels()) || (rc = preload_composite_kernels())) { free_ctx(c); return rc; }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { set_last_error("init sync -> %s", cudaGetErrorString(e)); free_ctx(c); return GSR_ERR_CUDA; }
     *out = c;
@@ -323,7 +349,7 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaFree(c->fb); c->fb = nullptr;
     cudaFree(c->fb2); c->fb2 = nullptr;
-    cudaFree(c->rgb[0]); cudaFree(c->rgb[1]); c->rgb[0] = c->rgb[1] = nullptr;
+    cudaFree(c->stage[0]); cudaFree(c->stage[1]); c->stage[0] = c->stage[1] = nullptr;
     c->fb_last = nullptr; c->copied_valid[0] = c->copied_valid[1] = false;
     // peer mode refers to the frames freed above (exported) or to another process's frames of the old size (imported): drop it.
     // The host must export / import again after a resize (every rank resizes, then the presenting rank re-exports).
@@ -401,6 +427,42 @@ static void frame_constants(const float *view_proj, const Uniforms &u, Projectio
     }
 }
 
+// ---- dynamic duplicate capacity ------------------------------------------------------------------------------------------
+static int grow_capacity(gsr_ctx *c, uint64_t want) {
+    if (want > c->capacity_max) want = c->capacity_max;
+    if (want <= c->capacity) return GSR_OK;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    cudaFree(c->keys); cudaFree(c->vals); c->keys = c->vals = nullptr;
+    sort_workspace_destroy(c->sort);
+    const bool unsorted = c->unsorted_keys != nullptr;
+    cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); c->unsorted_keys = c->unsorted_vals = nullptr;
+    c->capacity = want;
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->keys, sizeof(uint32_t) * 2ull * c->capacity));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->vals, sizeof(uint32_t) * 2ull * c->capacity));
+    if (unsorted) {
+        GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_keys, sizeof(uint32_t) * c->capacity));
+        GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_vals, sizeof(uint32_t) * c->capacity));
+    }
+    return sort_workspace_create(c->sort, c->capacity, /*need_alt_buffers=*/false);
+}
+
+// Examine the mirrors of the frames that have completed since the last call (no host sync: event queries) and grow the
+// capacity once M has used more than half of it -- an overflow then needs M to more than double from one frame to the next.
+static int track_capacity(gsr_ctx *c) {
+    if (c->flags & GSR_FLAG_STATIC_CAPACITY) return GSR_OK;
+    while (c->stats_polled < c->frame_counter) {
+        if (c->frame_counter - c->stats_polled > GSR_HISTORY_FRAMES) { c->stats_polled = c->frame_counter - GSR_HISTORY_FRAMES; continue; }
+        const uint32_t slot = (uint32_t)(c->stats_polled % GSR_HISTORY_FRAMES);
+        if (cudaEventQuery(c->ev_stat[slot]) != cudaSuccess) { cudaGetLastError(); break; }
+        const uint64_t m = c->host_ring[slot].dup_total;
+        if (m > c->m_high) c->m_high = m;
+        c->stats_polled += 1;
+    }
+    if (c->m_high * 2ull > c->capacity && c->capacity < c->capacity_max) return grow_capacity(c, c->m_high * 3ull);
+    return GSR_OK;
+}
+
 struct GroupFrame { uint32_t seq; int parity; };
 
 static GroupPeers group_peers(const gsr_ctx *c, int parity) {
@@ -423,6 +485,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     }
     int rc = use_device(c->device);
     if (rc) return rc;
+    if ((rc = track_capacity(c))) return rc;
     cudaStream_t s = c->stream;
     int launches = 0;
     // rasterizer.gd:127-128: clear M (this frame's history slot) + look-back words, clear tile bounds
@@ -524,6 +587,9 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
         launches += 1;
     }
     GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Render'
+    // this frame's counters (M, overflow, C) to the pinned mirror: what track_capacity() reads without ever syncing
+    GSR_CUDA_TRY(cudaMemcpyAsync(c->host_ring + slot, c->frame, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_stat[slot], s));
     c->ev_valid = true;
     c->frame_counter += 1;
     c->last_launches = (uint32_t)launches;
@@ -535,23 +601,36 @@ GSR_API int gsr_render(gsr_ctx *c, const float view_proj[32], const void *unifor
     int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
     if (rc) return rc;
     if (out_host) {
+        // synchronous path: a frame that overflowed the duplicate capacity is never returned -- grow and render it again
+        // (the reference truncates silently: rasterizer.gd:79, main.gd:100; GSR_FLAG_STATIC_CAPACITY keeps that behaviour)
+        for (int attempt = 0; attempt < 8 && !(c->flags & GSR_FLAG_STATIC_CAPACITY); ++attempt) {
+            const uint32_t slot = (uint32_t)((c->frame_counter - 1) % GSR_HISTORY_FRAMES);
+            GSR_CUDA_TRY(cudaEventSynchronize(c->ev_stat[slot]));
+            const FrameState &fs = c->host_ring[slot];
+            if (!fs.overflow || c->capacity >= c->capacity_max) break;
+            if ((rc = grow_capacity(c, fs.dup_total + fs.dup_total / 4ull + 1024ull))) return rc;
+            if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor))) return rc;
+        }
         GSR_CUDA_TRY(cudaMemcpyAsync(out_host, framebuffer(c), sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
         GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     return GSR_OK;
 }
 
-static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, float *pinned_host, bool rgb_only, uint32_t group_seq = 0) {
+static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, void *pinned_host, int format, uint32_t group_seq = 0) {
     const size_t pixels = (size_t)c->width * c->height;
+    const size_t bpp = present_bytes_per_pixel(format);
+    if (!bpp) { set_last_error("unknown output format 0x%x", format); return GSR_ERR_INVALID; }
     int rc;
-    if (rgb_only && !c->rgb[slot]) GSR_CUDA_TRY(cudaMalloc((void **)&c->rgb[slot], sizeof(float) * 3 * pixels + 64));
+    const bool convert = format != GSR_OUT_RGBA32F;
+    if (convert && !c->stage[slot]) GSR_CUDA_TRY(cudaMalloc(&c->stage[slot], sizeof(float4) * pixels + 64));
     GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
     GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
     // group mode: the other ranks' rows arrive over NVLink; their done flags gate the copy (device-side wait on the copy stream)
     if (group_seq && (rc = launch_group_wait_done(c->grp.flags[c->grp.rank], c->grp.world, group_seq, c->copy_stream))) return rc;
-    if (rgb_only) {
-        if ((rc = launch_pack_rgb(frame, c->rgb[slot], pixels, c->copy_stream))) return rc;
-        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, c->rgb[slot], sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (convert) {
+        if ((rc = launch_present(frame, c->stage[slot], pixels, format, c->copy_stream))) return rc;
+        GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, c->stage[slot], bpp * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
     } else {
         GSR_CUDA_TRY(cudaMemcpyAsync(pinned_host, frame, sizeof(float4) * pixels, cudaMemcpyDeviceToHost, c->copy_stream));
     }
@@ -560,7 +639,7 @@ static int readback_enqueue(gsr_ctx *c, float4 *frame, int slot, float *pinned_h
     return GSR_OK;
 }
 
-static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, float *pinned_host, bool rgb_only) {
+static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uniforms32, float heatmap_factor, void *pinned_host, int format) {
     if (!c) return GSR_ERR_INVALID;
     if (c->grp.world > 1) {   // shard group: every rank enqueues the same frame; rows land in the presenting rank's frames
         if (pinned_host) { set_last_error("group mode: render with a NULL host pointer on every rank, then gsr_readback_async on rank 0"); return GSR_ERR_STATE; }
@@ -588,7 +667,7 @@ static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uni
         return GSR_OK;
     }
     if (!pinned_host || c->fb_ext) {  // nothing to read back, or the caller owns the frame memory: plain enqueue
-        if (rgb_only && pinned_host) { set_last_error("gsr_render_async_rgb is unavailable with an external framebuffer"); return GSR_ERR_STATE; }
+        if (format != GSR_OUT_RGBA32F && pinned_host) { set_last_error("converted read-back is unavailable with an external framebuffer"); return GSR_ERR_STATE; }
         int rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor);
         if (rc) return rc;
         if (pinned_host)
@@ -604,30 +683,54 @@ static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uni
     float4 *target = slot ? c->fb2 : c->fb;
     if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
     if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, target))) return rc;
-    if ((rc = readback_enqueue(c, target, slot, pinned_host, rgb_only))) return rc;
+    if ((rc = readback_enqueue(c, target, slot, pinned_host, format))) return rc;
     c->async_counter += 1;
     return GSR_OK;
 }
 
 GSR_API int gsr_render_async(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host) {
-    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host, false);
+    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host, GSR_OUT_RGBA32F);
 }
 
 GSR_API int gsr_render_async_rgb(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, float *pinned_host_rgb) {
-    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host_rgb, true);
+    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host_rgb, GSR_OUT_RGB32F);
 }
 
-GSR_API int gsr_readback_async(gsr_ctx *c, float *pinned_host, int rgb_only) {
+GSR_API int gsr_render_async_fmt(gsr_ctx *c, const float view_proj[32], const void *uniforms32, float heatmap_factor, void *pinned_host, int32_t format) {
+    if (!present_bytes_per_pixel(format)) { set_last_error("unknown output format 0x%x", format); return GSR_ERR_INVALID; }
+    return render_async_impl(c, view_proj, uniforms32, heatmap_factor, pinned_host, format);
+}
+
+GSR_API size_t gsr_output_bytes(int32_t format, int32_t width, int32_t height) {
+    return (width > 0 && height > 0) ? present_bytes_per_pixel(format) * (size_t)width * (size_t)height : 0;
+}
+
+// Converted copy of the most recent frame into CALLER-OWNED DEVICE memory on the render stream: the hand-off to an imported
+// external image / buffer (Vulkan VK_KHR_external_memory via cudaImportExternalMemory, done by the embedder) without touching the host.
+GSR_API int gsr_present_device(gsr_ctx *c, void *dst_device, int32_t format) {
+    if (!c || !dst_device) return GSR_ERR_INVALID;
+    if (!c->fb_last && !c->fb_ext) { set_last_error("gsr_present_device: no frame rendered yet"); return GSR_ERR_STATE; }
+    if (!present_bytes_per_pixel(format)) { set_last_error("unknown output format 0x%x", format); return GSR_ERR_INVALID; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    if (c->grp.world > 1) {   // the other ranks' rows must have landed (device-side wait, same stream)
+        if (c->grp.rank != 0) { set_last_error("gsr_present_device: only rank 0 of a group presents the frame"); return GSR_ERR_STATE; }
+        if ((rc = launch_group_wait_done(c->grp.flags[0], c->grp.world, c->grp.seq, c->stream))) return rc;
+    }
+    return launch_present(framebuffer(c), dst_device, (uint64_t)c->width * c->height, format, c->stream);
+}
+
+GSR_API int gsr_readback_async(gsr_ctx *c, void *pinned_host, int32_t format) {
     if (!c || !pinned_host) return GSR_ERR_INVALID;
     if (!c->fb_last || c->fb_ext) { set_last_error("gsr_readback_async: no library-owned frame rendered yet"); return GSR_ERR_STATE; }
     int rc = use_device(c->device);
     if (rc) return rc;
     if (c->grp.world > 1) {
         if (c->grp.rank != 0) { set_last_error("gsr_readback_async: only rank 0 of a group presents the frame"); return GSR_ERR_STATE; }
-        return readback_enqueue(c, c->fb_last, (int)((c->grp.seq - 1u) & 1u), pinned_host, rgb_only != 0, c->grp.seq);
+        return readback_enqueue(c, c->fb_last, (int)((c->grp.seq - 1u) & 1u), pinned_host, format, c->grp.seq);
     }
     const int slot = (c->fb_last == c->fb2 || (c->peer_mode && c->fb_last == c->peer_fb[1])) ? 1 : 0;
-    return readback_enqueue(c, c->fb_last, slot, pinned_host, rgb_only != 0);
+    return readback_enqueue(c, c->fb_last, slot, pinned_host, format);
 }
 
 GSR_API int gsr_peer_export_framebuffers(gsr_ctx *c, void *handles128) {

@@ -91,26 +91,17 @@ __global__ void __launch_bounds__(INGEST_SPLATS) ply_to_soa_kernel(const float *
     for (int k = 0; k < 12; ++k) soa[(uint64_t)(3 + k) * plane_stride + id] = make_float4(sh[4 * k], sh[4 * k + 1], sh[4 * k + 2], sh[4 * k + 3]);
 }
 
-// RGBA32F -> RGB32F packing for the host read-back: alpha is the constant 1.0 (gsplat_render.glsl:101), so it does not
-// have to cross PCIe.  Thread i converts pixels 4i..4i+3: four float4 loads, three float4 stores (both contiguous).
-__global__ void __launch_bounds__(256) pack_rgb_kernel(const float4 *__restrict__ rgba, float4 *__restrict__ rgb, uint64_t quads, uint64_t pixels) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= quads) return;
-    const uint64_t p0 = 4 * i;
-    if (p0 + 4 <= pixels) {
-        const float4 a = rgba[p0], b = rgba[p0 + 1], c = rgba[p0 + 2], d = rgba[p0 + 3];
-        rgb[3 * i + 0] = make_float4(a.x, a.y, a.z, b.x);
-        rgb[3 * i + 1] = make_float4(b.y, b.z, c.x, c.y);
-        rgb[3 * i + 2] = make_float4(c.z, d.x, d.y, d.z);
-    } else {  // ragged tail (pixel count not a multiple of 4)
-        float *o = reinterpret_cast<float *>(rgb) + 3 * p0;
-        for (uint64_t p = p0; p < pixels; ++p) { const float4 a = rgba[p]; *o++ = a.x; *o++ = a.y; *o++ = a.z; }
-    }
-}
-
 }  // namespace
 
 #ifndef GSR_CPU_EMU  // host side: CUDA only
+// Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
+// kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
+int preload_ingest_kernels() {
+    cudaFuncAttributes fa;
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, ply_to_soa_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, aos_to_soa_kernel));
+    return GSR_OK;
+}
 int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
                       cudaStream_t stream) {
     if (count == 0) return GSR_OK;
@@ -118,14 +109,6 @@ int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float c
     if (smem > 48 * 1024) GSR_CUDA_TRY(cudaFuncSetAttribute(ply_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (uint32_t)((count + INGEST_SPLATS - 1) / INGEST_SPLATS);
     ply_to_soa_kernel<<<blocks, INGEST_SPLATS, smem, stream>>>(ply, nprops, count, creation_time, soa, plane_stride, first);
-    GSR_CUDA_TRY(cudaGetLastError());
-    return GSR_OK;
-}
-
-int launch_pack_rgb(const float4 *rgba, float4 *rgb, uint64_t pixels, cudaStream_t stream) {
-    const uint64_t quads = (pixels + 3) / 4;
-    if (!quads) return GSR_OK;
-    pack_rgb_kernel<<<(uint32_t)((quads + 255) / 256), 256, 0, stream>>>(rgba, rgb, quads, pixels);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

@@ -774,6 +774,16 @@ __global__ void __launch_bounds__(PROJ_THREADS) extent_kernel(const __grid_const
 uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_THREADS - 1) / PROJ_THREADS; }
 
 #ifndef GSR_CPU_EMU  // host side: CUDA only
+// Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
+// kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
+int preload_projection_kernels() {
+    cudaFuncAttributes fa;
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel<false>));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel<true>));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, extent_kernel));
+    return GSR_OK;
+}
 int launch_extents(const ProjectionArgs &frame_args, uint32_t first, uint32_t count, const GroupPeers &peers, int parity, uint32_t seq, cudaStream_t stream) {
     ProjectionArgs a = frame_args;   // the whole frame: no band, no row ownership, no reject
     a.band_y0 = 0; a.band_y1 = (a.u.dims[1] + TILE - 1) / TILE;

@@ -319,6 +319,15 @@ int g_sm_count = 0;
 
 #ifndef GSR_CPU_EMU  // host side: CUDA only (tests/kernel_emu drives the kernels above itself)
 
+// Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
+// kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
+int preload_sort_kernels() {
+    cudaFuncAttributes fa;
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, sort_hist_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, onesweep_kernel<SWEEP_THREADS, SWEEP_ITEMS, true>));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, onesweep_kernel<SWEEP_THREADS, SWEEP_ITEMS, false>));
+    return GSR_OK;
+}
 size_t SortWorkspace::bytes() const {
     return sizeof(uint32_t) * (4 * RADIX + 8) + sizeof(uint32_t) * 4ull * max_tiles * RADIX + (alt_keys ? 8ull * max_n : 0);
 }

@@ -66,6 +66,14 @@ __global__ void __launch_bounds__(256) band_fixup_kernel(const int32_t *__restri
 }  // namespace
 
 #ifndef GSR_CPU_EMU  // tests/kernel_emu compiles the kernels above for the CPU; the launchers are CUDA only
+// Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
+// kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
+int preload_ranges_kernels() {
+    cudaFuncAttributes fa;
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_ranges_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, band_fixup_kernel));
+    return GSR_OK;
+}
 int launch_band_fixup(const int32_t *global_last_plus1, float4 *out, int32_t width, int32_t height, int32_t tiles_x, int32_t num_tiles_total,
                       int32_t band_y0, int32_t band_y1, int32_t row_mod, int32_t row_rem, cudaStream_t stream) {
     band_fixup_kernel<<<1, 256, 0, stream>>>(global_last_plus1, out, width, height, tiles_x, num_tiles_total, band_y0, band_y1, row_mod, row_rem);

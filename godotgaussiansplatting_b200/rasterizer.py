@@ -153,13 +153,18 @@ class GaussianSplattingRasterizer:
         self._bind_texture()
 
     def render_raw(self, vp32: np.ndarray, uniforms32: bytes, heatmap: float = 0.0, host_ptr: int | None = None,
-                   asynchronous: bool = True, rgb_only: bool = False) -> None:
-        """rasterize() with pre-packed push constants / uniform block (bench hot loop).  rgb_only: the host frame is
-        RGB32F (alpha is constant 1.0 and stays on the device)."""
+                   asynchronous: bool = True, rgb_only: bool = False, out_format: int | None = None) -> None:
+        """rasterize() with pre-packed push constants / uniform block (bench hot loop).  out_format: GSR_OUT_* of the host frame
+        (| GSR_OUT_SRGB_TO_LINEAR); rgb_only is shorthand for GSR_OUT_RGB32F (alpha is constant 1.0 and stays on the device)."""
         L = _lib.lib()
-        fn = (L.gsr_render_async_rgb if rgb_only else L.gsr_render_async) if asynchronous else L.gsr_render
-        _lib.check(fn(self._ctx, vp32.ctypes.data_as(C.POINTER(C.c_float)), uniforms32, float(heatmap),
-                      None if host_ptr is None else C.c_void_p(host_ptr)), "gsr_render")
+        fmt = _lib.GSR_OUT_RGB32F if (rgb_only and out_format is None) else (out_format or _lib.GSR_OUT_RGBA32F)
+        vpp = vp32.ctypes.data_as(C.POINTER(C.c_float))
+        hp = None if host_ptr is None else C.c_void_p(host_ptr)
+        if not asynchronous:
+            assert fmt == _lib.GSR_OUT_RGBA32F, "gsr_render returns the RGBA32F frame"
+            _lib.check(L.gsr_render(self._ctx, vpp, uniforms32, float(heatmap), hp), "gsr_render")
+        else:
+            _lib.check(L.gsr_render_async_fmt(self._ctx, vpp, uniforms32, float(heatmap), hp, int(fmt)), "gsr_render_async_fmt")
 
     def set_stream(self, cuda_stream: int) -> None:
         _lib.check(_lib.lib().gsr_set_stream(self._ctx, C.c_void_p(cuda_stream)), "gsr_set_stream")
@@ -212,8 +217,13 @@ class GaussianSplattingRasterizer:
     def sync(self) -> None:
         _lib.check(_lib.lib().gsr_sync(self._ctx), "gsr_sync")
 
-    def readback_async(self, host_ptr: int, rgb_only: bool = False) -> None:
-        _lib.check(_lib.lib().gsr_readback_async(self._ctx, C.c_void_p(host_ptr), int(rgb_only)), "gsr_readback_async")
+    def readback_async(self, host_ptr: int, rgb_only: bool = False, out_format: int | None = None) -> None:
+        fmt = _lib.GSR_OUT_RGB32F if (rgb_only and out_format is None) else (out_format or _lib.GSR_OUT_RGBA32F)
+        _lib.check(_lib.lib().gsr_readback_async(self._ctx, C.c_void_p(host_ptr), int(fmt)), "gsr_readback_async")
+
+    def present_device(self, device_ptr: int, out_format: int = 0) -> None:
+        """Converted copy of the last frame into caller-owned device memory (imported external image / torch tensor)."""
+        _lib.check(_lib.lib().gsr_present_device(self._ctx, C.c_void_p(device_ptr), int(out_format)), "gsr_present_device")
 
     def peer_export(self) -> bytes:
         """Presenting rank: CUDA-IPC handles (128 bytes) of its two frames."""

@@ -43,6 +43,13 @@ enum {
 #define GSR_FLAG_FAST_REJECT      0x4u /* sharded (row-interleaved) contexts: force the conservative early reject + CTA-level compaction
                                           in the projection (exact; selected automatically from 6 ranks, where it is faster) */
 
+#define GSR_FLAG_STATIC_CAPACITY  0x8u /* keep the reference's fixed duplicate capacity factor*N and truncate on overflow (rasterizer.gd:79,
+                                          main.gd:100).  Default: the capacity starts at factor*N and GROWS -- every frame's M reaches a
+                                          pinned host mirror without a host sync and the buffers are enlarged once M passes half of them;
+                                          gsr_render with a host pointer re-renders a frame that still overflowed, so it never returns a
+                                          truncated frame; an asynchronous frame that overflowed is flagged (gsr_stats.overflow /
+                                          gsr_frame_record.overflow) and the next one has room */
+
 /* ---- gsr_debug_copy selectors (parity taps; not on the frame path) ---- */
 enum {
     GSR_BUF_RECORDS = 0, /* 48 B RasterizeData per splat id (gsplat_projection.glsl:42-48), max_splats entries */
@@ -63,7 +70,7 @@ typedef struct gsr_config {
     int32_t device;               /* CUDA ordinal (RenderingServer.get_rendering_device(), rasterizer.gd:70) */
     uint32_t flags;               /* GSR_FLAG_*; 0 = GSR_FLAG_REFERENCE_QUIRKS */
     uint64_t max_splats;          /* point_cloud.size (rasterizer.gd:79,83) */
-    uint32_t dup_capacity_factor; /* sort capacity = factor * max_splats; 0 -> 10 (rasterizer.gd:79) */
+    uint32_t dup_capacity_factor; /* initial sort capacity = factor * max_splats; 0 -> 10 (rasterizer.gd:79); grows on demand */
     uint32_t reserved;
 } gsr_config;
 
@@ -165,9 +172,29 @@ GSR_API int gsr_render_async(gsr_ctx *ctx, const float view_proj[32], const void
  * constant 1.0 (gsplat_render.glsl:101), so it is packed away on the device before the PCIe transfer (-25 % bytes). */
 GSR_API int gsr_render_async_rgb(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
                                  float *pinned_host_rgb);
+/* ---- presentation hand-off (scope row f3; resources/shaders/spatial/main.gdshader:7-19, rasterizer.gd:41,48,92,101).
+ *      The reference keeps an RGBA32F image and converts sRGB -> linear in the fragment shader that samples it.  A consumer that
+ *      wants fewer bytes (PCIe read-back, the gather message) or the converted values asks for them here; the conversion is fused
+ *      into the copy-out kernel.  format = GSR_OUT_* optionally OR-ed with GSR_OUT_SRGB_TO_LINEAR (rgb channels only). ---- */
+enum {
+    GSR_OUT_RGBA32F = 0, /* 16 B/pixel: the reference's texture, bit for bit */
+    GSR_OUT_RGB32F = 1,  /* 12 B/pixel: alpha is the constant 1.0 (gsplat_render.glsl:101) */
+    GSR_OUT_RGBA16F = 2, /*  8 B/pixel: IEEE binary16, round to nearest even */
+    GSR_OUT_RGBA8 = 3    /*  4 B/pixel: UNORM8 = rint(clamp(x, 0, 1) * 255) */
+};
+#define GSR_OUT_SRGB_TO_LINEAR 0x100 /* apply main.gdshader:7-11 srgb_to_linear() to r,g,b first (pow = the library's deterministic pow) */
+GSR_API size_t gsr_output_bytes(int32_t format, int32_t width, int32_t height);
+/* gsr_render_async with a converted host frame (gsr_output_bytes(format, w, h) bytes of page-locked memory). */
+GSR_API int gsr_render_async_fmt(gsr_ctx *ctx, const float view_proj[32], const void *uniforms32, float heatmap_factor,
+                                 void *pinned_host, int32_t format);
 /* Read the most recently rendered library-owned frame back to page-locked host memory on the copy stream, ordered
- * after everything enqueued on the render stream so far (multi-GPU: after the per-frame completion sync). */
-GSR_API int gsr_readback_async(gsr_ctx *ctx, float *pinned_host, int rgb_only);
+ * after everything enqueued on the render stream so far (shard group: after every rank's rows have landed).
+ * format: GSR_OUT_* (0 = RGBA32F, 1 = RGB32F -- the former `rgb_only` argument). */
+GSR_API int gsr_readback_async(gsr_ctx *ctx, void *pinned_host, int32_t format);
+/* Converted copy of the most recent frame into caller-owned DEVICE memory, on the render stream, no host involvement: the
+ * zero-copy hand-off to an image the embedder imported from its graphics API (Vulkan VK_KHR_external_memory_fd ->
+ * cudaImportExternalMemory -> cudaExternalMemoryGetMappedBuffer). */
+GSR_API int gsr_present_device(gsr_ctx *ctx, void *dst_device, int32_t format);
 GSR_API int gsr_stream_join(gsr_ctx *ctx);
 
 /* ---- Multi-GPU shard group (no reference counterpart -- the reference is single-device).  One context per GPU,

@@ -761,6 +761,45 @@ int orc_frame(const float *splat60, int64_t n, const float *vp, const orc_unifor
 }
 
 /* exported scalar taps so the tests can pin the deterministic math against libm */
+/* ---- presentation (scope row f3): resources/shaders/spatial/main.gdshader:7-11 srgb_to_linear() and the output packings the
+ *      library offers (include/gsr.h GSR_OUT_*).  format: 0 RGBA32F, 1 RGB32F, 2 RGBA16F, 3 RGBA8; | 0x100 = sRGB -> linear on rgb. ---- */
+static inline float orc_srgb_to_linear(float x) {
+    const float higher = orc_pow((x + 0.055f) / 1.055f, 2.4f); /* pow(): the gsr deterministic pow, like every pow of the path */
+    const float lower = x / 12.92f;
+    return (x < 0.04045f) ? lower : higher;                    /* mix(higher, lower, lessThan(x, 0.04045)) */
+}
+static inline uint16_t orc_f32_to_f16(float f) { /* IEEE binary32 -> binary16, round to nearest even */
+    const uint32_t u = f2u(f), sign = (u >> 16) & 0x8000u;
+    const uint32_t a = u & 0x7FFFFFFFu;
+    if (a >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | ((a > 0x7F800000u) ? (0x0200u | ((a >> 13) & 0x3FFu)) : 0u));
+    if (a >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                /* >= 65520 rounds to inf */
+    if (a < 0x33000001u) return (uint16_t)sign;                             /* <= 2^-25 rounds to zero */
+    int e = (int)(a >> 23) - 127;
+    uint32_t m = (a & 0x7FFFFFu) | 0x800000u;
+    int shift = (e < -14) ? (13 + (-14 - e)) : 13;                          /* subnormal halves lose extra bits */
+    uint32_t half_m = m >> shift, rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (half_m & 1u))) half_m += 1u;
+    uint32_t h = (e < -14) ? half_m : (((uint32_t)(e + 15) << 10) + (half_m - 0x400u));
+    return (uint16_t)(sign | h);
+}
+static inline uint32_t orc_unorm8(float x) {
+    const float c = orc_clamp(x, 0.0f, 1.0f);
+    if (!(c == c)) return 0u;
+    return (uint32_t)nearbyintf(c * 255.0f);
+}
+void orc_present(const float *rgba, int64_t pixels, int format, void *out) {
+    const int lin = (format & 0x100) != 0, fmt = format & 0xFF;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < pixels; ++i) {
+        float v[4] = {rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], rgba[4 * i + 3]};
+        if (lin) for (int k = 0; k < 3; ++k) v[k] = orc_srgb_to_linear(v[k]);
+        if (fmt == 0) memcpy((float *)out + 4 * i, v, 16);
+        else if (fmt == 1) memcpy((float *)out + 3 * i, v, 12);
+        else if (fmt == 2) for (int k = 0; k < 4; ++k) ((uint16_t *)out)[4 * i + k] = orc_f32_to_f16(v[k]);
+        else ((uint32_t *)out)[i] = orc_unorm8(v[0]) | (orc_unorm8(v[1]) << 8) | (orc_unorm8(v[2]) << 16) | (orc_unorm8(v[3]) << 24);
+    }
+}
+
 float orc_test_exp(float x) { return orc_exp(x); }
 float orc_test_pow(float x, float y) { return orc_pow(x, y); }
 float orc_test_log2(float x) { return orc_log2(x); }

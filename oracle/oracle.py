@@ -67,6 +67,7 @@ def lib():
             getattr(L, n).argtypes = [C.c_float]
         L.orc_test_pow.restype = C.c_float
         L.orc_test_pow.argtypes = [C.c_float, C.c_float]
+        L.orc_present.argtypes = [fp, i64, C.c_int, C.c_void_p]
         L.orc_set_blend_contraction.argtypes = [C.c_int]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
@@ -246,6 +247,16 @@ def frame(splat60, vp32, uniforms: _Uniforms, heatmap=0.0, quirks=True, band=Non
     return Frame(out, recs, keys[:m].copy(), vals[:m].copy(), bounds, int(st.visible), int(st.duplicates), int(st.staged),
                  int(st.last_tile), rc != 0,
                  {"Projection": st.ms_projection, "Sort": st.ms_sort, "Boundaries": st.ms_boundaries, "Render": st.ms_render})
+
+
+def present(rgba: np.ndarray, fmt: int) -> np.ndarray:
+    """include/gsr.h GSR_OUT_* applied to an RGBA32F frame (main.gdshader:7-11 when fmt has 0x100): the expected bytes."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    px = rgba.size // 4
+    shape = {0: ((px, 4), np.float32), 1: ((px, 3), np.float32), 2: ((px, 4), np.uint16), 3: ((px,), np.uint32)}[fmt & 0xFF]
+    out = np.zeros(shape[0], dtype=shape[1])
+    lib().orc_present(_f(rgba), px, int(fmt), out.ctypes.data)
+    return out
 
 
 def det_exp(x):

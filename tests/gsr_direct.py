@@ -90,8 +90,13 @@ class Ctx:
         _lib.check(self.L.gsr_render_async(self.h, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms, float(heatmap),
                                            None if host_ptr is None else C.c_void_p(host_ptr)), "gsr_render_async")
 
-    def readback_async(self, host_ptr, rgb_only=False):
-        _lib.check(self.L.gsr_readback_async(self.h, C.c_void_p(host_ptr), int(rgb_only)), "gsr_readback_async")
+    def readback_async(self, host_ptr, fmt=0):
+        _lib.check(self.L.gsr_readback_async(self.h, C.c_void_p(host_ptr), int(fmt)), "gsr_readback_async")
+
+    def render_async_fmt(self, vp, uniforms, host_ptr, fmt, heatmap=0.0):
+        vp = np.ascontiguousarray(vp, dtype=np.float32)
+        _lib.check(self.L.gsr_render_async_fmt(self.h, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms, float(heatmap), C.c_void_p(host_ptr), int(fmt)),
+                   "gsr_render_async_fmt")
 
     def sync(self):
         _lib.check(self.L.gsr_sync(self.h), "gsr_sync")

@@ -71,6 +71,7 @@ inline int __reduce_max_sync(unsigned, int v) {
     for (int i = 0; i < 32; ++i) if (c->sg_part & (1u << i)) { const int x = (int)c->sg_vals[i]; m = x > m ? x : m; }
     return m;
 }
+inline unsigned __float2uint_rn(float x) { return x != x ? 0u : (x <= 0.0f ? 0u : (x >= 4294967296.0f ? 0xFFFFFFFFu : (unsigned)nearbyintf(x))); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __threadfence() {}

@@ -12,6 +12,7 @@ namespace gsr { void set_last_error(const char *, ...) {} }
 #include "../../godotgaussiansplatting_b200/csrc/radix_sort.cu"
 #include "../../godotgaussiansplatting_b200/csrc/projection.cu"
 #include "../../godotgaussiansplatting_b200/csrc/ingest.cu"
+#include "../../godotgaussiansplatting_b200/csrc/present.cu"
 
 namespace {
 struct Launch { const gsr::CompositeArgs *args; int variant; };
@@ -239,7 +240,18 @@ void aos_body(void *p) { const AosLaunch *l = static_cast<const AosLaunch *>(p);
 struct PlyLaunch { const float *ply; uint32_t nprops; uint64_t count; float creation; float4 *soa; uint64_t stride, first; };
 void ply_body(void *p) { const PlyLaunch *l = static_cast<const PlyLaunch *>(p); gsr::ply_to_soa_kernel(l->ply, l->nprops, l->count, l->creation, l->soa, l->stride, l->first); }
 struct PackLaunch { const float4 *rgba; float4 *rgb; uint64_t quads, pixels; };
-void pack_body(void *p) { const PackLaunch *l = static_cast<const PackLaunch *>(p); gsr::pack_rgb_kernel(l->rgba, l->rgb, l->quads, l->pixels); }
+void pack_body(void *p) { const PackLaunch *l = static_cast<const PackLaunch *>(p); gsr::present_kernel<GSR_OUT_RGB32F, false>(l->rgba, l->rgb, l->pixels); }
+struct PresentLaunch { const float4 *rgba; void *out; uint64_t pixels; int format; };
+void present_body(void *p) {
+    const PresentLaunch *l = static_cast<const PresentLaunch *>(p);
+    const bool lin = (l->format & GSR_OUT_SRGB_TO_LINEAR) != 0;
+    switch (l->format & 0xFF) {
+        case GSR_OUT_RGBA32F: lin ? gsr::present_kernel<GSR_OUT_RGBA32F, true>(l->rgba, l->out, l->pixels) : gsr::present_kernel<GSR_OUT_RGBA32F, false>(l->rgba, l->out, l->pixels); break;
+        case GSR_OUT_RGB32F: lin ? gsr::present_kernel<GSR_OUT_RGB32F, true>(l->rgba, l->out, l->pixels) : gsr::present_kernel<GSR_OUT_RGB32F, false>(l->rgba, l->out, l->pixels); break;
+        case GSR_OUT_RGBA16F: lin ? gsr::present_kernel<GSR_OUT_RGBA16F, true>(l->rgba, l->out, l->pixels) : gsr::present_kernel<GSR_OUT_RGBA16F, false>(l->rgba, l->out, l->pixels); break;
+        default: lin ? gsr::present_kernel<GSR_OUT_RGBA8, true>(l->rgba, l->out, l->pixels) : gsr::present_kernel<GSR_OUT_RGBA8, false>(l->rgba, l->out, l->pixels); break;
+    }
+}
 void run_blocks(unsigned blocks, unsigned threads, void (*body)(void *), void *arg) {
     cuda_emu::g_block_dim = cuda_emu::dim{threads, 1, 1};
     cuda_emu::g_grid_dim = cuda_emu::dim{blocks, 1, 1};
@@ -259,6 +271,12 @@ extern "C" int emu_ply_to_soa(const float *ply, unsigned nprops, unsigned long l
     if (nprops > 256) return 1;
     PlyLaunch l{ply, nprops, count, creation_time, static_cast<float4 *>(soa), plane_stride, first};
     run_blocks((unsigned)((count + gsr::INGEST_SPLATS - 1) / gsr::INGEST_SPLATS), (unsigned)gsr::INGEST_SPLATS, &ply_body, &l);
+    return 0;
+}
+extern "C" int emu_present(const void *rgba, void *out, unsigned long long pixels, int format) {
+    PresentLaunch l{static_cast<const float4 *>(rgba), out, pixels, format};
+    const unsigned long long items = (format & 0xFF) == GSR_OUT_RGB32F ? (pixels + 3) / 4 : pixels;
+    run_blocks((unsigned)((items + 255) / 256), 256, &present_body, &l);
     return 0;
 }
 extern "C" int emu_pack_rgb(const void *rgba, void *rgb, unsigned long long pixels) {

@@ -126,9 +126,60 @@ def test_big_splats_many_tiles_per_splat():
 
 
 def test_overflow_is_reported():
-    ref, t = run_both(3000, 9, 640, 480, scale_boost=2.5, factor=2)
+    """GSR_FLAG_STATIC_CAPACITY = the reference's fixed factor*N capacity (rasterizer.gd:79): overflow is reported, not repaired."""
+    ref, t = run_both(3000, 9, 640, 480, scale_boost=2.5, factor=2, flags=_lib.GSR_FLAG_STATIC_CAPACITY)
     assert ref.overflow
     assert_frame_equal(ref, t)
+
+
+def test_capacity_grows_instead_of_truncating():
+    """Scope row f4 (rasterizer.gd:79 'FIXME: This should not be a static value!'): by default the duplicate capacity grows.  The
+    scene that overflows a 2 x N capacity must come out exactly like the oracle run with room for every instance -- through the
+    synchronous call at once, through the asynchronous one from the frame after the (flagged) overflow."""
+    n, w, h = 3000, 640, 480
+    splat60, vp, ub = make_scene(n, 9, w, h, scale_boost=2.5)
+    ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=400 * n)
+    assert not ref.overflow and ref.duplicates > 2 * n
+    with Ctx(n, w, h, factor=2) as c:          # synchronous: never a truncated frame
+        c.upload(splat60)
+        img = c.render(vp, ub)
+        t = c.taps()
+        assert not t["stats"].overflow and t["stats"].capacity >= ref.duplicates > 2 * n
+        np.testing.assert_array_equal(t["keys"], ref.keys)
+        np.testing.assert_array_equal(t["values"], ref.values)
+        np.testing.assert_array_equal(t["bounds"], ref.bounds)
+        np.testing.assert_array_equal(bits(img), bits(ref.rgba))
+    with Ctx(n, w, h, factor=2) as c:          # asynchronous: the overflowing frame is flagged, the next one has room
+        c.upload(splat60)
+        c.render_async(vp, ub)
+        c.sync()
+        assert c.stats().overflow == 1 and c.stats().duplicates == ref.duplicates
+        c.render_async(vp, ub)
+        c.sync()
+        t = c.taps()
+        assert not t["stats"].overflow
+        np.testing.assert_array_equal(t["keys"], ref.keys)
+        img = c.copy(_lib.GSR_BUF_FRAMEBUFFER, w * h * 4, np.float32).reshape(h, w, 4)
+        np.testing.assert_array_equal(bits(img), bits(ref.rgba))
+
+
+def test_not_yet_loaded_splats_are_dispatched_like_the_reference():
+    """The reference dispatches the projection over point_cloud.size every frame (rasterizer.gd:83,134), i.e. also over the
+    zero-initialised structs of splats the loader thread has not delivered yet; libgsr does the same (max_splats, zeroed SoA)."""
+    n, loaded, w, h = 20000, 12345, 640, 480
+    splat60, vp, ub = make_scene(n, 12, w, h)
+    partial = splat60.copy()
+    partial[loaded:] = 0.0
+    ref = orc.frame(partial, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)))
+    with Ctx(n, w, h) as c:
+        c.upload(splat60[:loaded])
+        img = c.render(vp, ub)
+        t = c.taps()
+    assert t["stats"].duplicates == ref.duplicates
+    np.testing.assert_array_equal(t["keys"], ref.keys)
+    np.testing.assert_array_equal(t["values"], ref.values)
+    np.testing.assert_array_equal(t["bounds"], ref.bounds)
+    np.testing.assert_array_equal(bits(img), bits(ref.rgba))
 
 
 @pytest.mark.parametrize("band", [(0, 7), (7, 20), (20, 30), (29, 30), (12, 12)])
@@ -371,3 +422,31 @@ def test_device_ply_ingest_matches_host_ingest():
     np.testing.assert_array_equal(ta["values"], tb["values"])
     np.testing.assert_array_equal(ta["bounds"], tb["bounds"])
     np.testing.assert_array_equal(bits(a), bits(b))
+
+
+@pytest.mark.parametrize("fmt", [_lib.GSR_OUT_RGBA32F, _lib.GSR_OUT_RGB32F, _lib.GSR_OUT_RGBA16F, _lib.GSR_OUT_RGBA8,
+                                 _lib.GSR_OUT_RGBA32F | _lib.GSR_OUT_SRGB_TO_LINEAR, _lib.GSR_OUT_RGBA16F | _lib.GSR_OUT_SRGB_TO_LINEAR,
+                                 _lib.GSR_OUT_RGBA8 | _lib.GSR_OUT_SRGB_TO_LINEAR])
+def test_presentation_formats_match_the_oracle_frame_through_the_same_conversion(fmt):
+    """Scope row f3: the fused copy-out conversions (csrc/present.cu; main.gdshader:7-11 for the sRGB -> linear variants) applied to
+    the frame equal oracle.present() of the oracle's frame byte for byte -- through the pipelined host read-back and through the
+    device-to-device hand-off (gsr_present_device, the path an imported Vulkan image takes)."""
+    import ctypes as C
+    import torch
+    n, w, h = 40000, 645, 363     # ragged: neither a tile multiple nor a multiple of 4 pixels
+    splat60, vp, ub = make_scene(n, 21, w, h, scale_boost=0.7)
+    ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), heatmap=1.0)
+    want = orc.present(ref.rgba, fmt)
+    nbytes = _lib.lib().gsr_output_bytes(fmt, w, h)
+    assert nbytes == want.nbytes
+    with Ctx(n, w, h) as c:
+        c.upload(splat60)
+        host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        c.render_async_fmt(vp, ub, host.data_ptr(), fmt, heatmap=1.0)
+        c.sync()
+        np.testing.assert_array_equal(host.numpy(), want.view(np.uint8).reshape(-1))
+        dev = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.lib().gsr_present_device(c.h, C.c_void_p(dev.data_ptr()), fmt), "gsr_present_device")
+        c.sync()
+        np.testing.assert_array_equal(dev[:nbytes].cpu().numpy(), want.view(np.uint8).reshape(-1))
+        assert not dev[nbytes:].any()

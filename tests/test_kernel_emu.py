@@ -403,3 +403,21 @@ def test_extent_table_mode_splits_the_cull_across_ranks(G):
             np.testing.assert_array_equal(bits(got["records"][f][ids]), bits(full.records[f][ids]), err_msg=f"record field {f}")
         seen += got["m"]
     assert seen == full.duplicates
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3, 0x100, 0x101, 0x102, 0x103])
+def test_present_kernel_matches_the_oracle_conversion(fmt):
+    """Scope row f3 (csrc/present.cu): RGBA32F -> GSR_OUT_* with the optional sRGB -> linear of main.gdshader:7-11, bit for bit
+    against oracle.present -- incl. values above 1, exact 0 / 1 / 0.04045, a ragged pixel count, inf and negative inputs."""
+    L = lib()
+    L.emu_present.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_int]
+    rng = np.random.default_rng(fmt)
+    px = 1003
+    rgba = (rng.random((px, 4)).astype(np.float32) ** 3) * 1.7
+    rgba[:8, :3] = np.array([[0.0, 1.0, 0.04045], [0.040449999, 0.5, 2.5], [np.inf, -0.25, 1e-30], [65519.0, 65520.0, 6e-8],
+                             [0.9999999, 0.0031308, 1e-5], [3e-5, 0.00196, 0.99803925], [0.5019608, 0.49803922, 0.2], [1e-40, 3.0, 0.7]], dtype=np.float32)
+    rgba[:, 3] = 1.0
+    want = orc.present(rgba, fmt)
+    got = np.zeros_like(want)
+    assert L.emu_present(rgba.ctypes.data, got.ctypes.data, px, fmt) == 0
+    np.testing.assert_array_equal(got.view(np.uint8), want.view(np.uint8))
