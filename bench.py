@@ -389,7 +389,7 @@ def main():
     rast = GaussianSplattingRasterizer(stub, (W, H), RenderTexture(), default_camera(aspect=W / H), device=local_rank)
     rast.init_gpu(load=False)
     rast.set_stream(stream.cuda_stream)
-    keep_host = rank == 0 and world == 1 and not args.no_cpu_baseline
+    keep_host = rank == 0 and not args.no_cpu_baseline   # N > 1: rank 0 keeps the scene for the one-frame parity check of the assembled frame
     host_chunks = []
     t_gen = time.perf_counter()
     for lo, blk in raw_chunks(wl):
@@ -540,8 +540,36 @@ def main():
             radix = {"error": str(e)}
 
     cpu_baseline = None
-    parity = {"checked": False, "why": "no oracle leg on this run (multi-GPU rank layout or --no-cpu-baseline)"}
-    if keep_host:
+    parity = {"checked": False, "why": "no oracle leg on this run (NCCL-gather mode or --no-cpu-baseline)"}
+    if world > 1 and (group or peer):
+        # ---- multi-GPU self-check: one more frame through the same path, assembled on rank 0, against the oracle ----
+        vp_c, ub_c = frames[args.warmup]
+        got_t = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+        torch.cuda.synchronize(); dist.barrier()
+        rast.render_raw(vp_c, ub_c, 0.0, None, asynchronous=True)
+        if peer:
+            if rank == 0:
+                rast.stream_join()
+            dist.all_reduce(sync_flag, op=dist.ReduceOp.MAX)
+            rast.band_fixup()
+        if rank == 0:
+            rast.readback_async(got_t.data_ptr())
+        rast.sync(); torch.cuda.synchronize(); dist.barrier()
+        if keep_host:
+            from oracle import oracle as orc
+            splat60 = np.concatenate([orc.preprocess_ply(blk, 0.0) for blk in host_chunks])
+            del host_chunks
+            ref = orc.frame(splat60, vp_c, orc.uniforms_from_bytes(np.frombuffer(ub_c, dtype=np.uint8)))
+            got = got_t.numpy()
+            parity = {"checked": True, "against": "oracle, same camera, full workload; frame assembled on rank 0 from all ranks' rows",
+                      "rgba_max_abs_err": float(np.abs(got - ref.rgba).max()),
+                      "rgba_bit_identical": bool(np.array_equal(got.view(np.uint32), ref.rgba.view(np.uint32))),
+                      "duplicates_M_oracle": int(ref.duplicates), "keys_equal": None, "ranges_equal": None,
+                      "note": "per-rank sorted pairs vs the oracle's owned rows are checked by tests/test_gpu_multi.py and tests/test_gpu_group.py"}
+            del splat60, ref
+            if not parity["rgba_max_abs_err"] <= 1e-4:
+                raise SystemExit(f"bench.py: PARITY FAILURE of the assembled multi-GPU frame against the oracle: {parity}")
+    elif keep_host and world == 1:
         from oracle import oracle as orc
         splat60 = np.concatenate([orc.preprocess_ply(blk, 0.0) for blk in host_chunks])
         del host_chunks

@@ -1,0 +1,17 @@
+# usage: bash scripts/gpu_r2c_mgpu.sh <N>   (run under gpurun --gpus N)
+N=${1:-2}
+out=gpurun_out/r2c_${N}gpu; mkdir -p $out
+nvidia-smi -L > $out/gpus.txt 2>&1
+nvidia-smi topo -m > $out/topo.txt 2>&1
+( time timeout 900 python -m pytest tests/test_gpu_multi.py -q -x ) > $out/pytest_multi.log 2>&1
+run() { # name, args...
+  name=$1; shift
+  NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N "$@" > $out/bench_$name.json 2> $out/bench_$name.err
+  echo "$name rc=$? $(python -c "import json,sys; d=json.load(open('$out/bench_$name.json')); print('fps',round(d['fps'],1),'e2e_fps',round(d['e2e']['fps'],1),'stages',{k:round(v,3) for k,v in d['stage_ms'].items()},'parity',d['parity'].get('rgba_bit_identical'))" 2>&1 | tail -1)"
+}
+run c3_group --steps 60 --warmup 10 --mgpu group --no-radix
+run c3_peer --steps 60 --warmup 10 --mgpu peer --no-radix
+run c4_group --steps 40 --warmup 10 --mgpu group --workload c4 --no-radix
+run c4_peer --steps 40 --warmup 10 --mgpu peer --workload c4 --no-radix
+run c3_default --steps 20 --warmup 5
+tail -5 $out/pytest_multi.log

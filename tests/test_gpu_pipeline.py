@@ -24,8 +24,11 @@ def bits(a):
 def run_both(n, seed, w, h, frame=None, flags=0, heatmap=0.0, band=None, time=10.0, model_scale=1.0, scale_boost=0.0, factor=10):
     splat60, vp, ub = make_scene(n, seed, w, h, frame=frame, time=time, model_scale=model_scale, scale_boost=scale_boost)
     quirks = not (flags & _lib.GSR_FLAG_FIXED_RANGES)
+    # default contexts grow their duplicate capacity (the synchronous render never returns a truncated frame): the oracle gets room
+    # for every instance; GSR_FLAG_STATIC_CAPACITY keeps the reference's fixed factor * N and its truncation
+    cap = factor * n if (flags & _lib.GSR_FLAG_STATIC_CAPACITY) else max(factor, 1000) * n
     ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), heatmap=heatmap, quirks=quirks,
-                    band=band, cap=factor * n)
+                    band=band, cap=cap)
     with Ctx(n, w, h, flags=flags, factor=factor) as c:
         c.upload(splat60)
         if band is not None:
