@@ -187,6 +187,8 @@ struct GroupPeers {                                             // the same poin
 // extents of splats [first, first+count) of the frame described by `a` (band / row ownership of `a` are ignored), stored into
 // EVERY rank's table (peer stores); the last CTA then publishes seq | last tile to every rank's meta[parity][rank].
 int launch_extents(const ProjectionArgs &a, uint32_t first, uint32_t count, const GroupPeers &peers, int parity, uint32_t seq, cudaStream_t stream);
+// 64-byte FrameState -> mapped pinned host memory with system-scope stores (no copy engine involved)
+int launch_publish_frame_state(const FrameState *frame, FrameState *host_mapped, cudaStream_t stream);
 int launch_group_wait_extents(GroupFlags *flags, int parity, int world, uint32_t seq, FrameState *frame, cudaStream_t stream);
 int launch_group_wait_released(GroupFlags *flags, uint32_t need, cudaStream_t stream);
 int launch_group_wait_done(GroupFlags *flags, int world, uint32_t seq, cudaStream_t stream);
@@ -218,11 +220,17 @@ struct CompositeArgs {
     uint32_t *queue;         // [GSR_COMP_MAX_PUSHES * num_tiles] zero-initialised: re-queued tiles (tile id + 1)
     float4 *state;           // [num_tiles][2][128] spilled per-pixel state of re-queued tiles
     uint32_t *state_chunk;   // [num_tiles] first chunk still to blend
+    const uint32_t *order;   // optional: ticket k renders owned tile order[k] (longest lists first, launch_tile_order); nullptr = natural order
+    int32_t quantum;         // chunks blended before an unfinished tile is handed back to the queue (>= 1; large = never)
+    int32_t requeue_only_if_fresh;  // hand a tile back only while fresh tiles are still waiting for a CTA
+    int32_t ctas_per_sm;     // resident CTAs per SM of the persistent grid (0 = as many as fit)
     ulonglong4 *trace;       // optional schedule trace (debug): {tile<<32|smid, t0_ns, t1_ns, first_chunk<<32|iters<<1|finished}
     uint32_t *trace_count;
     uint32_t trace_cap;
 };
 int launch_composite(const CompositeArgs &a, cudaStream_t stream);
+// order[0 .. num_tiles) = owned-tile indices sorted by descending list length (counting sort by 256-splat chunks, one CTA)
+int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *order, cudaStream_t stream);
 
 int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
                       cudaStream_t stream);

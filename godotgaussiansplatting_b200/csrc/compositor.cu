@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
             const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
             if (ticket < (uint32_t)p.num_tiles) {
                 // owned tiles: rows tile_begin/tiles_x + k*row_step, all columns (row_step == 1: one contiguous band)
-                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                const uint32_t k = p.order ? p.order[ticket] : ticket;   // owned-tile index: longest lists first when an order is given
+                s_tile = (uint32_t)p.tile_begin + (k / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + k % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
                 // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
@@ -299,8 +300,11 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
         }
 
         // at most COMP_MAX_PUSHES hand-backs per tile bound the queue: long lists get a proportionally longer quantum
-        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
-                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        // a resumed item means every fresh tile has been handed out (tickets are monotonic): yielding again would only cost a
+        // spill + restore, so (requeue_only_if_fresh) it runs to completion; a fresh tile yields after `quantum` chunks
+        const int q_min = p.quantum > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                              ? p.quantum : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int quantum = (p.requeue_only_if_fresh && resume) ? 0x3fffffff : q_min;
         const int i_begin = i0;
         bool finished = true;
         for (int i = i_begin; i < num_iterations; ++i) {
@@ -506,7 +510,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v2_kernel(const
         if (tid == 0) {
             const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
             if (ticket < (uint32_t)p.num_tiles) {
-                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                const uint32_t k = p.order ? p.order[ticket] : ticket;   // owned-tile index: longest lists first when an order is given
+                s_tile = (uint32_t)p.tile_begin + (k / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + k % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
                 // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
@@ -585,8 +590,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v2_kernel(const
             }
         };
 
-        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
-                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        // a resumed item means every fresh tile has been handed out (tickets are monotonic): yielding again would only cost a
+        // spill + restore, so (requeue_only_if_fresh) it runs to completion; a fresh tile yields after `quantum` chunks
+        const int q_min = p.quantum > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                              ? p.quantum : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int quantum = (p.requeue_only_if_fresh && resume) ? 0x3fffffff : q_min;
         const int i_begin = i0;
         bool finished = true;
         int b = 0;
@@ -709,12 +717,11 @@ inline void comp_mbar_wait(uint64_t *, uint32_t) {}
 
 // phase A over the one-array staging layout; also returns om2 = 1 - alpha (off the transmittance chain)
 template <bool CVT>
-__device__ __forceinline__ void phase_a_v3(const float4 *s, int j, u64 npx2, float fpy, const BlendK &K, u64 al2[GU], u64 om2[GU]) {
-    float4 A[GU];
+__device__ __forceinline__ void phase_a_v3(const float4 A[GU], const float4 B[GU], u64 npx2, float fpy, const BlendK &K, u64 al2[GU], u64 om2[GU]) {
     float bx[GU], by[GU], oy[GU];
     u64 ox2[GU], pw2[GU], tm2[GU], e2[GU];
 #pragma unroll
-    for (int u = 0; u < GU; ++u) { A[u] = s[3 * (j + u)]; const float4 b = s[3 * (j + u) + 1]; bx[u] = b.x; by[u] = b.y; }
+    for (int u = 0; u < GU; ++u) { bx[u] = B[u].x; by[u] = B[u].y; }
 #pragma unroll
     for (int u = 0; u < GU; ++u) { ox2[u] = add2(bc(A[u].x), npx2); oy[u] = A[u].y - fpy; }
 #pragma unroll
@@ -789,11 +796,13 @@ __device__ __forceinline__ void phase_a_v3(const float4 *s, int j, u64 npx2, flo
 }
 
 // phase B with the short transmittance chain: per splat FMUL2 (t * (1 - alpha)) and one select per pixel
-__device__ __forceinline__ void phase_b_v3(const float4 *s, int j, const u64 al2[GU], const u64 om2[GU], u64 &cr2, u64 &cg2, u64 &cb2, float &t0, float &t1) {
+__device__ __forceinline__ void phase_b_v3(const float4 *s, int j, const float4 B[GU], const u64 al2[GU], const u64 om2[GU], u64 &cr2, u64 &cg2, u64 &cb2,
+                                           float &t0, float &t1, bool &alive_mid) {
 #pragma unroll
     for (int u = 0; u < GU; ++u) {
-        const float4 b = s[3 * (j + u) + 1];
+        const float4 b = B[u];
         const float cbl = s[3 * (j + u) + 2].x;
+        if (u == GU / 2) alive_mid = (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA);   // liveness half a group early: the vote leaves the critical path
         const bool a0 = t0 > MIN_ALPHA, a1 = t1 > MIN_ALPHA;   // gsplat_render.glsl:79: a dead pixel has left the loop
         float al, ah, pl, ph;
         upk(al2[u], al, ah);
@@ -808,7 +817,7 @@ __device__ __forceinline__ void phase_b_v3(const float4 *s, int j, const u64 al2
     }
 }
 
-template <int MIN_BLOCKS, bool CVT>
+template <int MIN_BLOCKS, bool CVT, bool PIPE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v3_kernel(const __grid_constant__ CompositeArgs p) {
     __shared__ __align__(128) float4 s_st[2][CHUNK * 3];   // two staging halves; slot k = float4[3k..3k+2]: the raw 48-byte record lands
                                                            // there (TMA) and is pre-scaled in place by the thread that fetched it
@@ -828,7 +837,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v3_kernel(const
         if (tid == 0) {
             const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
             if (ticket < (uint32_t)p.num_tiles) {
-                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                const uint32_t k = p.order ? p.order[ticket] : ticket;   // owned-tile index: longest lists first when an order is given
+                s_tile = (uint32_t)p.tile_begin + (k / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + k % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
                 // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
@@ -903,8 +913,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v3_kernel(const
             }
         };
 
-        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
-                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        // a resumed item means every fresh tile has been handed out (tickets are monotonic): yielding again would only cost a
+        // spill + restore, so (requeue_only_if_fresh) it runs to completion; a fresh tile yields after `quantum` chunks
+        const int q_min = p.quantum > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                              ? p.quantum : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int quantum = (p.requeue_only_if_fresh && resume) ? 0x3fffffff : q_min;
         const int i_begin = i0;
         bool finished = true;
         int b = 0;
@@ -928,11 +941,38 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) composite_v3_kernel(const
             }
 
             const int chunk4 = (chunk + GU - 1) & ~(GU - 1);
-            for (int j = 0; j < chunk4; j += GU) {
-                if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
-                u64 al2[GU], om2[GU];
-                phase_a_v3<CVT>(s_st[b], j, npx2, fpy, K, al2, om2);
-                phase_b_v3(s_st[b], j, al2, om2, cr2, cg2, cb2, t0, t1);
+            if (PIPE) {
+                // software-pipelined: the (a, b) words of group g+1 are loaded while group g is blended, and the warp's "anybody alive?"
+                // test uses the transmittance after the first half of the group -- a dead warp may blend one more (fully masked,
+                // exact no-op) group before it leaves, in exchange the vote and the shared-memory latency leave the loop-carried path
+                float4 A[GU], B[GU];
+#pragma unroll
+                for (int u = 0; u < GU; ++u) { A[u] = s_st[b][3 * u]; B[u] = s_st[b][3 * u + 1]; }
+                bool go = __any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA));
+                for (int j = 0; j < chunk4 && go; j += GU) {
+                    u64 al2[GU], om2[GU];
+                    phase_a_v3<CVT>(A, B, npx2, fpy, K, al2, om2);
+                    float4 Bc[GU];
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) Bc[u] = B[u];
+                    const int jn = (j + GU < CHUNK) ? j + GU : j;   // the last group re-reads itself instead of running off the half
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) { A[u] = s_st[b][3 * (jn + u)]; B[u] = s_st[b][3 * (jn + u) + 1]; }
+                    bool alive_mid = true;
+                    phase_b_v3(s_st[b], j, Bc, al2, om2, cr2, cg2, cb2, t0, t1, alive_mid);
+                    go = __any_sync(0xffffffffu, alive_mid);
+                }
+            } else {
+                for (int j = 0; j < chunk4; j += GU) {
+                    if (!__any_sync(0xffffffffu, (t0 > MIN_ALPHA) || (t1 > MIN_ALPHA))) break;
+                    float4 A[GU], B[GU];
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) { A[u] = s_st[b][3 * (j + u)]; B[u] = s_st[b][3 * (j + u) + 1]; }
+                    u64 al2[GU], om2[GU];
+                    bool alive_mid;
+                    phase_a_v3<CVT>(A, B, npx2, fpy, K, al2, om2);
+                    phase_b_v3(s_st[b], j, B, al2, om2, cr2, cg2, cb2, t0, t1, alive_mid);
+                }
             }
             if (fetch_next) finalize(va0, va1, b ^ 1);   // nobody reads half b^1 before the barrier below
 
@@ -1106,7 +1146,8 @@ __global__ void __launch_bounds__(P4_THREADS, GSR_COMP_P4_MIN_BLOCKS) composite_
         if (tid == 0) {
             const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
             if (ticket < (uint32_t)p.num_tiles) {
-                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                const uint32_t k = p.order ? p.order[ticket] : ticket;   // owned-tile index: longest lists first when an order is given
+                s_tile = (uint32_t)p.tile_begin + (k / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + k % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
                 // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
@@ -1185,8 +1226,11 @@ __global__ void __launch_bounds__(P4_THREADS, GSR_COMP_P4_MIN_BLOCKS) composite_
             }
         };
 
-        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
-                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        // a resumed item means every fresh tile has been handed out (tickets are monotonic): yielding again would only cost a
+        // spill + restore, so (requeue_only_if_fresh) it runs to completion; a fresh tile yields after `quantum` chunks
+        const int q_min = p.quantum > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                              ? p.quantum : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int quantum = (p.requeue_only_if_fresh && resume) ? 0x3fffffff : q_min;
         const int i_begin = i0;
         bool finished = true;
         int b = 0;
@@ -1318,7 +1362,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
         if (tid == 0) {
             const uint32_t ticket = atomicAdd(&p.frame->comp_head, 1u);
             if (ticket < (uint32_t)p.num_tiles) {
-                s_tile = (uint32_t)p.tile_begin + (ticket / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + ticket % (uint32_t)p.tiles_x;
+                const uint32_t k = p.order ? p.order[ticket] : ticket;   // owned-tile index: longest lists first when an order is given
+                s_tile = (uint32_t)p.tile_begin + (k / (uint32_t)p.tiles_x) * (uint32_t)(p.row_step * p.tiles_x) + k % (uint32_t)p.tiles_x;
                 s_resume = 0u;
             } else {
                 // a tile is pushed at most COMP_MAX_PUSHES times: later tickets can never be served and must not touch the queue
@@ -1368,8 +1413,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
         Staged n0 = null_splat();  // 256 threads stage one record each
         if (i0 < num_iterations && CHUNK * i0 + (int)tid < num_splats) n0 = gather(p.records, p.values, bounds.x + (uint32_t)(CHUNK * i0) + tid);
 
-        const int quantum = GSR_COMP_QUANTUM > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
-                                ? GSR_COMP_QUANTUM : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        // a resumed item means every fresh tile has been handed out (tickets are monotonic): yielding again would only cost a
+        // spill + restore, so (requeue_only_if_fresh) it runs to completion; a fresh tile yields after `quantum` chunks
+        const int q_min = p.quantum > (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1)
+                              ? p.quantum : (num_iterations + COMP_MAX_PUSHES) / (COMP_MAX_PUSHES + 1);
+        const int quantum = (p.requeue_only_if_fresh && resume) ? 0x3fffffff : q_min;
         const int i_begin = i0;
         bool finished = true;
         for (int i = i_begin; i < num_iterations; ++i) {
@@ -1494,12 +1542,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) composite_ws_kernel(const __gri
 int preload_composite_kernels() {
     cudaFuncAttributes fa;
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, composite_kernel<false>));
-    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, composite_v3_kernel<6, false>));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, composite_v3_kernel<6, false, false>));
     return GSR_OK;
 }
 int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     if (a.num_tiles <= 0) return GSR_OK;
-    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, use_p4 = 0, use_v3 = 0, use_cvt = 0, cfg_dev = -1;
+    static int ctas_per_sm = 0, sms = 0, use_ws = GSR_COMP_WS_DEFAULT, use_hwexp = 0, use_v2 = 0, use_p4 = 0, use_v3 = 0, use_cvt = 0, use_pipe = 0, cfg_dev = -1;
     int dev = 0;
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     if (cfg_dev != dev) {
@@ -1519,10 +1567,14 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         const char *cvte = getenv("GSR_COMP_CVT");
         use_cvt = (cvte && atoi(cvte) != 0) ? 1 : 0;
         if (use_v3) use_v2 = 0;
-        if (use_v3 >= 8 && use_cvt) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<8, true>, THREADS, 0));
-        else if (use_v3 >= 8) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<8, false>, THREADS, 0));
-        else if (use_v3 && use_cvt) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<6, true>, THREADS, 0));
-        else if (use_v3) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<6, false>, THREADS, 0));
+        const char *pipee = getenv("GSR_COMP_PIPE");
+        use_pipe = (pipee && atoi(pipee) != 0) ? 1 : 0;
+        if (use_v3 == 4 && use_pipe) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<4, false, true>, THREADS, 0));
+        else if (use_v3 == 4) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<4, false, false>, THREADS, 0));
+        else if (use_v3 >= 8 && use_cvt) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<8, true, false>, THREADS, 0));
+        else if (use_v3 >= 8) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<8, false, false>, THREADS, 0));
+        else if (use_v3 && use_cvt) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<6, true, false>, THREADS, 0));
+        else if (use_v3) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v3_kernel<6, false, false>, THREADS, 0));
         else if (use_p4) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_p4_kernel, P4_THREADS, 0));
         else if (use_v2 >= 8) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<8>, THREADS, 0));
         else if (use_v2 >= 6) GSR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, composite_v2_kernel<6>, THREADS, 0));
@@ -1534,11 +1586,14 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         const char *e = getenv("GSR_COMP_CTAS_PER_SM");  // experiment knob
         if (e && atoi(e) > 0 && atoi(e) < ctas_per_sm) ctas_per_sm = atoi(e);
     }
-    const int grid = a.num_tiles < sms * ctas_per_sm ? a.num_tiles : sms * ctas_per_sm;
-    if (use_v3 >= 8 && use_cvt) composite_v3_kernel<8, true><<<grid, THREADS, 0, stream>>>(a);
-    else if (use_v3 >= 8) composite_v3_kernel<8, false><<<grid, THREADS, 0, stream>>>(a);
-    else if (use_v3 && use_cvt) composite_v3_kernel<6, true><<<grid, THREADS, 0, stream>>>(a);
-    else if (use_v3) composite_v3_kernel<6, false><<<grid, THREADS, 0, stream>>>(a);
+    const int per_sm = (a.ctas_per_sm > 0 && a.ctas_per_sm < ctas_per_sm) ? a.ctas_per_sm : ctas_per_sm;
+    const int grid = a.num_tiles < sms * per_sm ? a.num_tiles : sms * per_sm;
+    if (use_v3 == 4 && use_pipe) composite_v3_kernel<4, false, true><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3 == 4) composite_v3_kernel<4, false, false><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3 >= 8 && use_cvt) composite_v3_kernel<8, true, false><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3 >= 8) composite_v3_kernel<8, false, false><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3 && use_cvt) composite_v3_kernel<6, true, false><<<grid, THREADS, 0, stream>>>(a);
+    else if (use_v3) composite_v3_kernel<6, false, false><<<grid, THREADS, 0, stream>>>(a);
     else if (use_p4) composite_p4_kernel<<<grid, P4_THREADS, 0, stream>>>(a);
     else if (use_v2 >= 8) composite_v2_kernel<8><<<grid, THREADS, 0, stream>>>(a);
     else if (use_v2 >= 6) composite_v2_kernel<6><<<grid, THREADS, 0, stream>>>(a);

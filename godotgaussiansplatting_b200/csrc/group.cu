@@ -58,6 +58,17 @@ __global__ void group_store_u32_kernel(GroupPeers peers, int which, int index, i
     }
 }
 
+__global__ void __launch_bounds__(32) publish_frame_state_kernel(const FrameState *__restrict__ frame, FrameState *host_mapped) {
+    if (threadIdx.x < 4u) {
+        const uint4 v = reinterpret_cast<const uint4 *>(frame)[threadIdx.x];
+        reinterpret_cast<volatile uint4 *>(host_mapped)[threadIdx.x].x = v.x;
+        reinterpret_cast<volatile uint4 *>(host_mapped)[threadIdx.x].y = v.y;
+        reinterpret_cast<volatile uint4 *>(host_mapped)[threadIdx.x].z = v.z;
+        reinterpret_cast<volatile uint4 *>(host_mapped)[threadIdx.x].w = v.w;
+    }
+    __threadfence_system();
+}
+
 }  // namespace
 
 #ifndef GSR_CPU_EMU
@@ -68,6 +79,12 @@ int preload_group_kernels() {
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, group_wait_extents_kernel));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, group_wait_u32_kernel));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, group_store_u32_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, publish_frame_state_kernel));
+    return GSR_OK;
+}
+int launch_publish_frame_state(const FrameState *frame, FrameState *host_mapped, cudaStream_t stream) {
+    publish_frame_state_kernel<<<1, 32, 0, stream>>>(frame, host_mapped);
+    GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
 int launch_group_wait_extents(GroupFlags *flags, int parity, int world, uint32_t seq, FrameState *frame, cudaStream_t stream) {

@@ -45,7 +45,8 @@ struct gsr_ctx {
     uint32_t lookback_blocks = 0;
     uint64_t frame_counter = 0;
     uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
-    uint32_t *comp_queue = nullptr, *comp_chunk = nullptr;
+    uint32_t *comp_queue = nullptr, *comp_chunk = nullptr, *comp_order = nullptr;
+    int comp_ctas_per_sm = 0, comp_quantum = 2, comp_order_mode = 0, comp_policy = 0;   // scheduling of the compositor (gsr_debug_compositor_config)
     float4 *comp_state = nullptr;
     FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
     ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
@@ -153,7 +154,7 @@ void free_ctx(gsr_ctx *c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); }
     cudaFree(c->stage[0]); cudaFree(c->stage[1]);
-    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
+    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->comp_order); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->sync_word);
@@ -260,7 +261,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     for (int i = 0; i < GSR_HISTORY_FRAMES; ++i) {
         if (cudaEventCreateWithFlags(&c->ev_stat[i], cudaEventDisableTiming) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
     }
-    if (cudaHostAlloc((void **)&c->host_ring, sizeof(FrameState) * GSR_HISTORY_FRAMES, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&c->host_ring, sizeof(FrameState) * GSR_HISTORY_FRAMES, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         set_last_error("cudaHostAlloc(frame mirror) failed"); c->host_ring = nullptr; free_ctx(c); return GSR_ERR_OOM;
     }
     memset(c->host_ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES);
@@ -346,6 +347,7 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     cudaFree(c->bounds); c->bounds = nullptr;
     cudaFree(c->comp_state); c->comp_state = nullptr;
     cudaFree(c->comp_chunk); c->comp_chunk = nullptr;
+    cudaFree(c->comp_order); c->comp_order = nullptr;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaFree(c->fb); c->fb = nullptr;
     cudaFree(c->fb2); c->fb2 = nullptr;
@@ -360,6 +362,7 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     c->comp_queue = reinterpret_cast<uint32_t *>(c->bounds + (size_t)tx * ty);
     GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_state, sizeof(float4) * 256ull * (size_t)tx * ty));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_chunk, sizeof(uint32_t) * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_order, sizeof(uint32_t) * (size_t)tx * ty));
     if (!c->pick_frame) GSR_CUDA_TRY(cudaMalloc((void **)&c->pick_frame, sizeof(FrameState)));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb, sizeof(float4) * (size_t)width * height));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb2, sizeof(float4) * (size_t)width * height));
@@ -574,6 +577,12 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     ca.pick = c->pick;
     ca.frame = c->frame; ca.count_staged = 1;
     ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
+    ca.order = nullptr; ca.quantum = c->comp_quantum; ca.requeue_only_if_fresh = c->comp_policy; ca.ctas_per_sm = c->comp_ctas_per_sm;
+    if (c->comp_order_mode && ca.num_tiles > 0) {   // longest lists first: the long sequential chains start at once instead of in the tail
+        if ((rc = launch_tile_order(c->bounds, ca.tile_begin, ca.row_step, ca.tiles_x, ca.num_tiles, c->comp_order, s))) return rc;
+        ca.order = c->comp_order;
+        launches += 1;
+    }
     ca.trace = c->trace; ca.trace_count = c->trace_count; ca.trace_cap = c->trace_cap;
     if (c->trace) GSR_CUDA_TRY(cudaMemsetAsync(c->trace_count, 0, sizeof(uint32_t), s));
     if (gf && c->grp.rank != 0 && gf->seq >= 3u) {   // the presenting rank must have consumed the frame that used this slot
@@ -588,7 +597,9 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     }
     GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Render'
     // this frame's counters (M, overflow, C) to the pinned mirror: what track_capacity() reads without ever syncing
-    GSR_CUDA_TRY(cudaMemcpyAsync(c->host_ring + slot, c->frame, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+    // (a 16-byte-store kernel into mapped pinned memory, NOT a cudaMemcpyAsync: a D2H copy on the render stream would queue behind the
+    // frame read-back on the copy engine and serialise the two streams)
+    if ((rc = launch_publish_frame_state(c->frame, c->host_ring + slot, s))) return rc;
     GSR_CUDA_TRY(cudaEventRecord(c->ev_stat[slot], s));
     c->ev_valid = true;
     c->frame_counter += 1;
@@ -925,6 +936,7 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
         ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
         ca.frame = c->pick_frame; ca.count_staged = 0;  // own queue counters; slot 0 of the queue, state slot 0
         ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
+        ca.order = nullptr; ca.quantum = c->comp_quantum; ca.requeue_only_if_fresh = c->comp_policy; ca.ctas_per_sm = 0;
         ca.trace = nullptr; ca.trace_count = nullptr; ca.trace_cap = 0;
         for (int i = 0; i < 2; ++i)   // the re-dispatch rewrites the tile's pixels: not under a read-back in flight
             if (c->copied_valid[i]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));
@@ -999,6 +1011,12 @@ GSR_API int gsr_debug_keep_unsorted(gsr_ctx *c, int enable) {
         GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_vals, sizeof(uint32_t) * c->capacity));
     }
     c->keep_unsorted = enable != 0;
+    return GSR_OK;
+}
+
+GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t quantum, int32_t longest_first, int32_t resumed_run_to_completion) {
+    if (!c || quantum < 1 || ctas_per_sm < 0) return GSR_ERR_INVALID;
+    c->comp_ctas_per_sm = ctas_per_sm; c->comp_quantum = quantum; c->comp_order_mode = longest_first != 0; c->comp_policy = resumed_run_to_completion != 0;
     return GSR_OK;
 }
 

@@ -63,15 +63,48 @@ __global__ void __launch_bounds__(256) band_fixup_kernel(const int32_t *__restri
     if (px < width && py < height) out[(uint64_t)py * (uint64_t)width + (uint64_t)px] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
 }
 
+// Longest-list-first order of the tiles a compositor launch owns (scheduling only: pixels do not depend on it).  One CTA: histogram of
+// min(chunks, 255) in shared memory, descending exclusive scan, scatter.  Owned tile k <-> tile id exactly as in the compositor.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint2 *__restrict__ bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x,
+                                                          int32_t num_tiles, uint32_t *__restrict__ order) {
+    __shared__ uint32_t s_hist[256], s_base[256];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 256u) s_hist[tid] = 0u;
+    __syncthreads();
+    auto bin_of = [&](int32_t k) -> uint32_t {
+        const uint32_t tile = (uint32_t)tile_begin + ((uint32_t)k / (uint32_t)tiles_x) * (uint32_t)(row_step * tiles_x) + (uint32_t)k % (uint32_t)tiles_x;
+        const uint2 b = bounds[tile];
+        const int32_t d = (int32_t)(b.y - b.x);
+        const uint32_t chunks = d > 0 ? ((uint32_t)d + 255u) >> 8 : 0u;
+        return chunks < 255u ? chunks : 255u;
+    };
+    for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) atomicAdd(&s_hist[bin_of(k)], 1u);
+    __syncthreads();
+    if (tid == 0) {   // 256 bins: a serial descending scan is cheaper than a barrier tree
+        uint32_t acc = 0u;
+        for (int b = 255; b >= 0; --b) { s_base[b] = acc; acc += s_hist[b]; }
+    }
+    __syncthreads();
+    for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) order[atomicAdd(&s_base[bin_of(k)], 1u)] = (uint32_t)k;
+}
+
 }  // namespace
 
 #ifndef GSR_CPU_EMU  // tests/kernel_emu compiles the kernels above for the CPU; the launchers are CUDA only
+int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *order, cudaStream_t stream) {
+    if (num_tiles <= 0) return GSR_OK;
+    tile_order_kernel<<<1, 1024, 0, stream>>>(bounds, tile_begin, row_step, tiles_x, num_tiles, order);
+    GSR_CUDA_TRY(cudaGetLastError());
+    return GSR_OK;
+}
+
 // Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
 // kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
 int preload_ranges_kernels() {
     cudaFuncAttributes fa;
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_ranges_kernel));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, band_fixup_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_order_kernel));
     return GSR_OK;
 }
 int launch_band_fixup(const int32_t *global_last_plus1, float4 *out, int32_t width, int32_t height, int32_t tiles_x, int32_t num_tiles_total,

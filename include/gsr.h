@@ -240,6 +240,9 @@ GSR_API int gsr_debug_copy(gsr_ctx *ctx, int which, void *dst, size_t bytes);
 /* Record, for every work item of the compositor, {tile<<32|SM id, start ns, end ns, first_chunk<<32|chunks<<1|finished}
  * (4 x uint64 per item, %globaltimer).  max_items = 0 disables.  Profiling aid; not on the frame path by default. */
 GSR_API int gsr_debug_enable_trace(gsr_ctx *ctx, uint32_t max_items);
+/* Scheduling of the compositor's persistent grid (results never depend on it): resident CTAs per SM (0 = as many as fit), chunks a
+ * fresh tile blends before it yields to the queue, longest-list-first ticket order, resumed tiles run to completion. */
+GSR_API int gsr_debug_compositor_config(gsr_ctx *ctx, int32_t ctas_per_sm, int32_t quantum, int32_t longest_first, int32_t resumed_run_to_completion);
 /* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
 GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);
 

@@ -22,8 +22,9 @@ void body(void *p) {
         case 0: gsr::composite_kernel<false>(*l->args); break;   // the shipped kernel
         case 1: gsr::composite_v2_kernel<5>(*l->args); break;       // GSR_COMP_V2
         case 3: gsr::composite_p4_kernel(*l->args); break;       // GSR_COMP_P4 (64 threads)
-        case 4: gsr::composite_v3_kernel<6, false>(*l->args); break;   // GSR_COMP_V3: TMA staging, short transmittance chain
-        case 5: gsr::composite_v3_kernel<6, true>(*l->args); break;    // ... + F2I/I2F rounding of the exp2 argument
+        case 4: gsr::composite_v3_kernel<6, false, false>(*l->args); break;   // GSR_COMP_V3: TMA staging, short transmittance chain
+        case 5: gsr::composite_v3_kernel<6, true, false>(*l->args); break;    // ... + F2I/I2F rounding of the exp2 argument
+        case 6: gsr::composite_v3_kernel<4, false, true>(*l->args); break;    // ... software-pipelined blend loop (prefetched group, early liveness vote)
         default: gsr::composite_kernel<true>(*l->args); break;   // GSR_COMP_HWEXP (exp2f stands in for MUFU.EX2)
     }
 }
@@ -33,7 +34,7 @@ void body(void *p) {
 // which exercises the whole item logic: staging, blend, vote, quantum, spill, re-queue, resume.
 extern "C" int emu_composite(int variant, const void *records, const uint32_t *values, const uint32_t *bounds, float *out_rgba, int width,
                              int height, int tile_begin, int row_step, int num_tiles, float heatmap_factor, uint32_t target_tile_id,
-                             float *pick4, unsigned long long *staged_out, unsigned *pushes_out) {
+                             float *pick4, unsigned long long *staged_out, unsigned *pushes_out, int quantum, int sched_flags) {
     const int tiles_x = (width + 15) / 16;
     gsr::FrameState frame;
     memset(&frame, 0, sizeof frame);
@@ -53,6 +54,16 @@ extern "C" int emu_composite(int variant, const void *records, const uint32_t *v
     a.pick = reinterpret_cast<float4 *>(pick4);
     a.frame = &frame; a.count_staged = 1;
     a.queue = queue; a.state = state; a.state_chunk = state_chunk;
+    a.quantum = quantum > 0 ? quantum : 2; a.requeue_only_if_fresh = (sched_flags & 2) ? 1 : 0; a.ctas_per_sm = 0;
+    uint32_t *order = static_cast<uint32_t *>(calloc(nt, sizeof(uint32_t)));
+    if ((sched_flags & 1) && num_tiles > 0) {   // longest-list-first ticket order (csrc/ranges.cu tile_order_kernel, one block of 1024)
+        struct OL { const uint2 *b; int tb, rs, tx, n; uint32_t *o; } ol{a.bounds, tile_begin, row_step, tiles_x, num_tiles, order};
+        cuda_emu::g_block_dim = cuda_emu::dim{1024, 1, 1};
+        cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
+        glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(1024, 1, 1),
+                            [](void *p) { OL *l = static_cast<OL *>(p); gsr::tile_order_kernel(l->b, l->tb, l->rs, l->tx, l->n, l->o); }, &ol);
+        a.order = order;
+    }
     Launch l{&a, variant};
     const unsigned threads = variant == 3 ? 64u : 128u;
     cuda_emu::g_block_dim = cuda_emu::dim{threads, 1, 1};
@@ -61,7 +72,7 @@ extern "C" int emu_composite(int variant, const void *records, const uint32_t *v
     if (staged_out) *staged_out = frame.staged;
     if (pushes_out) *pushes_out = frame.comp_tail;
     const int ok = (int)frame.comp_done == num_tiles ? 0 : 1;
-    free(queue); free(state); free(state_chunk);
+    free(queue); free(state); free(state_chunk); free(order);
     return ok;
 }
 

@@ -65,7 +65,8 @@ def emu_ranges(keys, T, quirks=1, sharded=0, global_last=-1, grid=7):
     return bounds, int(sync[0])
 
 
-def emu_composite(variant, records, values, bounds, w, h, heat=0.0, target=0xFFFFFFFF, tile_begin=0, row_step=1, num_tiles=None, out=None):
+def emu_composite(variant, records, values, bounds, w, h, heat=0.0, target=0xFFFFFFFF, tile_begin=0, row_step=1, num_tiles=None, out=None,
+                  quantum=2, sched_flags=0):
     gx, gy = (w + 15) // 16, (h + 15) // 16
     out = np.zeros((h, w, 4), dtype=np.float32) if out is None else out
     pick = np.zeros(4, dtype=np.float32)
@@ -73,7 +74,7 @@ def emu_composite(variant, records, values, bounds, w, h, heat=0.0, target=0xFFF
     vals = np.concatenate([np.asarray(values, dtype=np.uint32), np.zeros(512, dtype=np.uint32)])   # the kernels never read past a range
     recs, bnds = np.ascontiguousarray(records), np.ascontiguousarray(bounds, dtype=np.uint32)
     rc = lib().emu_composite(variant, recs.ctypes.data, vals.ctypes.data, bnds.ctypes.data, out.ctypes.data, w, h, tile_begin, row_step,
-                             gx * gy if num_tiles is None else num_tiles, heat, target, pick.ctypes.data, C.byref(staged), C.byref(pushes))
+                             gx * gy if num_tiles is None else num_tiles, heat, target, pick.ctypes.data, C.byref(staged), C.byref(pushes), quantum, sched_flags)
     assert rc == 0, "not every tile was finished"
     return out, int(staged.value), int(pushes.value), pick
 
@@ -92,7 +93,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("variant", [SHIPPED, V2, P4, 4, 5], ids=["shipped", "v2", "p4", "v3", "v3cvt"])
+@pytest.mark.parametrize("variant", [SHIPPED, V2, P4, 4, 5, 6], ids=["shipped", "v2", "p4", "v3", "v3cvt", "v3pipe"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_compositor_kernels_reproduce_the_oracle(case, variant):
     n, seed, w, h, heat, kw = CASES[case]
@@ -112,7 +113,7 @@ def test_hwexp_variant_stays_inside_the_tolerance():
     assert np.abs(out - fr.rgba).max() <= 1e-4 and staged == fr.staged
 
 
-@pytest.mark.parametrize("variant", [SHIPPED, V2, P4, 4, 5], ids=["shipped", "v2", "p4", "v3", "v3cvt"])
+@pytest.mark.parametrize("variant", [SHIPPED, V2, P4, 4, 5, 6], ids=["shipped", "v2", "p4", "v3", "v3cvt", "v3pipe"])
 def test_pick_and_row_interleave(variant):
     n, seed, w, h = 20000, 15, 320, 240
     fr = oracle_frame(n, seed, w, h, scale_boost=1.0)
@@ -421,3 +422,24 @@ def test_present_kernel_matches_the_oracle_conversion(fmt):
     got = np.zeros_like(want)
     assert L.emu_present(rgba.ctypes.data, got.ctypes.data, px, fmt) == 0
     np.testing.assert_array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("variant", [SHIPPED, 4, 6], ids=["shipped", "v3", "v3pipe"])
+@pytest.mark.parametrize("quantum,flags", [(1, 3), (1000, 1), (3, 2), (2, 1)])
+def test_compositor_scheduling_knobs_do_not_change_pixels(variant, quantum, flags):
+    """gsr_debug_compositor_config: longest-list-first ticket order (tile_order_kernel), yield quantum, resumed tiles running to completion
+    -- scheduling only: frame, staged-instance count and pick stay bit-identical to the oracle; also with cyclic row ownership."""
+    n, seed, w, h, heat, kw = CASES["long_lists"]
+    fr = oracle_frame(n, seed, w, h, heat, **kw)
+    out, staged, pushes, _ = emu_composite(variant, fr.records, fr.values, fr.bounds, w, h, heat, quantum=quantum, sched_flags=flags)
+    np.testing.assert_array_equal(bits(out), bits(fr.rgba))
+    assert staged == fr.staged
+    if quantum >= 1000:
+        assert pushes == 0
+    gx, gy = (w + 15) // 16, (h + 15) // 16
+    out2 = np.zeros_like(out)
+    for rem in range(3):
+        rows = len(range(rem, gy, 3))
+        emu_composite(variant, fr.records, fr.values, fr.bounds, w, h, heat, tile_begin=rem * gx, row_step=3, num_tiles=rows * gx, out=out2,
+                      quantum=quantum, sched_flags=flags)
+    np.testing.assert_array_equal(bits(out2), bits(fr.rgba))
