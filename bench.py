@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--splats", type=int, default=int(os.environ.get("GSR_BENCH_SPLATS", "0")), help="debug: override N (marks the line reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-radix", action="store_true")
+    ap.add_argument("--present", default=os.environ.get("GSR_BENCH_PRESENT", "root"), choices=["root", "rows"],
+                    help="group mode, e2e: 'root' = the frame is assembled on rank 0's device and read back over its PCIe link; 'rows' = every rank "
+                         "reads its own tile rows back into one shared page-locked host frame (a PCIe link per GPU)")
     ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["group", "peer", "nccl"],
                     help="N>1: 'group' = NCCL-free shard group (cull split across the ranks, extents exchanged and rows composited over "
                          "NVLink peer memory, device-side flags); 'peer' = replicated cull, compositor stores bands into the root's frame over "
@@ -103,6 +106,8 @@ def make_config(args, wl):
                ("cull split across the ranks, row extents exchanged with peer stores, device-side flags (no NCCL on the frame path)" if args.mgpu == "group"
                 else "replicated cull with early reject, 4-byte NCCL all-reduce per frame") +
                ", compositor stores into the root frame over NVLink peer memory")
+    if args.gpus > 1 and args.mgpu == "group" and args.present == "rows":
+        par += "; e2e: every rank reads its own rows back into one shared page-locked host frame"
     return {"workload": f"{args.workload}: {wl['desc']}", "splats": wl["n"], "width": wl["w"], "height": wl["h"], "sh_degree": 3,
             "parallelism": par, "reduced": bool(args.splats),
             "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * wl["n"] / 1e6)}
@@ -430,6 +435,25 @@ def main():
         rast.set_band(*band)
     # two page-locked host frames: the application consumes frame i while frame i+1 is being copied
     pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+    shared2 = None
+    if group and args.present == "rows":
+        # rows-local presentation: the two host frames live in shared memory, page-locked in EVERY rank's process; each rank copies
+        # its own tile rows over its own PCIe link (no frame data on NVLink, one eighth of the frame per link at 8 GPUs)
+        names = [None, None]
+        if rank == 0:
+            names = [f"/dev/shm/gsr_bench_{os.getpid()}_{k}" for k in range(2)]
+            for nm in names:
+                with open(nm, "wb") as f:
+                    f.truncate(H * W * 16)
+        dist.broadcast_object_list(names, src=0)
+        shared2 = [torch.from_file(nm, shared=True, size=H * W * 4, dtype=torch.float32).view(H, W, 4) for nm in names]
+        for t in shared2:
+            err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
+            assert int(err) == 0, f"cudaHostRegister -> {err}"
+        dist.barrier()
+        if rank == 0:
+            for nm in names:
+                os.unlink(nm)
     can_pack_rgb = world == 1 or peer or group  # optional RGB32F read-back (alpha == 1.0 stays on the device), reported beside the RGBA headline
     pinned = pinned2[0] if rank == 0 else None
 
@@ -444,7 +468,9 @@ def main():
             rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=rgb)
         elif group:
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # extents + rows travel over NVLink; flags order the ranks on the devices
-            if e2e and rank == 0:
+            if e2e and shared2 is not None and not rgb:
+                rast.readback_rows_async(shared2[i & 1].data_ptr())   # every rank: its own rows, its own PCIe link
+            elif e2e and rank == 0:
                 rast.readback_async(pinned2[i & 1].data_ptr(), rgb_only=rgb)
         elif peer:
             rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # band lands in the root's frame (slot i & 1) over NVLink
@@ -461,6 +487,10 @@ def main():
                 pinned.copy_(fb[:H], non_blocking=True)
 
     def timed(e2e):
+        if group and shared2 is not None:   # RGBA e2e: rows stay local and are read back by their owners; otherwise: frame on rank 0
+            torch.cuda.synchronize(); dist.barrier()
+            rast.group_set_present(e2e == "rgba")
+            dist.barrier()
         for i in range(args.warmup):
             step(i, e2e)
         torch.cuda.synchronize()
@@ -471,7 +501,7 @@ def main():
         e0.record(stream)
         for i in range(args.warmup, args.warmup + args.steps):
             step(i, e2e)
-        if e2e and (world == 1 or ((peer or group) and rank == 0)):
+        if e2e and (world == 1 or ((peer or group) and rank == 0) or (group and shared2 is not None)):
             rast.stream_join()  # the timed region ends when the last frame has landed in host memory
         e1.record(stream)
         torch.cuda.synchronize()
@@ -546,6 +576,8 @@ def main():
         vp_c, ub_c = frames[args.warmup]
         got_t = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
         torch.cuda.synchronize(); dist.barrier()
+        if group and shared2 is not None:
+            rast.group_set_present(False); dist.barrier()
         rast.render_raw(vp_c, ub_c, 0.0, None, asynchronous=True)
         if peer:
             if rank == 0:

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSR_LIB_PATH") or os.path.join(HERE, "libgsr.so")  # env override: kernel-variant experiments only
 
 GSR_OK, GSR_ERR_INVALID, GSR_ERR_CUDA, GSR_ERR_OOM, GSR_ERR_STATE, GSR_ERR_OVERFLOW = range(6)
-GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES, GSR_FLAG_FAST_REJECT, GSR_FLAG_STATIC_CAPACITY = 0x1, 0x2, 0x4, 0x8
+GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES, GSR_FLAG_FAST_REJECT, GSR_FLAG_STATIC_CAPACITY, GSR_FLAG_UNCONTRACTED_BLEND = 0x1, 0x2, 0x4, 0x8, 0x10
 (GSR_BUF_RECORDS, GSR_BUF_KEYS, GSR_BUF_VALUES, GSR_BUF_BOUNDS, GSR_BUF_KEYS_UNSORTED, GSR_BUF_VALUES_UNSORTED,
  GSR_BUF_FRAMEBUFFER, GSR_BUF_COMPOSITOR_TRACE, GSR_BUF_COMPOSITOR_TRACE_COUNT) = range(9)
 
@@ -20,7 +20,7 @@ GSR_FLAG_REFERENCE_QUIRKS, GSR_FLAG_FIXED_RANGES, GSR_FLAG_FAST_REJECT, GSR_FLAG
 EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_upload_ply_raw", "gsr_resize", "gsr_set_band", "gsr_set_row_interleave", "gsr_band_sync_word", "gsr_band_fixup", "gsr_render",
     "gsr_render_async", "gsr_render_async_rgb", "gsr_render_async_fmt", "gsr_output_bytes", "gsr_present_device", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
-    "gsr_stream_join", "gsr_group_export", "gsr_group_attach", "gsr_group_detach", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
+    "gsr_stream_join", "gsr_group_export", "gsr_group_attach", "gsr_group_detach", "gsr_group_set_present", "gsr_readback_rows_async", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
     "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_compositor_config", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
     "gsr_device_count", "gsr_version",
@@ -91,6 +91,8 @@ def lib():
         L.gsr_group_export.argtypes = [vp, vp]
         L.gsr_group_attach.argtypes = [vp, C.c_int32, C.c_int32, vp]
         L.gsr_group_detach.argtypes = [vp]
+        L.gsr_group_set_present.argtypes = [vp, C.c_int32]
+        L.gsr_readback_rows_async.argtypes = [vp, vp]
         L.gsr_readback_async.argtypes = [vp, vp, C.c_int]
         L.gsr_peer_export_framebuffers.argtypes = [vp, vp]
         L.gsr_peer_import_framebuffers.argtypes = [vp, vp]
@@ -103,7 +105,7 @@ def lib():
         L.gsr_debug_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.gsr_debug_keep_unsorted.argtypes = [vp, C.c_int]
         L.gsr_debug_enable_trace.argtypes = [vp, u32]
-        L.gsr_debug_compositor_config.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.gsr_debug_compositor_config.argtypes = [vp, C.c_int32, C.c_int32]
         L.gsr_sorter_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp)]
         L.gsr_sorter_destroy.argtypes = [vp]
         L.gsr_sorter_sort_device.argtypes = [vp, vp, vp, C.c_uint64, vp]

@@ -11,7 +11,6 @@ namespace gsr {
 constexpr int TILE = 16;            // rasterizer.gd:4 TILE_SIZE
 constexpr int NUM_PLANES = 15;      // 60-float Splat = 15 float4 planes in SoA
 constexpr int PROJ_THREADS = 256;   // gsplat_projection.glsl:31 local_size_x
-#define GSR_COMP_MAX_PUSHES 7         // a tile is handed back to the compositor queue at most this many times
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -92,11 +91,8 @@ struct FrameState {
     uint32_t proj_ticket;          // dynamic block id for the projection look-back
     uint32_t pad0;
     unsigned long long staged;     // C: instances staged by the compositor (sum of consumed chunk sizes)
-    uint32_t comp_head;            // compositor work queue: next ticket
-    uint32_t comp_tail;            //                        next free slot for a re-queued tile
-    uint32_t comp_done;            //                        tiles finished
-    uint32_t comp_qhead;           //                        next re-queued entry to pop
-    uint32_t pad[2];
+    uint32_t comp_head;            // compositor: next tile ticket of the persistent grid
+    uint32_t pad[5];
 };
 static_assert(sizeof(FrameState) == 64, "FrameState is one 64-byte slot of the history ring");
 
@@ -215,22 +211,24 @@ struct CompositeArgs {
     float heatmap_factor;
     uint32_t target_tile_id; // 0xFFFFFFFF = none (rasterizer.gd:158)
     float4 *pick;            // tile_splat_pos buffer (gsplat_render.glsl:33-36)
-    FrameState *frame;       // per-launch queue counters (comp_head/tail/done must be 0) + staged-instance counter
+    FrameState *frame;       // ticket counter (comp_head must be 0) + staged-instance counter
     int32_t count_staged;    // add this launch's consumed instances to frame->staged (0 for the pick re-dispatch)
-    uint32_t *queue;         // [GSR_COMP_MAX_PUSHES * num_tiles] zero-initialised: re-queued tiles (tile id + 1)
-    float4 *state;           // [num_tiles][2][128] spilled per-pixel state of re-queued tiles
-    uint32_t *state_chunk;   // [num_tiles] first chunk still to blend
-    const uint32_t *order;   // optional: ticket k renders owned tile order[k] (longest lists first, launch_tile_order); nullptr = natural order
-    int32_t quantum;         // chunks blended before an unfinished tile is handed back to the queue (>= 1; large = never)
-    int32_t requeue_only_if_fresh;  // hand a tile back only while fresh tiles are still waiting for a CTA
-    int32_t ctas_per_sm;     // resident CTAs per SM of the persistent grid (0 = as many as fit)
-    ulonglong4 *trace;       // optional schedule trace (debug): {tile<<32|smid, t0_ns, t1_ns, first_chunk<<32|iters<<1|finished}
+    const uint32_t *order;   // optional: ticket k renders owned tile order[k] (longest chains first, launch_tile_order); nullptr = natural order
+    uint32_t *consumed;      // optional [num_tiles]: chunks each owned tile blended before its stop rule fired | 1u << 31 (next frame's order hint)
+    int32_t ctas_per_sm;     // resident CTAs per SM of the persistent grid
+    int32_t sm_count;
+    int32_t contract;        // 1: the gsr spec (explicit fma at the GLSL-legal contraction points); 0: no contraction (GSR_FLAG_UNCONTRACTED_BLEND)
+    ulonglong4 *trace;       // optional schedule trace (debug): {tile<<32|smid, t0_ns, t1_ns, consumed<<32|list_chunks<<1|1}
     uint32_t *trace_count;
     uint32_t trace_cap;
 };
 int launch_composite(const CompositeArgs &a, cudaStream_t stream);
-// order[0 .. num_tiles) = owned-tile indices sorted by descending list length (counting sort by 256-splat chunks, one CTA)
-int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *order, cudaStream_t stream);
+int composite_max_ctas_per_sm(int *out);
+// order[0 .. num_tiles) = owned-tile indices sorted by descending expected chain length: the chunk count the tile consumed in the
+// previous frame (hint[k] with bit 31 set; the bit is cleared here) or, without a hint, its list length in chunks capped at
+// `cap_chunks` (a list is rarely consumed beyond ~20 chunks).  Counting sort, one CTA.  Scheduling only: pixels do not depend on it.
+int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *hint, uint32_t *order,
+                      cudaStream_t stream);
 
 int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
                       cudaStream_t stream);

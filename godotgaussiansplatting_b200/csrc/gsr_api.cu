@@ -45,9 +45,9 @@ struct gsr_ctx {
     uint32_t lookback_blocks = 0;
     uint64_t frame_counter = 0;
     uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
-    uint32_t *comp_queue = nullptr, *comp_chunk = nullptr, *comp_order = nullptr;
-    int comp_ctas_per_sm = 0, comp_quantum = 2, comp_order_mode = 0, comp_policy = 0;   // scheduling of the compositor (gsr_debug_compositor_config)
-    float4 *comp_state = nullptr;
+    uint32_t *comp_order = nullptr, *comp_hint = nullptr;   // longest-chain-first ticket order of the compositor + last frame's consumed chunks
+    int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
+    uint64_t comp_hint_key = 0;   // ownership (band, rows) the hints were recorded under: a change invalidates them
     FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
     ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
     uint32_t *trace_count = nullptr;
@@ -83,6 +83,7 @@ struct gsr_ctx {
         float4 *root_fb[2] = {nullptr, nullptr};  // the presenting rank's two frames
         void *opened[3 * GROUP_MAX] = {};    // IPC mappings to close
         int n_opened = 0;
+        int present_rows = 0;             // 1: every rank keeps its rows in its own frames and reads them back itself (gsr_group_set_present)
         uint32_t seq = 0;                 // frames rendered by the group so far (lockstep on all ranks)
         uint64_t slice = 0;               // splats per rank (256-aligned)
     } grp;
@@ -139,7 +140,7 @@ void group_detach(gsr_ctx *c) {
     for (int i = 0; i < c->grp.n_opened; ++i) cudaIpcCloseMemHandle(c->grp.opened[i]);
     c->grp.n_opened = 0;
     if (c->grp.world > 1) { c->row_mod = 1; c->row_rem = 0; }
-    c->grp.world = 0; c->grp.rank = 0; c->grp.seq = 0;
+    c->grp.world = 0; c->grp.rank = 0; c->grp.seq = 0; c->grp.present_rows = 0;
     c->grp.root_fb[0] = c->grp.root_fb[1] = nullptr;
 }
 
@@ -154,7 +155,7 @@ void free_ctx(gsr_ctx *c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); }
     cudaFree(c->stage[0]); cudaFree(c->stage[1]);
-    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_state); cudaFree(c->comp_chunk); cudaFree(c->comp_order); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
+    cudaFree(c->ring); cudaFree(c->lookback); cudaFree(c->bounds); cudaFree(c->comp_order); cudaFree(c->comp_hint); cudaFree(c->pick_frame); cudaFree(c->fb); cudaFree(c->fb2); cudaFree(c->pick); cudaFree(c->staging);
     for (int i = 0; i < 2; ++i) { if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->sync_word);
@@ -216,6 +217,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     if (c->capacity > c->capacity_max) c->capacity = c->capacity_max;
     c->plane_stride = (c->max_splats + 255ull) & ~255ull;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    if ((rc = composite_max_ctas_per_sm(&c->comp_max_ctas))) { delete c; return rc; }
 
 #define TRY_ALLOC(ptr, bytes)                                                                      \
     do {                                                                                           \
@@ -345,9 +347,8 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->width = c->height = c->tiles_x = c->tiles_y = 0;  // a failure below leaves the context in the "before gsr_resize" state
     cudaFree(c->bounds); c->bounds = nullptr;
-    cudaFree(c->comp_state); c->comp_state = nullptr;
-    cudaFree(c->comp_chunk); c->comp_chunk = nullptr;
     cudaFree(c->comp_order); c->comp_order = nullptr;
+    cudaFree(c->comp_hint); c->comp_hint = nullptr;
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaFree(c->fb); c->fb = nullptr;
     cudaFree(c->fb2); c->fb2 = nullptr;
@@ -358,11 +359,11 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); c->peer_opened = false; }
     c->peer_mode = false; c->peer_fb[0] = c->peer_fb[1] = nullptr; c->peer_counter = 0; c->async_counter = 0;
     group_detach(c);   // same for a shard group: every rank resizes, exports and attaches again
-    GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)tx * ty));
-    c->comp_queue = reinterpret_cast<uint32_t *>(c->bounds + (size_t)tx * ty);
-    GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_state, sizeof(float4) * 256ull * (size_t)tx * ty));
-    GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_chunk, sizeof(uint32_t) * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->bounds, sizeof(uint2) * (size_t)tx * ty));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_order, sizeof(uint32_t) * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->comp_hint, sizeof(uint32_t) * (size_t)tx * ty));
+    GSR_CUDA_TRY(cudaMemsetAsync(c->comp_hint, 0, sizeof(uint32_t) * (size_t)tx * ty, c->stream));
+    c->comp_hint_key = 0;
     if (!c->pick_frame) GSR_CUDA_TRY(cudaMalloc((void **)&c->pick_frame, sizeof(FrameState)));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb, sizeof(float4) * (size_t)width * height));
     GSR_CUDA_TRY(cudaMalloc((void **)&c->fb2, sizeof(float4) * (size_t)width * height));
@@ -466,7 +467,7 @@ static int track_capacity(gsr_ctx *c) {
     return GSR_OK;
 }
 
-struct GroupFrame { uint32_t seq; int parity; };
+struct GroupFrame { uint32_t seq; int parity; int rows_local; };
 
 static GroupPeers group_peers(const gsr_ctx *c, int parity) {
     GroupPeers p;
@@ -497,7 +498,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     cudaEvent_t *ev = c->ev + 5 * slot;
     GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
     GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->max_splats), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, (sizeof(uint2) + GSR_COMP_MAX_PUSHES * sizeof(uint32_t)) * (size_t)c->tiles_x * c->tiles_y, s));  // bounds + queue
+    GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
     GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 
     ProjectionArgs pa;
@@ -512,15 +513,13 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
     // Conservative early reject + compaction of the survivors over 1024-splat CTAs (projection_sharded_kernel): exact, and
     // measured on B200 (c3, one rank of G emulated): G=8 0.39 vs 0.46 ms, G=4 equal, G=2 slower (with two ranks nearly every
-    // splat's conservative extent touches both).  So: on by default from 6 ranks, or on request (flag / GSR_FAST_REJECT=1).
-    static const int env_reject = getenv("GSR_FAST_REJECT") ? atoi(getenv("GSR_FAST_REJECT")) : -1;
-    const bool want_reject = env_reject >= 0 ? env_reject != 0 : ((c->flags & GSR_FLAG_FAST_REJECT) != 0 || c->row_mod >= 6);
-    pa.fast_reject = (want_reject && c->row_mod >= 2) ? 1 : 0;
+    // splat's conservative extent touches both).  So: on by default from 6 ranks, or on request (GSR_FLAG_FAST_REJECT).
+    const bool want_reject = (c->flags & GSR_FLAG_FAST_REJECT) != 0 || c->row_mod >= 6;
+    pa.fast_reject = (want_reject && fast) ? 1 : 0;
     pa.fast_mode = fast ? 1 : 0;
     // full frame: 12 of 32 lanes (below that, per-lane 128-bit gathers move fewer bytes); sharded: few lanes of a warp land in
     // this rank's rows and the latency-bound gather path was measured slower than fetching the whole 6 KB slice (0.60 vs 0.46 ms)
-    static const int bulk_env = getenv("GSR_SH_BULK_MIN") ? atoi(getenv("GSR_SH_BULK_MIN")) : 0;
-    pa.sh_bulk_min = bulk_env > 0 ? bulk_env : (fast ? 1 : 12);
+    pa.sh_bulk_min = fast ? 1 : 12;
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
     pa.extents = nullptr;
@@ -576,22 +575,27 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     ca.target_tile_id = 0xFFFFFFFFu;  // rasterizer.gd:158
     ca.pick = c->pick;
     ca.frame = c->frame; ca.count_staged = 1;
-    ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
-    ca.order = nullptr; ca.quantum = c->comp_quantum; ca.requeue_only_if_fresh = c->comp_policy; ca.ctas_per_sm = c->comp_ctas_per_sm;
-    if (c->comp_order_mode && ca.num_tiles > 0) {   // longest lists first: the long sequential chains start at once instead of in the tail
-        if ((rc = launch_tile_order(c->bounds, ca.tile_begin, ca.row_step, ca.tiles_x, ca.num_tiles, c->comp_order, s))) return rc;
+    ca.order = nullptr; ca.consumed = c->comp_hint;
+    ca.ctas_per_sm = c->comp_ctas_per_sm < c->comp_max_ctas ? c->comp_ctas_per_sm : c->comp_max_ctas; ca.sm_count = c->sm_count;
+    ca.contract = (c->flags & GSR_FLAG_UNCONTRACTED_BLEND) ? 0 : 1;
+    {   // the hints describe the owned-tile indexing of the frame that wrote them: drop them when the ownership changes
+        const uint64_t key = ((uint64_t)(uint32_t)ca.tile_begin << 32) ^ ((uint64_t)(uint32_t)ca.row_step << 24) ^ (uint64_t)(uint32_t)ca.num_tiles;
+        if (key != c->comp_hint_key) { GSR_CUDA_TRY(cudaMemsetAsync(c->comp_hint, 0, sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y, s)); c->comp_hint_key = key; }
+    }
+    if (c->comp_order_mode && ca.num_tiles > 0) {   // longest chains first: the long sequential chains start at once instead of in the tail
+        if ((rc = launch_tile_order(c->bounds, ca.tile_begin, ca.row_step, ca.tiles_x, ca.num_tiles, c->comp_hint, c->comp_order, s))) return rc;
         ca.order = c->comp_order;
         launches += 1;
     }
     ca.trace = c->trace; ca.trace_count = c->trace_count; ca.trace_cap = c->trace_cap;
     if (c->trace) GSR_CUDA_TRY(cudaMemsetAsync(c->trace_count, 0, sizeof(uint32_t), s));
-    if (gf && c->grp.rank != 0 && gf->seq >= 3u) {   // the presenting rank must have consumed the frame that used this slot
+    if (gf && !gf->rows_local && c->grp.rank != 0 && gf->seq >= 3u) {   // the presenting rank must have consumed the frame that used this slot
         if ((rc = launch_group_wait_released(c->grp.flags[c->grp.rank], gf->seq - 2u, s))) return rc;
         launches += 1;
     }
     if ((rc = launch_composite(ca, s))) return rc;
     launches += ca.num_tiles > 0 ? 1 : 0;
-    if (gf) {   // rows have landed in the presenting rank's frame: tell it (system-scope flag store after the kernel boundary)
+    if (gf && !gf->rows_local) {   // rows have landed in the presenting rank's frame: tell it (system-scope flag store after the kernel boundary)
         if ((rc = launch_group_signal_done(group_peers(c, gf->parity), 0, c->grp.rank, gf->seq, s))) return rc;
         launches += 1;
     }
@@ -659,11 +663,16 @@ static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uni
         GroupFrame gf;
         gf.seq = c->grp.seq + 1u; gf.parity = (int)(gf.seq & 1u);
         const int slot = (int)((gf.seq - 1u) & 1u);
-        if (c->grp.rank == 0) {
+        gf.rows_local = c->grp.present_rows;
+        float4 *target = c->grp.root_fb[slot];
+        if (gf.rows_local) {   // every rank presents its own rows (host consumer, one PCIe link per GPU): only its own read-back gates the slot
+            target = slot ? c->fb2 : c->fb;
+            if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+        } else if (c->grp.rank == 0) {
             if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
             if (gf.seq >= 3u && (rc = launch_group_release(group_peers(c, gf.parity), c->grp.world, gf.seq - 2u, c->stream))) return rc;
         }
-        if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, c->grp.root_fb[slot], &gf))) return rc;
+        if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, target, &gf))) return rc;
         c->grp.seq = gf.seq;
         return GSR_OK;
     }
@@ -742,6 +751,43 @@ GSR_API int gsr_readback_async(gsr_ctx *c, void *pinned_host, int32_t format) {
     }
     const int slot = (c->fb_last == c->fb2 || (c->peer_mode && c->fb_last == c->peer_fb[1])) ? 1 : 0;
     return readback_enqueue(c, c->fb_last, slot, pinned_host, format);
+}
+
+GSR_API int gsr_group_set_present(gsr_ctx *c, int32_t rows_local) {
+    if (!c) return GSR_ERR_INVALID;
+    if (c->grp.world <= 1) { set_last_error("gsr_group_set_present: attach the group first"); return GSR_ERR_STATE; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    c->grp.present_rows = rows_local != 0;
+    c->copied_valid[0] = c->copied_valid[1] = false;
+    return GSR_OK;
+}
+
+// Rows-local presentation: this rank's tile rows (row % world == rank) of the most recent frame -> the same rows of a full-frame
+// RGBA32F host image (`host_frame` = address of pixel (0,0); page-locked in THIS process), on this rank's copy stream and PCIe link.
+GSR_API int gsr_readback_rows_async(gsr_ctx *c, void *host_frame) {
+    if (!c || !host_frame) return GSR_ERR_INVALID;
+    if (c->grp.world <= 1 || !c->grp.present_rows || !c->fb_last) { set_last_error("gsr_readback_rows_async: needs an attached group in rows-local presentation and a rendered frame"); return GSR_ERR_STATE; }
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    const int slot = (int)((c->grp.seq - 1u) & 1u);
+    const size_t row_bytes = sizeof(float4) * (size_t)c->width, slab = row_bytes * TILE;
+    const int G = c->grp.world, r = c->grp.rank;
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->stream));
+    GSR_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+    const int full_rows = c->height / TILE;                        // tile rows that are 16 pixel rows high
+    const int n_full = r < full_rows ? (full_rows - 1 - r) / G + 1 : 0;
+    const char *src = reinterpret_cast<const char *>(c->fb_last);
+    char *dst = static_cast<char *>(host_frame);
+    if (n_full) GSR_CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)r * slab, (size_t)G * slab, src + (size_t)r * slab, (size_t)G * slab, slab, (size_t)n_full,
+                                               cudaMemcpyDeviceToHost, c->copy_stream));
+    if (c->height % TILE && full_rows % G == r)                    // the ragged last tile row, if this rank owns it
+        GSR_CUDA_TRY(cudaMemcpyAsync(dst + (size_t)full_rows * slab, src + (size_t)full_rows * slab, row_bytes * (size_t)(c->height % TILE), cudaMemcpyDeviceToHost, c->copy_stream));
+    GSR_CUDA_TRY(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->copied_valid[slot] = true;
+    return GSR_OK;
 }
 
 GSR_API int gsr_peer_export_framebuffers(gsr_ctx *c, void *handles128) {
@@ -935,13 +981,12 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
         ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1; ca.row_step = 1;
         ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
         ca.frame = c->pick_frame; ca.count_staged = 0;  // own queue counters; slot 0 of the queue, state slot 0
-        ca.queue = c->comp_queue; ca.state = c->comp_state; ca.state_chunk = c->comp_chunk;
-        ca.order = nullptr; ca.quantum = c->comp_quantum; ca.requeue_only_if_fresh = c->comp_policy; ca.ctas_per_sm = 0;
+        ca.order = nullptr; ca.consumed = nullptr; ca.ctas_per_sm = 1; ca.sm_count = c->sm_count;
+        ca.contract = (c->flags & GSR_FLAG_UNCONTRACTED_BLEND) ? 0 : 1;
         ca.trace = nullptr; ca.trace_count = nullptr; ca.trace_cap = 0;
         for (int i = 0; i < 2; ++i)   // the re-dispatch rewrites the tile's pixels: not under a read-back in flight
             if (c->copied_valid[i]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));
         GSR_CUDA_TRY(cudaMemsetAsync(c->pick_frame, 0, sizeof(FrameState), c->stream));
-        GSR_CUDA_TRY(cudaMemsetAsync(c->comp_queue, 0, sizeof(uint32_t) * GSR_COMP_MAX_PUSHES, c->stream));  // one tile => <= 7 pushes
         if ((rc = launch_composite(ca, c->stream))) return rc;
     }
     GSR_CUDA_TRY(cudaMemcpyAsync(out_xyzn, c->pick, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -1014,9 +1059,9 @@ GSR_API int gsr_debug_keep_unsorted(gsr_ctx *c, int enable) {
     return GSR_OK;
 }
 
-GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t quantum, int32_t longest_first, int32_t resumed_run_to_completion) {
-    if (!c || quantum < 1 || ctas_per_sm < 0) return GSR_ERR_INVALID;
-    c->comp_ctas_per_sm = ctas_per_sm; c->comp_quantum = quantum; c->comp_order_mode = longest_first != 0; c->comp_policy = resumed_run_to_completion != 0;
+GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t longest_first) {
+    if (!c || ctas_per_sm < 0) return GSR_ERR_INVALID;
+    c->comp_ctas_per_sm = ctas_per_sm ? ctas_per_sm : c->comp_max_ctas; c->comp_order_mode = longest_first != 0;
     return GSR_OK;
 }
 

@@ -778,6 +778,10 @@ uint32_t projection_num_blocks(uint32_t num_splats) { return (num_splats + PROJ_
 // kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
 int preload_projection_kernels() {
     cudaFuncAttributes fa;
+    // dynamic shared memory opt-in is a per-device function attribute: set here, once per context creation, on the context's device
+    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROJ_SMEM_BYTES));
+    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
+    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_kernel));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel<false>));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel<true>));
@@ -798,26 +802,11 @@ int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     const uint32_t blocks = projection_num_blocks(a.num_splats);
     if (blocks == 0) return GSR_OK;
     if (a.fast_reject || a.extents) {  // sharded variant: 1024 splats per CTA
-        static int sh_dev = -1;
-        int d = 0;
-        GSR_CUDA_TRY(cudaGetDevice(&d));
-        if (sh_dev != d) {
-            GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
-            GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
-            sh_dev = d;
-        }
         const uint32_t sblocks = (a.num_splats + SH_SPLATS - 1) / SH_SPLATS;
         if (a.extents) projection_sharded_kernel<true><<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
         else projection_sharded_kernel<false><<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
         GSR_CUDA_TRY(cudaGetLastError());
         return GSR_OK;
-    }
-    static int attr_dev = -1;  // function attributes are per device: re-apply when the calling context's device changes
-    int dev = 0;
-    GSR_CUDA_TRY(cudaGetDevice(&dev));
-    if (attr_dev != dev) {
-        GSR_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROJ_SMEM_BYTES));
-        attr_dev = dev;
     }
     projection_kernel<<<blocks, PROJ_THREADS, PROJ_SMEM_BYTES, stream>>>(a);
     GSR_CUDA_TRY(cudaGetLastError());

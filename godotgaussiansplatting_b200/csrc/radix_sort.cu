@@ -313,8 +313,6 @@ constexpr size_t sweep_smem() {
     return sizeof(uint32_t) * ((SWEEP_THREADS / 32) * RADIX + SWEEP_TILE * (PAIRS ? 2 : 1));
 }
 
-int g_sm_count = 0;
-
 }  // namespace
 
 #ifndef GSR_CPU_EMU  // host side: CUDA only (tests/kernel_emu drives the kernels above itself)
@@ -350,7 +348,8 @@ int sort_workspace_create(SortWorkspace &ws, uint64_t max_n, bool need_alt_buffe
     }
     int dev = 0;
     GSR_CUDA_TRY(cudaGetDevice(&dev));
-    GSR_CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    int sm_count = 0;
+    GSR_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     auto kp = onesweep_kernel<SWEEP_THREADS, SWEEP_ITEMS, true>;
     auto kk = onesweep_kernel<SWEEP_THREADS, SWEEP_ITEMS, false>;
     GSR_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem<true>()));
@@ -363,9 +362,9 @@ int sort_workspace_create(SortWorkspace &ws, uint64_t max_n, bool need_alt_buffe
         return GSR_ERR_CUDA;
     }
     auto cap_grid = [&](int g) { return (int)((uint32_t)g < ws.max_tiles ? (uint32_t)g : ws.max_tiles); };
-    ws.grid_sweep_pairs = cap_grid(g_sm_count * occ_p);
-    ws.grid_sweep_keys = cap_grid(g_sm_count * occ_k);
-    ws.grid_hist = g_sm_count * 4;
+    ws.grid_sweep_pairs = cap_grid(sm_count * occ_p);
+    ws.grid_sweep_keys = cap_grid(sm_count * occ_k);
+    ws.grid_hist = sm_count * 4;
     return GSR_OK;
 }
 

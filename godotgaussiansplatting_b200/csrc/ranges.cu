@@ -63,43 +63,49 @@ __global__ void __launch_bounds__(256) band_fixup_kernel(const int32_t *__restri
     if (px < width && py < height) out[(uint64_t)py * (uint64_t)width + (uint64_t)px] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
 }
 
-// Longest-list-first order of the tiles a compositor launch owns (scheduling only: pixels do not depend on it).  One CTA: histogram of
-// min(chunks, 255) in shared memory, descending exclusive scan, scatter.  Owned tile k <-> tile id exactly as in the compositor.
+// Longest-chain-first order of the tiles a compositor launch owns (scheduling only: pixels do not depend on it).  One CTA: histogram
+// of the expected chunk count in shared memory, descending exclusive scan, scatter.  Expected chunks = what the tile consumed in the
+// previous frame when the compositor left a hint (bit 31 set), else min(list chunks, NO_HINT_CAP): beyond a few chunks the list
+// length says little about where the tile-stop vote fires (measured on c3: lists of 16..360 chunks are all consumed to ~8 +- 4).
+// Owned tile k <-> tile id exactly as in the compositor.
+constexpr uint32_t ORDER_BINS = 64, ORDER_NO_HINT_CAP = 24;
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2 *__restrict__ bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x,
-                                                          int32_t num_tiles, uint32_t *__restrict__ order) {
-    __shared__ uint32_t s_hist[256], s_base[256];
+                                                          int32_t num_tiles, uint32_t *__restrict__ hint, uint32_t *__restrict__ order) {
+    __shared__ uint32_t s_hist[ORDER_BINS], s_base[ORDER_BINS];
     const uint32_t tid = threadIdx.x;
-    if (tid < 256u) s_hist[tid] = 0u;
+    if (tid < ORDER_BINS) s_hist[tid] = 0u;
     __syncthreads();
     auto bin_of = [&](int32_t k) -> uint32_t {
         const uint32_t tile = (uint32_t)tile_begin + ((uint32_t)k / (uint32_t)tiles_x) * (uint32_t)(row_step * tiles_x) + (uint32_t)k % (uint32_t)tiles_x;
         const uint2 b = bounds[tile];
         const int32_t d = (int32_t)(b.y - b.x);
-        const uint32_t chunks = d > 0 ? ((uint32_t)d + 255u) >> 8 : 0u;
-        return chunks < 255u ? chunks : 255u;
+        const uint32_t list = d > 0 ? ((uint32_t)d + 255u) >> 8 : 0u;
+        uint32_t expect = list < ORDER_NO_HINT_CAP ? list : ORDER_NO_HINT_CAP;
+        if (hint) {
+            const uint32_t h = hint[k];
+            if (h & 0x80000000u) {   // the chain can be at most one chunk longer per chunk the list grew; an empty list stays empty
+                const uint32_t c = (h & 0x7FFFFFFFu) + 1u;
+                expect = list < c ? list : c;
+            }
+        }
+        return expect < ORDER_BINS - 1u ? expect : ORDER_BINS - 1u;
     };
     for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) atomicAdd(&s_hist[bin_of(k)], 1u);
     __syncthreads();
-    if (tid == 0) {   // 256 bins: a serial descending scan is cheaper than a barrier tree
+    if (tid == 0) {   // 64 bins: a serial descending scan is cheaper than a barrier tree
         uint32_t acc = 0u;
-        for (int b = 255; b >= 0; --b) { s_base[b] = acc; acc += s_hist[b]; }
+        for (int b = (int)ORDER_BINS - 1; b >= 0; --b) { s_base[b] = acc; acc += s_hist[b]; }
     }
     __syncthreads();
     for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) order[atomicAdd(&s_base[bin_of(k)], 1u)] = (uint32_t)k;
+    __syncthreads();
+    if (hint) for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) hint[k] &= 0x7FFFFFFFu;   // consumed: the compositor sets bit 31 again
 }
 
 }  // namespace
 
 #ifndef GSR_CPU_EMU  // tests/kernel_emu compiles the kernels above for the CPU; the launchers are CUDA only
-int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *order, cudaStream_t stream) {
-    if (num_tiles <= 0) return GSR_OK;
-    tile_order_kernel<<<1, 1024, 0, stream>>>(bounds, tile_begin, row_step, tiles_x, num_tiles, order);
-    GSR_CUDA_TRY(cudaGetLastError());
-    return GSR_OK;
-}
-
-// Force-load this file's kernels (CUDA loads modules lazily; a first launch that has to load code while another context's
-// kernel spins on a flag this launch would satisfy can stall the host: see gsr_group_attach).
+// Force-load this file's kernels (CUDA loads modules lazily; see gsr_create).
 int preload_ranges_kernels() {
     cudaFuncAttributes fa;
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_ranges_kernel));
@@ -107,6 +113,15 @@ int preload_ranges_kernels() {
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_order_kernel));
     return GSR_OK;
 }
+
+int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *hint, uint32_t *order,
+                      cudaStream_t stream) {
+    if (num_tiles <= 0) return GSR_OK;
+    tile_order_kernel<<<1, 1024, 0, stream>>>(bounds, tile_begin, row_step, tiles_x, num_tiles, hint, order);
+    GSR_CUDA_TRY(cudaGetLastError());
+    return GSR_OK;
+}
+
 int launch_band_fixup(const int32_t *global_last_plus1, float4 *out, int32_t width, int32_t height, int32_t tiles_x, int32_t num_tiles_total,
                       int32_t band_y0, int32_t band_y1, int32_t row_mod, int32_t row_rem, cudaStream_t stream) {
     band_fixup_kernel<<<1, 256, 0, stream>>>(global_last_plus1, out, width, height, tiles_x, num_tiles_total, band_y0, band_y1, row_mod, row_rem);

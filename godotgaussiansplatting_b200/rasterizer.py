@@ -246,6 +246,12 @@ class GaussianSplattingRasterizer:
         buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
         _lib.check(_lib.lib().gsr_group_attach(self._ctx, int(rank), int(world), buf), "gsr_group_attach")
 
+    def group_set_present(self, rows_local: bool) -> None:
+        _lib.check(_lib.lib().gsr_group_set_present(self._ctx, int(bool(rows_local))), "gsr_group_set_present")
+
+    def readback_rows_async(self, host_frame_ptr: int) -> None:
+        _lib.check(_lib.lib().gsr_readback_rows_async(self._ctx, C.c_void_p(host_frame_ptr)), "gsr_readback_rows_async")
+
     def group_detach(self) -> None:
         _lib.check(_lib.lib().gsr_group_detach(self._ctx), "gsr_group_detach")
 

@@ -50,6 +50,11 @@ enum {
                                           truncated frame; an asynchronous frame that overflowed is flagged (gsr_stats.overflow /
                                           gsr_frame_record.overflow) and the next one has room */
 
+#define GSR_FLAG_UNCONTRACTED_BLEND 0x10u /* debug: evaluate gsplat_render.glsl:84-90 with one rounding per GLSL operator (no fma anywhere).
+                                            The default contracts at the five GLSL-legal points of the gsr spec; without
+                                            contraction the frame is bit-identical to the reference's own shader text executed on the CPU
+                                            (oracle/_ref; oracle.set_blend_contraction(False)). */
+
 /* ---- gsr_debug_copy selectors (parity taps; not on the frame path) ---- */
 enum {
     GSR_BUF_RECORDS = 0, /* 48 B RasterizeData per splat id (gsplat_projection.glsl:42-48), max_splats entries */
@@ -215,6 +220,14 @@ GSR_API int gsr_stream_join(gsr_ctx *ctx);
 GSR_API int gsr_group_export(gsr_ctx *ctx, void *blob /* GSR_GROUP_BLOB_BYTES */);
 GSR_API int gsr_group_attach(gsr_ctx *ctx, int32_t rank, int32_t world, const void *blobs /* world x GSR_GROUP_BLOB_BYTES, rank order */);
 GSR_API int gsr_group_detach(gsr_ctx *ctx);
+/* Where an attached group presents (same value on every rank; default 0):
+ *   0  rows are composited into rank 0's frames over NVLink -- the frame is complete on ONE device (display GPU, gsr_present_device,
+ *      gsr_readback_async on rank 0);
+ *   1  every rank keeps its rows in its own frames and reads them back itself with gsr_readback_rows_async into one full-frame
+ *      RGBA32F host image that is page-locked in every rank's process (shared memory): a host consumer gets the frame over
+ *      world PCIe links instead of one, and no frame data crosses NVLink at all. */
+GSR_API int gsr_group_set_present(gsr_ctx *ctx, int32_t rows_local);
+GSR_API int gsr_readback_rows_async(gsr_ctx *ctx, void *host_frame_rgba32f);
 GSR_API int gsr_sync(gsr_ctx *ctx);
 
 /* Device pointer of the RGBA32F frame (render_texture.texture_rd_rid, rasterizer.gd:48,101); row-major W*H. */
@@ -240,9 +253,9 @@ GSR_API int gsr_debug_copy(gsr_ctx *ctx, int which, void *dst, size_t bytes);
 /* Record, for every work item of the compositor, {tile<<32|SM id, start ns, end ns, first_chunk<<32|chunks<<1|finished}
  * (4 x uint64 per item, %globaltimer).  max_items = 0 disables.  Profiling aid; not on the frame path by default. */
 GSR_API int gsr_debug_enable_trace(gsr_ctx *ctx, uint32_t max_items);
-/* Scheduling of the compositor's persistent grid (results never depend on it): resident CTAs per SM (0 = as many as fit), chunks a
- * fresh tile blends before it yields to the queue, longest-list-first ticket order, resumed tiles run to completion. */
-GSR_API int gsr_debug_compositor_config(gsr_ctx *ctx, int32_t ctas_per_sm, int32_t quantum, int32_t longest_first, int32_t resumed_run_to_completion);
+/* Scheduling of the compositor's persistent grid (results never depend on it): resident CTAs per SM (0 = as many as fit; default 2)
+ * and longest-chain-first ticket order (default on). */
+GSR_API int gsr_debug_compositor_config(gsr_ctx *ctx, int32_t ctas_per_sm, int32_t longest_first);
 /* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
 GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);
 

@@ -56,6 +56,22 @@ def main():
             ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=(40 if boost else 10) * n)
             got = hosts[k].numpy()
             assert np.array_equal(got.view(np.uint32), ref.rgba.view(np.uint32)), f"frame {k} differs from the oracle (max abs {np.abs(got - ref.rgba).max()})"
+        # ---- rows-local presentation: every rank reads its own tile rows back into ONE host frame (a PCIe link per rank) ----
+        for c in ctxs:
+            c.group_set_present(True)
+        hosts2 = [pinned((h, w, 4)) for _ in range(4)]
+        for k in range(4):
+            _, vp, ub = frames[k]
+            for c in ctxs:
+                c.render_async(vp, ub)
+            for c in ctxs:
+                c.readback_rows_async(hosts2[k].data_ptr())
+        for c in ctxs:
+            c.sync()
+        for k in range(4):
+            _, vp, ub = frames[k]
+            ref = orc.frame(splat60, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=(40 if boost else 10) * n)
+            assert np.array_equal(hosts2[k].numpy().view(np.uint32), ref.rgba.view(np.uint32)), f"rows-local frame {k} differs from the oracle"
         print(f"GROUP_INPROCESS_OK G={G}", flush=True)
     finally:
         for c in ctxs:

@@ -85,6 +85,12 @@ class Ctx:
         buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
         _lib.check(self.L.gsr_group_attach(self.h, rank, world, buf), "gsr_group_attach")
 
+    def group_set_present(self, rows_local):
+        _lib.check(self.L.gsr_group_set_present(self.h, int(bool(rows_local))), "gsr_group_set_present")
+
+    def readback_rows_async(self, host_ptr):
+        _lib.check(self.L.gsr_readback_rows_async(self.h, C.c_void_p(host_ptr)), "gsr_readback_rows_async")
+
     def render_async(self, vp, uniforms, heatmap=0.0, host_ptr=None):
         vp = np.ascontiguousarray(vp, dtype=np.float32)
         _lib.check(self.L.gsr_render_async(self.h, vp.ctypes.data_as(C.POINTER(C.c_float)), uniforms, float(heatmap),

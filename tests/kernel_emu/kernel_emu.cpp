@@ -2,6 +2,8 @@
 // compositor.cu) compiled for the CPU.
 // TEST INFRASTRUCTURE: see cuda_shim.h.  Built by tests/kernel_emu/build.py into tests/kernel_emu/libkernel_emu.so.
 #define GSR_CPU_EMU 1
+#include <vector>
+
 #include "cuda_shim.h"
 
 namespace cuda_emu { dim g_block_dim{128, 1, 1}, g_grid_dim{1, 1, 1}; }
@@ -18,30 +20,20 @@ namespace {
 struct Launch { const gsr::CompositeArgs *args; int variant; };
 void body(void *p) {
     const Launch *l = static_cast<const Launch *>(p);
-    switch (l->variant) {
-        case 0: gsr::composite_kernel<false>(*l->args); break;   // the shipped kernel
-        case 1: gsr::composite_v2_kernel<5>(*l->args); break;       // GSR_COMP_V2
-        case 3: gsr::composite_p4_kernel(*l->args); break;       // GSR_COMP_P4 (64 threads)
-        case 4: gsr::composite_v3_kernel<6, false, false>(*l->args); break;   // GSR_COMP_V3: TMA staging, short transmittance chain
-        case 5: gsr::composite_v3_kernel<6, true, false>(*l->args); break;    // ... + F2I/I2F rounding of the exp2 argument
-        case 6: gsr::composite_v3_kernel<4, false, true>(*l->args); break;    // ... software-pipelined blend loop (prefetched group, early liveness vote)
-        default: gsr::composite_kernel<true>(*l->args); break;   // GSR_COMP_HWEXP (exp2f stands in for MUFU.EX2)
-    }
+    if (l->variant == 1) gsr::composite_kernel<false>(*l->args);   // GSR_FLAG_UNCONTRACTED_BLEND
+    else gsr::composite_kernel<true>(*l->args);
 }
 }  // namespace
 
-// One persistent block works through every tile of the launch (fresh tickets first, then its own hand-backs in FIFO order),
-// which exercises the whole item logic: staging, blend, vote, quantum, spill, re-queue, resume.
+// One persistent block works through every tile of the launch in ticket order (natural, or longest-chain-first through
+// tile_order_kernel with or without the previous frame's consumed-chunk hints).
 extern "C" int emu_composite(int variant, const void *records, const uint32_t *values, const uint32_t *bounds, float *out_rgba, int width,
                              int height, int tile_begin, int row_step, int num_tiles, float heatmap_factor, uint32_t target_tile_id,
-                             float *pick4, unsigned long long *staged_out, unsigned *pushes_out, int quantum, int sched_flags) {
+                             float *pick4, unsigned long long *staged_out, uint32_t *hint /* nullable: [num_tiles] in/out */, int sched_flags) {
     const int tiles_x = (width + 15) / 16;
     gsr::FrameState frame;
     memset(&frame, 0, sizeof frame);
     const size_t nt = (size_t)(num_tiles > 0 ? num_tiles : 1);
-    uint32_t *queue = static_cast<uint32_t *>(calloc(nt * GSR_COMP_MAX_PUSHES, sizeof(uint32_t)));
-    float4 *state = static_cast<float4 *>(calloc(nt * 256, sizeof(float4)));
-    uint32_t *state_chunk = static_cast<uint32_t *>(calloc(nt, sizeof(uint32_t)));
     gsr::CompositeArgs a;
     memset(&a, 0, sizeof a);
     a.records = static_cast<const float4 *>(records);
@@ -53,27 +45,26 @@ extern "C" int emu_composite(int variant, const void *records, const uint32_t *v
     a.heatmap_factor = heatmap_factor; a.target_tile_id = target_tile_id;
     a.pick = reinterpret_cast<float4 *>(pick4);
     a.frame = &frame; a.count_staged = 1;
-    a.queue = queue; a.state = state; a.state_chunk = state_chunk;
-    a.quantum = quantum > 0 ? quantum : 2; a.requeue_only_if_fresh = (sched_flags & 2) ? 1 : 0; a.ctas_per_sm = 0;
+    a.consumed = hint; a.ctas_per_sm = 1; a.sm_count = 1; a.contract = variant == 1 ? 0 : 1;
     uint32_t *order = static_cast<uint32_t *>(calloc(nt, sizeof(uint32_t)));
-    if ((sched_flags & 1) && num_tiles > 0) {   // longest-list-first ticket order (csrc/ranges.cu tile_order_kernel, one block of 1024)
-        struct OL { const uint2 *b; int tb, rs, tx, n; uint32_t *o; } ol{a.bounds, tile_begin, row_step, tiles_x, num_tiles, order};
+    if ((sched_flags & 1) && num_tiles > 0) {   // longest-chain-first ticket order (csrc/ranges.cu tile_order_kernel, one block of 1024)
+        struct OL { const uint2 *b; int tb, rs, tx, n; uint32_t *h, *o; } ol{a.bounds, tile_begin, row_step, tiles_x, num_tiles, hint, order};
         cuda_emu::g_block_dim = cuda_emu::dim{1024, 1, 1};
         cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
         glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(1024, 1, 1),
-                            [](void *p) { OL *l = static_cast<OL *>(p); gsr::tile_order_kernel(l->b, l->tb, l->rs, l->tx, l->n, l->o); }, &ol);
+                            [](void *p) { OL *l = static_cast<OL *>(p); gsr::tile_order_kernel(l->b, l->tb, l->rs, l->tx, l->n, l->h, l->o); }, &ol);
         a.order = order;
+        // a permutation of the owned tiles?
+        std::vector<char> seen(nt, 0);
+        for (int k = 0; k < num_tiles; ++k) { if (order[k] >= (uint32_t)num_tiles || seen[order[k]]) { free(order); return 2; } seen[order[k]] = 1; }
     }
     Launch l{&a, variant};
-    const unsigned threads = variant == 3 ? 64u : 128u;
-    cuda_emu::g_block_dim = cuda_emu::dim{threads, 1, 1};
-    if (num_tiles > 0) glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(threads, 1, 1), &body, &l);
     cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
+    if (num_tiles > 0) glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(128, 1, 1), &body, &l);
     if (staged_out) *staged_out = frame.staged;
-    if (pushes_out) *pushes_out = frame.comp_tail;
-    const int ok = (int)frame.comp_done == num_tiles ? 0 : 1;
-    free(queue); free(state); free(state_chunk); free(order);
-    return ok;
+    const int ok = frame.comp_head >= (uint32_t)(num_tiles > 0 ? num_tiles : 0);
+    free(order);
+    return ok ? 0 : 1;
 }
 
 // ---- csrc/ranges.cu: `grid` blocks of 256 threads, run one after another (the kernel has no inter-block dependence) ----

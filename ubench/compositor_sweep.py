@@ -1,6 +1,6 @@
-"""Scheduling sweep of the compositor's persistent grid on c3 frames (and optionally one emulated rank of an 8-GPU group):
-resident CTAs/SM x yield quantum x longest-list-first order x resumed-run-to-completion -- gsr_debug_compositor_config, results never
-depend on it.  One scene upload, many configurations:   [GSR_COMP_V3=6] python ubench/compositor_sweep.py [rows_mod]"""
+"""Scheduling sweep of the compositor's persistent grid on c3 frames (and optionally one emulated rank of a G-GPU group):
+resident CTAs/SM x longest-chain-first ticket order -- gsr_debug_compositor_config, results never depend on it.
+One scene upload, many configurations:   python ubench/compositor_sweep.py [rows_mod]"""
 import os, sys, itertools
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +10,6 @@ from godotgaussiansplatting_b200.camera import default_camera
 from godotgaussiansplatting_b200.ply_file import PlyFile
 from godotgaussiansplatting_b200.rasterizer import GaussianSplattingRasterizer, RenderTexture
 
-mode = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("GSR_COMP_")) or "shipped"
 rows_mod = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 wl = dict(bench.WORKLOADS[os.environ.get("SWEEP_WORKLOAD", "c3")])
 stub = PlyFile(); stub.size = wl["n"]
@@ -23,16 +22,14 @@ if rows_mod > 1:
 frames = bench.frame_params(wl, 40)
 L = _lib.lib()
 res = []
-for ctas, quantum, lpt, pol in itertools.product((0, 3, 2), (2, 4, 1000), (0, 1), (0, 1)):
-    if quantum == 1000 and pol:
-        continue
-    _lib.check(L.gsr_debug_compositor_config(r._ctx, ctas, quantum, lpt, pol), "config")
+for ctas, lpt in itertools.product((0, 4, 3, 2, 1), (0, 1)):
+    _lib.check(L.gsr_debug_compositor_config(r._ctx, ctas, lpt), "config")
     for vp_, ub_ in frames:
         r.render_raw(vp_, ub_, 0.0, None, asynchronous=True)
     r.sync()
     hist = r.frame_history()[-30:]
     ms = np.array([[f.stage_ms[i] for i in range(5)] for f in hist])
-    res.append((ms[:, 3].mean(), ctas, quantum, lpt, pol, ms[:, 4].mean()))
-    print(f"[{mode} rows/{rows_mod}] ctas/SM {ctas or 'max'} quantum {quantum:4d} longest-first {lpt} resumed-complete {pol}: compositor {ms[:, 3].mean():.3f} ms  frame {ms[:, 4].mean():.3f} ms", flush=True)
+    res.append((ms[:, 3].mean(), ctas, lpt, ms[:, 4].mean()))
+    print(f"[rows/{rows_mod}] ctas/SM {ctas or 'max'} longest-first {lpt}: compositor {ms[:, 3].mean():.3f} ms  frame {ms[:, 4].mean():.3f} ms", flush=True)
 best = min(res)
-print(f"[{mode} rows/{rows_mod}] BEST compositor {best[0]:.3f} ms: ctas {best[1]} quantum {best[2]} longest-first {best[3]} resumed-complete {best[4]}")
+print(f"[rows/{rows_mod}] BEST compositor {best[0]:.3f} ms: ctas {best[1]} longest-first {best[2]}")

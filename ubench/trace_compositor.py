@@ -25,3 +25,13 @@ st = r.stats()
 os.makedirs("gpurun_out", exist_ok=True)
 np.save("gpurun_out/trace.npy", tr)
 print("items", n, "render ms", st.stage_ms[3], "C", st.staged)
+# item = {tile << 32 | SM id, start ns, end ns, consumed chunks << 32 | list chunks << 1 | 1}
+t0 = tr[:, 1].astype(np.float64); t1 = tr[:, 2].astype(np.float64)
+cons = (tr[:, 3] >> 32).astype(np.int64)
+busy = cons > 0
+base = t0.min()
+print("span us", (t1.max() - base) / 1e3, "busy tiles", int(busy.sum()), "chunks", int(cons.sum()),
+      "mean us/chunk/CTA", float(((t1 - t0)[busy]).sum() / max(cons.sum(), 1) / 1e3))
+sm = (tr[:, 0] & 0xffffffff).astype(np.int64)
+last = np.array([t1[busy & (sm == s)].max() if (busy & (sm == s)).any() else base for s in np.unique(sm)])
+print("per-SM last busy end us: min/median/max", (last.min() - base) / 1e3, (np.median(last) - base) / 1e3, (last.max() - base) / 1e3)
