@@ -105,7 +105,7 @@ def lib():
         L.gsr_debug_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.gsr_debug_keep_unsorted.argtypes = [vp, C.c_int]
         L.gsr_debug_enable_trace.argtypes = [vp, u32]
-        L.gsr_debug_compositor_config.argtypes = [vp, C.c_int32, C.c_int32]
+        L.gsr_debug_compositor_config.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
         L.gsr_sorter_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp)]
         L.gsr_sorter_destroy.argtypes = [vp]
         L.gsr_sorter_sort_device.argtypes = [vp, vp, vp, C.c_uint64, vp]

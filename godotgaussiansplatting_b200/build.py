@@ -57,5 +57,23 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
     return out or OUT
 
 
+GODOT_DIR = os.path.join(HERE, "godot")
+GODOT_OUT = os.path.join(GODOT_DIR, "libgsr_godot.so")
+
+
+def build_godot_shim(force: bool = False) -> str:
+    """The GDExtension entry (godot/gsr_gdextension.c) -> godot/libgsr_godot.so, linked against the in-tree libgsr.so."""
+    src = os.path.join(GODOT_DIR, "gsr_gdextension.c")
+    deps = [src, os.path.join(GODOT_DIR, "gdextension_min.h"), os.path.join(HERE, "..", "include", "gsr.h"), OUT]
+    if force or not os.path.exists(GODOT_OUT) or any(os.path.getmtime(d) > os.path.getmtime(GODOT_OUT) for d in deps if os.path.exists(d)):
+        cmd = ["/usr/bin/gcc", "-std=gnu11", "-O2", "-Wall", "-Wextra", "-fPIC", "-fvisibility=hidden", "-shared", src, "-o", GODOT_OUT,
+               "-L", HERE, "-lgsr", "-Wl,-rpath,$ORIGIN:$ORIGIN/.."]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("building the GDExtension shim failed")
+    return GODOT_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -125,3 +125,90 @@ def default_camera(aspect: float = 16.0 / 9.0, fov: float = 75.0) -> Camera3D:
     cam.aspect = aspect
     cam.reset()
     return cam
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The application's own orbit (scope row f4): util/camera.gd FreeLookCamera -- set_focused_position (:144-149), the ORBIT
+# branch of _input (:52-60) and the orbit branch of _update_movement (:127-137) once its 0.4 s ease-in is over (t = 1).
+# ---------------------------------------------------------------------------------------------------------------------
+def _rotated(v, axis, angle):
+    """Vector3.rotated(axis, angle): Rodrigues' rotation about a unit axis."""
+    v = np.asarray(v, dtype=np.float64)
+    k = _normalize(axis)
+    c, s = math.cos(angle), math.sin(angle)
+    return v * c + np.cross(k, v) * s + k * np.dot(k, v) * (1.0 - c)
+
+
+class FreeLookCamera(Camera3D):
+    """util/camera.gd: the part that decides where the camera is while the user orbits a picked position.
+    `target` is the $Target node the camera eases towards; in steady state (orbit_time >= 0.4, camera.gd:134) the camera's
+    basis equals the target's and its position is the target position at the camera's current orbit radius."""
+
+    def __init__(self, fov: float = 75.0, aspect: float = 16.0 / 9.0, mouse_sensitivity: float = 0.4):
+        super().__init__(fov=fov)
+        self.aspect = aspect
+        self.mouse_sensitivity = float(mouse_sensitivity)          # camera.gd:5
+        self.target = Camera3D(fov=fov)                             # $Target (a Node3D: only basis + position are used)
+        self.reset()
+
+    def reset(self) -> None:                                        # camera.gd:151-159
+        super().reset()
+        self.orbit_position = np.array([0.0, 0.0, 2.0])             # -Vector3.FORWARD * 2.0
+        self.target.basis = np.eye(3, dtype=np.float32)
+        self.target.global_position = np.zeros(3, dtype=np.float32)
+
+    def set_focused_position(self, target_position) -> None:        # camera.gd:144-149 (main.gd:89-91 calls it with the picked splat)
+        self.orbit_position = np.asarray(target_position, dtype=np.float64)
+        # $Target is top_level (main.tscn:53-54): its position is global -- two units from the focus along the camera's view axis
+        self.target.global_position = (self.orbit_position + self.basis[2].astype(np.float64) * 2.0).astype(np.float32)
+        # :140-141 the camera eases to target.position; then, holding the orbit button, OrbitSwapTimer (:38-43) makes the target look at
+        # the focus from there and the camera eases into the target's orientation (:127-137).  Steady state of both:
+        self.global_position = self.target.global_position.copy()
+        self.target.look_at_from_position(self.global_position.astype(np.float64), self.orbit_position)
+        self.basis = self.target.basis.copy()
+
+    def _target_pitch_deg(self) -> float:
+        """target.rotation_degrees.x: Euler YXZ of a roll-free look-at basis = asin(-basis.z.y)."""
+        return math.degrees(math.asin(max(-1.0, min(1.0, -float(self.target.basis[2][1])))))
+
+    def orbit_mouse_motion(self, relative_x: float, relative_y: float) -> None:
+        """InputEventMouseMotion in RotationMode.ORBIT (camera.gd:52-60), then one _process tick in steady state (:127-137, t = 1)."""
+        off_x, off_y = -relative_x * self.mouse_sensitivity, -relative_y * self.mouse_sensitivity      # :49
+        pitch = self._target_pitch_deg() - off_y                                                       # :53
+        tp = self.target.global_position.astype(np.float64)
+        rotated = tp - self.orbit_position                                                             # :54
+        tb = self.target.basis.astype(np.float64)
+        if -80.0 <= pitch <= 70.0:                                                                     # :55-56
+            rotated = _rotated(rotated, tb[0], math.radians(-off_y))
+        rotated = _rotated(rotated, tb[1], math.radians(-off_x) * math.cos(math.radians(pitch)))      # :57
+        rotated = rotated + self.orbit_position                                                        # :58
+        self.target.look_at_from_position(rotated, self.orbit_position)                                # :59
+        # _update_movement, orbit branch with t = 1: the camera takes the target's orientation and the target's direction
+        # from the orbit position at its own current radius (:129-137)
+        radius = float(np.linalg.norm(self.orbit_position - self.global_position.astype(np.float64)))
+        d = _normalize(self.target.global_position.astype(np.float64) - self.orbit_position)
+        self.basis = self.target.basis.copy()
+        self.global_position = (self.orbit_position + d * radius).astype(np.float32)
+        # :140-141 smooth distance transition towards target.position: in steady state the camera has arrived
+        self.global_position = self.target.global_position.copy()
+
+
+def reference_orbit_sweep(n_frames: int, focus=(0.0, 0.0, 2.5), yaw_step_deg: float = 1.0, start_pitch_deg: float = -10.0, zoom_clicks: int = 2,
+                          fov: float = 75.0, aspect: float = 16.0 / 9.0):
+    """The c3 sweep driven the way the application drives it: focus the camera on `focus` (a picked splat position, main.gd:86-91),
+    then one mouse-motion event per frame whose horizontal movement turns the view by `yaw_step_deg` about the focus
+    (camera.gd:57: the yaw applied is offset.x * cos(pitch), so the event carries yaw_step / (sensitivity * cos(pitch)))."""
+    cam = FreeLookCamera(fov=fov, aspect=aspect)
+    cam.set_focused_position(focus)
+    for _ in range(zoom_clicks):   # MOUSE_BUTTON_WHEEL_DOWN (:76-78): the target backs off the focus by 0.25 per click, the camera follows (:140-141)
+        tp = cam.target.global_position.astype(np.float64)
+        cam.target.global_position = (tp - _normalize(cam.orbit_position - tp) * 0.25).astype(np.float32)
+        cam.global_position = cam.target.global_position.copy()
+    if start_pitch_deg:
+        cam.orbit_mouse_motion(0.0, -start_pitch_deg / cam.mouse_sensitivity * -1.0)   # one vertical drag to the starting pitch
+    out = []
+    for _ in range(n_frames):
+        out.append((cam.get_camera_transform(), cam.get_camera_projection(), cam.global_position.copy()))
+        pitch = cam._target_pitch_deg()
+        cam.orbit_mouse_motion(-yaw_step_deg / (cam.mouse_sensitivity * math.cos(math.radians(pitch))), 0.0)
+    return out

@@ -92,7 +92,8 @@ struct FrameState {
     uint32_t pad0;
     unsigned long long staged;     // C: instances staged by the compositor (sum of consumed chunk sizes)
     uint32_t comp_head;            // compositor: next tile ticket of the persistent grid
-    uint32_t pad[5];
+    uint32_t comp_cta_limit;       // compositor: CTAs that may work (0 = all launched); set by tile_order_kernel for sparse frames
+    uint32_t pad[4];
 };
 static_assert(sizeof(FrameState) == 64, "FrameState is one 64-byte slot of the history ring");
 
@@ -227,8 +228,10 @@ int composite_max_ctas_per_sm(int *out);
 // order[0 .. num_tiles) = owned-tile indices sorted by descending expected chain length: the chunk count the tile consumed in the
 // previous frame (hint[k] with bit 31 set; the bit is cleared here) or, without a hint, its list length in chunks capped at
 // `cap_chunks` (a list is rarely consumed beyond ~20 chunks).  Counting sort, one CTA.  Scheduling only: pixels do not depend on it.
+// Sparse frames: when at most `sparse_tiles` owned tiles are occupied, frame->comp_cta_limit = sparse_cta_limit (one CTA per SM:
+// a chain that has an SM to itself advances fastest); otherwise 0 = every launched CTA works.
 int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *hint, uint32_t *order,
-                      cudaStream_t stream);
+                      FrameState *frame, uint32_t sparse_tiles, uint32_t sparse_cta_limit, cudaStream_t stream);
 
 int launch_ply_to_soa(const float *ply, uint32_t nprops, uint64_t count, float creation_time, float4 *soa, uint64_t plane_stride, uint64_t first,
                       cudaStream_t stream);

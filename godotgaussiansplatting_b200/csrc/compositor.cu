@@ -221,6 +221,10 @@ __global__ void __launch_bounds__(THREADS, GSR_COMP_MIN_BLOCKS) composite_kernel
     __shared__ uint32_t s_tile;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    {   // sparse frame: only the first `comp_cta_limit` CTAs (one per SM: the block scheduler deals a fresh grid breadth-first) work
+        const uint32_t limit = p.frame->comp_cta_limit;
+        if (limit && blockIdx.x >= limit) return;
+    }
     const BlendK K = make_blend_k();
     uint32_t staged = 0;  // SURVEY 8 symbol C, summed over the tiles this CTA processed (uniform across the CTA)
     unsigned long long t_start = 0;  // trace only

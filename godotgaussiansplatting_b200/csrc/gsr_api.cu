@@ -46,7 +46,7 @@ struct gsr_ctx {
     uint64_t frame_counter = 0;
     uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
     uint32_t *comp_order = nullptr, *comp_hint = nullptr;   // longest-chain-first ticket order of the compositor + last frame's consumed chunks
-    int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
+    int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1, comp_sparse_per_sm = 3;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
     uint64_t comp_hint_key = 0;   // ownership (band, rows) the hints were recorded under: a change invalidates them
     FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
     ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
@@ -583,7 +583,8 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
         if (key != c->comp_hint_key) { GSR_CUDA_TRY(cudaMemsetAsync(c->comp_hint, 0, sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y, s)); c->comp_hint_key = key; }
     }
     if (c->comp_order_mode && ca.num_tiles > 0) {   // longest chains first: the long sequential chains start at once instead of in the tail
-        if ((rc = launch_tile_order(c->bounds, ca.tile_begin, ca.row_step, ca.tiles_x, ca.num_tiles, c->comp_hint, c->comp_order, s))) return rc;
+        if ((rc = launch_tile_order(c->bounds, ca.tile_begin, ca.row_step, ca.tiles_x, ca.num_tiles, c->comp_hint, c->comp_order, c->frame,
+                                    (uint32_t)(c->comp_sparse_per_sm * c->sm_count), (uint32_t)c->sm_count, s))) return rc;
         ca.order = c->comp_order;
         launches += 1;
     }
@@ -1059,9 +1060,9 @@ GSR_API int gsr_debug_keep_unsorted(gsr_ctx *c, int enable) {
     return GSR_OK;
 }
 
-GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t longest_first) {
-    if (!c || ctas_per_sm < 0) return GSR_ERR_INVALID;
-    c->comp_ctas_per_sm = ctas_per_sm ? ctas_per_sm : c->comp_max_ctas; c->comp_order_mode = longest_first != 0;
+GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t longest_first, int32_t sparse_tiles_per_sm) {
+    if (!c || ctas_per_sm < 0 || sparse_tiles_per_sm < 0) return GSR_ERR_INVALID;
+    c->comp_ctas_per_sm = ctas_per_sm ? ctas_per_sm : c->comp_max_ctas; c->comp_order_mode = longest_first != 0; c->comp_sparse_per_sm = sparse_tiles_per_sm;
     return GSR_OK;
 }
 

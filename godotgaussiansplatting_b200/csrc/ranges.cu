@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) band_fixup_kernel(const int32_t *__restri
 // Owned tile k <-> tile id exactly as in the compositor.
 constexpr uint32_t ORDER_BINS = 64, ORDER_NO_HINT_CAP = 24;
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2 *__restrict__ bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x,
-                                                          int32_t num_tiles, uint32_t *__restrict__ hint, uint32_t *__restrict__ order) {
+                                                          int32_t num_tiles, uint32_t *__restrict__ hint, uint32_t *__restrict__ order,
+                                                          FrameState *__restrict__ frame, uint32_t sparse_tiles, uint32_t sparse_cta_limit) {
     __shared__ uint32_t s_hist[ORDER_BINS], s_base[ORDER_BINS];
     const uint32_t tid = threadIdx.x;
     if (tid < ORDER_BINS) s_hist[tid] = 0u;
@@ -95,6 +96,8 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2 *__restric
     if (tid == 0) {   // 64 bins: a serial descending scan is cheaper than a barrier tree
         uint32_t acc = 0u;
         for (int b = (int)ORDER_BINS - 1; b >= 0; --b) { s_base[b] = acc; acc += s_hist[b]; }
+        // few chains (a sparse view, one rank's share of a multi-GPU frame): let each have an SM to itself
+        if (frame) frame->comp_cta_limit = ((uint32_t)num_tiles - s_hist[0] <= sparse_tiles) ? sparse_cta_limit : 0u;
     }
     __syncthreads();
     for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) order[atomicAdd(&s_base[bin_of(k)], 1u)] = (uint32_t)k;
@@ -115,9 +118,9 @@ int preload_ranges_kernels() {
 }
 
 int launch_tile_order(const uint2 *bounds, int32_t tile_begin, int32_t row_step, int32_t tiles_x, int32_t num_tiles, uint32_t *hint, uint32_t *order,
-                      cudaStream_t stream) {
+                      FrameState *frame, uint32_t sparse_tiles, uint32_t sparse_cta_limit, cudaStream_t stream) {
     if (num_tiles <= 0) return GSR_OK;
-    tile_order_kernel<<<1, 1024, 0, stream>>>(bounds, tile_begin, row_step, tiles_x, num_tiles, hint, order);
+    tile_order_kernel<<<1, 1024, 0, stream>>>(bounds, tile_begin, row_step, tiles_x, num_tiles, hint, order, frame, sparse_tiles, sparse_cta_limit);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }

@@ -48,11 +48,11 @@ extern "C" int emu_composite(int variant, const void *records, const uint32_t *v
     a.consumed = hint; a.ctas_per_sm = 1; a.sm_count = 1; a.contract = variant == 1 ? 0 : 1;
     uint32_t *order = static_cast<uint32_t *>(calloc(nt, sizeof(uint32_t)));
     if ((sched_flags & 1) && num_tiles > 0) {   // longest-chain-first ticket order (csrc/ranges.cu tile_order_kernel, one block of 1024)
-        struct OL { const uint2 *b; int tb, rs, tx, n; uint32_t *h, *o; } ol{a.bounds, tile_begin, row_step, tiles_x, num_tiles, hint, order};
+        struct OL { const uint2 *b; int tb, rs, tx, n; uint32_t *h, *o; gsr::FrameState *f; } ol{a.bounds, tile_begin, row_step, tiles_x, num_tiles, hint, order, &frame};
         cuda_emu::g_block_dim = cuda_emu::dim{1024, 1, 1};
         cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
         glsl::run_workgroup(glsl::uvec3(0, 0, 0), glsl::uvec3(1024, 1, 1),
-                            [](void *p) { OL *l = static_cast<OL *>(p); gsr::tile_order_kernel(l->b, l->tb, l->rs, l->tx, l->n, l->h, l->o); }, &ol);
+                            [](void *p) { OL *l = static_cast<OL *>(p); gsr::tile_order_kernel(l->b, l->tb, l->rs, l->tx, l->n, l->h, l->o, l->f, 3u, 1u); }, &ol);
         a.order = order;
         // a permutation of the owned tiles?
         std::vector<char> seen(nt, 0);

@@ -156,3 +156,32 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     ref = cb["reference_shaders"]       # the reference's own shaders on a bounded sample (oracle/_ref), when available
     assert "unavailable" in ref or (ref["kind"] == "reference" and ref["keys_and_ranges_identical_to_port"])
+
+
+def test_free_look_camera_orbits_like_util_camera_gd():
+    """Scope row f4: FreeLookCamera restates util/camera.gd's orbit (set_focused_position :144-149, ORBIT mouse motion :52-60, the
+    t = 1 steady state of _update_movement :127-141): the camera stays on a sphere about the focused position, always looks at it,
+    turns by offset.x * cos(pitch) about the target's own y axis per event, and refuses pitches outside [-80, 70] degrees."""
+    from godotgaussiansplatting_b200 import camera as cam
+    focus = np.array([0.3, -0.2, 2.5])
+    c = cam.FreeLookCamera()
+    c.set_focused_position(focus)
+    np.testing.assert_allclose(np.linalg.norm(c.global_position - focus), 2.0, atol=1e-6)        # :147 two units along the view axis
+    for k in range(200):
+        c.orbit_mouse_motion(7.0, -1.5 if k < 40 else 0.3)
+        p = c.global_position.astype(np.float64)
+        np.testing.assert_allclose(np.linalg.norm(p - focus), 2.0, atol=2e-5)
+        view = -c.basis[2].astype(np.float64)
+        np.testing.assert_allclose(view, (focus - p) / np.linalg.norm(focus - p), atol=2e-5)       # look_at_from_position(rotated, orbit_position)
+        assert -80.5 <= c._target_pitch_deg() <= 70.5
+    c2 = cam.FreeLookCamera()
+    c2.set_focused_position(focus)
+    for _ in range(400):
+        c2.orbit_mouse_motion(0.0, -5.0)    # keep dragging up: the pitch guard of :55 stops the rotation, the camera never flips
+    assert 69.0 <= c2._target_pitch_deg() <= 70.5 or -80.5 <= c2._target_pitch_deg() <= -79.0
+    sweep = cam.reference_orbit_sweep(360, focus=(0.0, 0.0, 2.5))
+    pos = np.array([p for _, _, p in sweep], dtype=np.float64)
+    ang = np.unwrap(np.arctan2(pos[:, 0], -(pos[:, 2] - 2.5)))
+    assert 355.0 <= np.degrees(ang[-1] - ang[0]) * 360.0 / 359.0 <= 370.0                            # one turn of the orbit
+    vp = cam.pack_camera_push_constants(sweep[5][0], sweep[5][1])
+    assert vp.shape == (32,) and np.isfinite(vp).all()

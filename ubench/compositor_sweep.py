@@ -22,14 +22,14 @@ if rows_mod > 1:
 frames = bench.frame_params(wl, 40)
 L = _lib.lib()
 res = []
-for ctas, lpt in itertools.product((0, 4, 3, 2, 1), (0, 1)):
-    _lib.check(L.gsr_debug_compositor_config(r._ctx, ctas, lpt), "config")
+for ctas, lpt, sparse in [(2, 1, 3), (2, 1, 0), (2, 0, 0), (1, 1, 0), (1, 0, 0), (3, 1, 0), (0, 0, 0)]:
+    _lib.check(L.gsr_debug_compositor_config(r._ctx, ctas, lpt, sparse), "config")
     for vp_, ub_ in frames:
         r.render_raw(vp_, ub_, 0.0, None, asynchronous=True)
     r.sync()
     hist = r.frame_history()[-30:]
     ms = np.array([[f.stage_ms[i] for i in range(5)] for f in hist])
-    res.append((ms[:, 3].mean(), ctas, lpt, ms[:, 4].mean()))
-    print(f"[rows/{rows_mod}] ctas/SM {ctas or 'max'} longest-first {lpt}: compositor {ms[:, 3].mean():.3f} ms  frame {ms[:, 4].mean():.3f} ms", flush=True)
+    res.append((ms[:, 3].mean(), ctas, lpt, sparse, ms[:, 4].mean()))
+    print(f"[rows/{rows_mod}] ctas/SM {ctas or 'max'} longest-first {lpt} sparse-rule {sparse}: compositor {ms[:, 3].mean():.3f} ms  frame {ms[:, 4].mean():.3f} ms", flush=True)
 best = min(res)
-print(f"[rows/{rows_mod}] BEST compositor {best[0]:.3f} ms: ctas {best[1]} longest-first {best[2]}")
+print(f"[rows/{rows_mod}] BEST compositor {best[0]:.3f} ms: ctas {best[1]} longest-first {best[2]} sparse-rule {best[3]}")
