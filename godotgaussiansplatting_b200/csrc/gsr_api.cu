@@ -83,6 +83,7 @@ struct gsr_ctx {
         float4 *root_fb[2] = {nullptr, nullptr};  // the presenting rank's two frames
         void *opened[3 * GROUP_MAX] = {};    // IPC mappings to close
         int n_opened = 0;
+        int split_cull_from = 4;          // ranks from which the per-frame cull is split across the group (below: replicated cull)
         int present_rows = 0;             // 1: every rank keeps its rows in its own frames and reads them back itself (gsr_group_set_present)
         uint32_t seq = 0;                 // frames rendered by the group so far (lockstep on all ranks)
         uint64_t slice = 0;               // splats per rank (256-aligned)
@@ -519,13 +520,15 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.fast_mode = fast ? 1 : 0;
     // full frame: 12 of 32 lanes (below that, per-lane 128-bit gathers move fewer bytes); sharded: few lanes of a warp land in
     // this rank's rows and the latency-bound gather path was measured slower than fetching the whole 6 KB slice (0.60 vs 0.46 ms)
-    pa.sh_bulk_min = fast ? 1 : 12;
+    pa.sh_bulk_min = (fast || c->row_mod > 1) ? 1 : 12;
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
     pa.extents = nullptr;
-    if (gf) {
+    if (gf && c->grp.world >= c->grp.split_cull_from) {
         // group mode: this rank culls ITS slice of the splats and stores the tile-row extents into every rank's table (peer
-        // stores over NVLink), waits for the other slices, then runs the projection maths only for the splats whose rows it owns
+        // stores over NVLink), waits for the other slices, then runs the projection maths only for the splats whose rows it owns.
+        // (Small groups cull every splat on every rank instead -- measured: with 2 ranks ~65 % of the splats own a row here and the
+        // table-mode gathers cost more than the replicated cull saves; the last occupied tile is then known locally, exactly.)
         const uint64_t first = (uint64_t)c->grp.rank * c->grp.slice;
         const uint64_t count = first < c->max_splats ? ((c->max_splats - first) < c->grp.slice ? (c->max_splats - first) : c->grp.slice) : 0;
         pa.band_y0 = 0; pa.band_y1 = c->tiles_y; pa.fast_reject = 0; pa.fast_mode = 0;
