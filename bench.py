@@ -439,20 +439,20 @@ def main():
     if group and args.present == "rows":
         # rows-local presentation: the two host frames live in shared memory, page-locked in EVERY rank's process; each rank copies
         # its own tile rows over its own PCIe link (no frame data on NVLink, one eighth of the frame per link at 8 GPUs)
-        names = [None, None]
+        shm_names = [None, None]
         if rank == 0:
-            names = [f"/dev/shm/gsr_bench_{os.getpid()}_{k}" for k in range(2)]
-            for nm in names:
+            shm_names = [f"/dev/shm/gsr_bench_{os.getpid()}_{k}" for k in range(2)]
+            for nm in shm_names:
                 with open(nm, "wb") as f:
                     f.truncate(H * W * 16)
-        dist.broadcast_object_list(names, src=0)
-        shared2 = [torch.from_file(nm, shared=True, size=H * W * 4, dtype=torch.float32).view(H, W, 4) for nm in names]
+        dist.broadcast_object_list(shm_names, src=0)
+        shared2 = [torch.from_file(nm, shared=True, size=H * W * 4, dtype=torch.float32).view(H, W, 4) for nm in shm_names]
         for t in shared2:
             err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
             assert int(err) == 0, f"cudaHostRegister -> {err}"
         dist.barrier()
         if rank == 0:
-            for nm in names:
+            for nm in shm_names:
                 os.unlink(nm)
     can_pack_rgb = world == 1 or peer or group  # optional RGB32F read-back (alpha == 1.0 stays on the device), reported beside the RGBA headline
     pinned = pinned2[0] if rank == 0 else None
@@ -486,6 +486,8 @@ def main():
             if e2e and rank == 0:
                 pinned.copy_(fb[:H], non_blocking=True)
 
+    host_enqueue_ms = {}
+
     def timed(e2e):
         if group and shared2 is not None:   # RGBA e2e: rows stay local and are read back by their owners; otherwise: frame on rank 0
             torch.cuda.synchronize(); dist.barrier()
@@ -499,8 +501,10 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        t_host = time.perf_counter()
         for i in range(args.warmup, args.warmup + args.steps):
             step(i, e2e)
+        host_enqueue_ms[str(e2e)] = (time.perf_counter() - t_host) * 1e3 / args.steps   # CPU time spent enqueueing one step (a blocking call shows here)
         if e2e and (world == 1 or ((peer or group) and rank == 0) or (group and shared2 is not None)):
             rast.stream_join()  # the timed region ends when the last frame has landed in host memory
         e1.record(stream)
@@ -519,6 +523,7 @@ def main():
     hist = rast.frame_history(min(args.steps, 512))
     st = rast.stats()
     e2e_ms = timed(e2e="rgba")
+    hist_e2e = rast.frame_history(min(args.steps, 512))   # the same per-stage GPU timestamps while frames are being read back
     e2e_rgb_ms = timed(e2e="rgb") if can_pack_rgb else None
 
     ms_per_step = total_ms / args.steps
@@ -642,6 +647,8 @@ def main():
             "run_info": {"duplicates_M": M, "visible_V": V, "staged_C": Cc, "scene_build_s": t_gen},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),
                     "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * 16,
+                    "stage_ms": {nm: float(np.mean([r.stage_ms[i] for r in hist_e2e])) for i, nm in enumerate(names)},
+                    "host_enqueue_ms_per_step": host_enqueue_ms,
                     "path": "gsr_render_async(ctx, view_proj, uniforms, pinned host RGBA32F) per frame -- the frame the reference's RGBA32F texture holds (rasterizer.gd:92); 160 B of camera constants in, full frame out; read-back of frame i overlaps frame i+1 (two device + two host frames); timed region ends after the last frame landed on the host",
                     "rgb32f_packed": None if e2e_rgb_ms is None else {
                         "value": N / 1e6 * 1000.0 / (e2e_rgb_ms / args.steps), "fps": 1000.0 / (e2e_rgb_ms / args.steps), "d2h_bytes_per_step": P * 12,

@@ -154,10 +154,6 @@ struct ProjectionArgs {
     uint32_t capacity;
     unsigned long long *lookback;  // one word per projection CTA (256 splats)
     FrameState *frame;
-    // group mode (gsr_group_attach): tile-row extent of every splat's un-banded rect, y0 | y1 << 16 (0 = not visible), computed
-    // once per frame by ONE rank per splat slice (launch_extents, peer stores into every rank's table); a rank then runs the
-    // projection maths only for the splats whose rows it owns instead of culling all N itself.  nullptr = off.
-    const uint32_t *extents;
 };
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
 
@@ -167,26 +163,48 @@ int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
 constexpr int GROUP_MAX = 16;                                   // ranks per group (one NVSwitch domain)
 #define GSR_GROUP_TIMEOUT_NS 10000000000ull                     // every device-side wait gives up after 10 s
 struct GroupFlags {                                             // offset 0 of a rank's arena; written by the peers over NVLink
-    unsigned long long meta[2][GROUP_MAX];  // [frame parity][source rank] = seq << 32 | (last tile of the source's slice + 1)
+    // [frame parity][source rank][0] = seq << 32 | pairs the source sent to THIS rank's receive segment,
+    //                            [1] = seq << 32 | (largest tile id touched by the source's splats + 1)
+    unsigned long long seg_meta[2][GROUP_MAX][2];
     uint32_t done[GROUP_MAX];               // presenting rank: done[r] = seq of the newest frame whose rows from rank r have landed
     uint32_t released;                      // set by the presenting rank: frames with seq <= released no longer need their slot
-    uint32_t error;                         // local: a wait timed out (1 = extents, 2 = done / released)
-    uint32_t ext_ticket;                    // local: CTAs of the extent kernel that have finished
-    int32_t ext_last;                       // local: atomicMax target, last tile + 1 over this rank's slice
+    uint32_t error;                         // local: a wait timed out (1 = segments of a peer, 2 = done / released)
+    uint32_t scat_ticket;                   // local: CTAs of the scatter projection that have finished
+    int32_t scat_last;                      // local: atomicMax target, last tile + 1 over this rank's slice
+    unsigned long long seg_total[GROUP_MAX];  // local: pairs this rank sent to each destination this frame (scan total)
+    uint32_t seg_prefix[GROUP_MAX + 1];     // local: exclusive prefix of the received (clamped) segment lengths, [world] = M of this rank
 };
 constexpr size_t GROUP_FLAGS_BYTES = 4096;                      // the two extent tables follow the flag page
 static_assert(sizeof(GroupFlags) <= GROUP_FLAGS_BYTES, "flag page");
 struct GroupPeers {                                             // the same pointers on every rank, indexed by rank
     GroupFlags *flags[GROUP_MAX];
-    uint32_t *table[GROUP_MAX];                                 // extent table of the CURRENT frame parity in rank r's arena
     int world, rank;
 };
-// extents of splats [first, first+count) of the frame described by `a` (band / row ownership of `a` are ignored), stored into
-// EVERY rank's table (peer stores); the last CTA then publishes seq | last tile to every rank's meta[parity][rank].
-int launch_extents(const ProjectionArgs &a, uint32_t first, uint32_t count, const GroupPeers &peers, int parity, uint32_t seq, cudaStream_t stream);
+// What the scatter projection of one rank needs to know about the group: every destination's record table and receive segment
+// (peer pointers) of the current frame parity, and this rank's slice of the splats.
+struct ScatterPeers {
+    int world, rank, parity;
+    uint32_t seq;
+    uint32_t first, count;                  // this rank projects splats [first, first + count)
+    uint32_t seg_cap;                       // pairs one source may send to one destination per frame
+    float4 *records[GROUP_MAX];             // destination d's record table (3 float4 per splat id) of this parity
+    uint32_t *keys[GROUP_MAX];              // destination d's receive segment for THIS source: pairs land at [0, seg_cap)
+    uint32_t *values[GROUP_MAX];
+    GroupFlags *flags[GROUP_MAX];
+    unsigned long long *lookback;           // [blocks][world] scan links of this launch (zeroed)
+};
+// Projection sharded by SPLATS (group mode): rank r projects its slice with the full-frame maths of projection_kernel and emits every
+// (key, value) pair and every record straight into the memory of the rank that owns the pair's tile row (row % world), in splat-id
+// order per destination -- the all-to-all of SURVEY 8e's "alternative" fused into the kernel as peer stores over NVLink.
+int launch_projection_scatter(const ProjectionArgs &a, const ScatterPeers &sp, cudaStream_t stream);
+uint32_t projection_scatter_blocks(uint32_t count);
+// destination side: wait for every source's segment of this frame, publish M / overflow / the frame-global last tile, then pack the
+// world receive segments into the contiguous sort input (source-rank order = splat-id order)
+int launch_group_wait_segments(GroupFlags *flags, int parity, int world, uint32_t seq, uint32_t seg_cap, uint32_t capacity, FrameState *frame, cudaStream_t stream);
+int launch_gather_segments(const GroupFlags *flags, int world, uint32_t seg_cap, const uint32_t *rx_keys, const uint32_t *rx_vals, uint32_t *keys, uint32_t *vals,
+                           int grid, cudaStream_t stream);
 // 64-byte FrameState -> mapped pinned host memory with system-scope stores (no copy engine involved)
 int launch_publish_frame_state(const FrameState *frame, FrameState *host_mapped, cudaStream_t stream);
-int launch_group_wait_extents(GroupFlags *flags, int parity, int world, uint32_t seq, FrameState *frame, cudaStream_t stream);
 int launch_group_wait_released(GroupFlags *flags, uint32_t need, cudaStream_t stream);
 int launch_group_wait_done(GroupFlags *flags, int world, uint32_t seq, cudaStream_t stream);
 int launch_group_signal_done(const GroupPeers &peers, int root, int rank, uint32_t seq, cudaStream_t stream);

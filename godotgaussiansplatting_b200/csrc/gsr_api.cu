@@ -46,7 +46,7 @@ struct gsr_ctx {
     uint64_t frame_counter = 0;
     uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
     uint32_t *comp_order = nullptr, *comp_hint = nullptr;   // longest-chain-first ticket order of the compositor + last frame's consumed chunks
-    int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1, comp_sparse_per_sm = 3;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
+    int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1, comp_sparse_per_sm = 5;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
     uint64_t comp_hint_key = 0;   // ownership (band, rows) the hints were recorded under: a change invalidates them
     FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
     ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
@@ -75,18 +75,19 @@ struct gsr_ctx {
     int32_t *sync_word = nullptr;   // local (then all-reduced) last occupied tile + 1
     // multi-GPU shard group (gsr_group_export / gsr_group_attach): NCCL-free frame path, see group.cu
     struct Group {
-        void *arena = nullptr;            // this rank's arena: flag page + two extent tables
-        uint64_t table_entries = 0;       // entries per table
+        void *arena = nullptr;            // this rank's arena: flag page | receive segments (2 parities x keys, values) | records (2 parities)
+        uint64_t rx_capacity = 0;         // pairs per receive buffer (all sources together); seg_cap = rx_capacity / world
         int rank = 0, world = 0;          // world > 1 <=> attached
-        GroupFlags *flags[GROUP_MAX] = {};   // every rank's flag page (peer pointers)
-        uint32_t *table[2][GROUP_MAX] = {};  // every rank's two extent tables
+        char *peer_arena[GROUP_MAX] = {};    // every rank's arena (peer pointers)
+        GroupFlags *flags[GROUP_MAX] = {};   // every rank's flag page
         float4 *root_fb[2] = {nullptr, nullptr};  // the presenting rank's two frames
         void *opened[3 * GROUP_MAX] = {};    // IPC mappings to close
         int n_opened = 0;
-        int split_cull_from = 4;          // ranks from which the per-frame cull is split across the group (below: replicated cull)
         int present_rows = 0;             // 1: every rank keeps its rows in its own frames and reads them back itself (gsr_group_set_present)
         uint32_t seq = 0;                 // frames rendered by the group so far (lockstep on all ranks)
         uint64_t slice = 0;               // splats per rank (256-aligned)
+        uint32_t seg_cap = 0;             // pairs one source may send to one destination per frame
+        float4 *records_cur = nullptr;    // record table (of this rank's arena) the most recent frame composited from
     } grp;
     cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
     // dynamic duplicate capacity (replaces the reference's static 10 x N, rasterizer.gd:79 "FIXME: This should not be a static
@@ -245,7 +246,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     TRY_ALLOC(c->vals, sizeof(uint32_t) * 2ull * c->capacity);
     c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats);  // one scan link per CTA
     TRY_ALLOC(c->ring, sizeof(FrameState) * GSR_HISTORY_FRAMES);
-    TRY_ALLOC(c->lookback, sizeof(unsigned long long) * (size_t)c->lookback_blocks);
+    TRY_ALLOC(c->lookback, sizeof(unsigned long long) * ((size_t)c->lookback_blocks + 2u * GROUP_MAX * GROUP_MAX));  // scatter mode: (N/G/256 + 1) x G links
     c->frame = c->ring;
     TRY_ALLOC(c->pick, sizeof(float4));
     TRY_ALLOC(c->sync_word, sizeof(int32_t));
@@ -470,11 +471,18 @@ static int track_capacity(gsr_ctx *c) {
 
 struct GroupFrame { uint32_t seq; int parity; int rows_local; };
 
+// arena layout (identical on every rank of a group: same max_splats, same rx_capacity)
+static size_t arena_rx_keys_off(uint64_t cap, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * (size_t)parity; }
+static size_t arena_rx_vals_off(uint64_t cap, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * (size_t)(2 + parity); }
+static size_t arena_records_off(uint64_t cap, uint64_t max_splats, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * 4 + sizeof(float4) * 3ull * max_splats * (size_t)parity; }
+static size_t arena_bytes(uint64_t cap, uint64_t max_splats) { return arena_records_off(cap, max_splats, 2); }
+
 static GroupPeers group_peers(const gsr_ctx *c, int parity) {
+    (void)parity;
     GroupPeers p;
     memset(&p, 0, sizeof p);
     p.world = c->grp.world; p.rank = c->grp.rank;
-    for (int r = 0; r < c->grp.world; ++r) { p.flags[r] = c->grp.flags[r]; p.table[r] = c->grp.table[parity][r]; }
+    for (int r = 0; r < c->grp.world; ++r) p.flags[r] = c->grp.flags[r];
     return p;
 }
 
@@ -523,23 +531,42 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     pa.sh_bulk_min = (fast || c->row_mod > 1) ? 1 : 12;
     pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
-    pa.extents = nullptr;
-    if (gf && c->grp.world >= c->grp.split_cull_from) {
-        // group mode: this rank culls ITS slice of the splats and stores the tile-row extents into every rank's table (peer
-        // stores over NVLink), waits for the other slices, then runs the projection maths only for the splats whose rows it owns.
-        // (Small groups cull every splat on every rank instead -- measured: with 2 ranks ~65 % of the splats own a row here and the
-        // table-mode gathers cost more than the replicated cull saves; the last occupied tile is then known locally, exactly.)
+    float4 *records = c->records;
+    if (gf) {
+        // group mode: the projection is sharded by SPLATS.  This rank projects its slice and stores every pair and record into the
+        // memory of the rank that owns it (peer stores over NVLink); then it waits for the other sources' flags and packs what it
+        // received -- its own rows' pairs of ALL splats, in splat-id order -- into the sort input.
+        const int G = c->grp.world;
+        ScatterPeers sp;
+        memset(&sp, 0, sizeof sp);
+        sp.world = G; sp.rank = c->grp.rank; sp.parity = gf->parity; sp.seq = gf->seq;
         const uint64_t first = (uint64_t)c->grp.rank * c->grp.slice;
-        const uint64_t count = first < c->max_splats ? ((c->max_splats - first) < c->grp.slice ? (c->max_splats - first) : c->grp.slice) : 0;
-        pa.band_y0 = 0; pa.band_y1 = c->tiles_y; pa.fast_reject = 0; pa.fast_mode = 0;
-        if ((rc = launch_extents(pa, (uint32_t)first, (uint32_t)count, group_peers(c, gf->parity), gf->parity, gf->seq, s))) return rc;
-        if ((rc = launch_group_wait_extents(c->grp.flags[c->grp.rank], gf->parity, c->grp.world, gf->seq, c->frame, s))) return rc;
-        pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
-        pa.extents = c->grp.table[gf->parity][c->grp.rank];
-        launches += 2;
+        sp.first = (uint32_t)(first < c->max_splats ? first : c->max_splats);
+        sp.count = (uint32_t)(first < c->max_splats ? ((c->max_splats - first) < c->grp.slice ? (c->max_splats - first) : c->grp.slice) : 0);
+        sp.seg_cap = c->grp.seg_cap;
+        for (int d = 0; d < G; ++d) {
+            char *ar = c->grp.peer_arena[d];
+            sp.records[d] = reinterpret_cast<float4 *>(ar + arena_records_off(c->grp.rx_capacity, c->max_splats, gf->parity));
+            sp.keys[d] = reinterpret_cast<uint32_t *>(ar + arena_rx_keys_off(c->grp.rx_capacity, gf->parity)) + (size_t)c->grp.rank * c->grp.seg_cap;
+            sp.values[d] = reinterpret_cast<uint32_t *>(ar + arena_rx_vals_off(c->grp.rx_capacity, gf->parity)) + (size_t)c->grp.rank * c->grp.seg_cap;
+            sp.flags[d] = c->grp.flags[d];
+        }
+        sp.lookback = c->lookback;
+        GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * (size_t)projection_scatter_blocks(sp.count) * G, s));
+        if ((rc = launch_projection_scatter(pa, sp, s))) return rc;
+        char *mine = c->grp.peer_arena[c->grp.rank];
+        if ((rc = launch_group_wait_segments(c->grp.flags[c->grp.rank], gf->parity, G, gf->seq, c->grp.seg_cap, (uint32_t)c->capacity, c->frame, s))) return rc;
+        if ((rc = launch_gather_segments(c->grp.flags[c->grp.rank], G, c->grp.seg_cap,
+                                         reinterpret_cast<const uint32_t *>(mine + arena_rx_keys_off(c->grp.rx_capacity, gf->parity)),
+                                         reinterpret_cast<const uint32_t *>(mine + arena_rx_vals_off(c->grp.rx_capacity, gf->parity)), c->keys, c->vals,
+                                         c->sm_count * 8, s))) return rc;
+        records = reinterpret_cast<float4 *>(mine + arena_records_off(c->grp.rx_capacity, c->max_splats, gf->parity));
+        c->grp.records_cur = records;
+        launches += 3;
+    } else {
+        if ((rc = launch_projection(pa, s))) return rc;
+        launches += pa.num_splats ? 1 : 0;
     }
-    if ((rc = launch_projection(pa, s))) return rc;
-    launches += pa.num_splats ? 1 : 0;
     GSR_CUDA_TRY(cudaEventRecord(ev[1], s));  // 'Projection'
 
     if (c->keep_unsorted) {
@@ -565,7 +592,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
         if (c->copied_valid[i] && owned == out_fb) GSR_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_copied[i], 0));
     }
     c->fb_last = out_fb;
-    ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = out_fb;
+    ca.records = records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = out_fb;
     ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
     {   // owned tile rows: band rows with row % row_mod == row_rem
         int first = c->band_y0 + ((c->row_rem - c->band_y0 % c->row_mod) + c->row_mod) % c->row_mod;
@@ -826,7 +853,7 @@ struct GroupBlob {   // what gsr_group_export hands to the other ranks (any tran
     uint32_t magic, version;
     uint64_t pid;
     int32_t device, width, height, pad;
-    uint64_t max_splats, table_entries;
+    uint64_t max_splats, rx_capacity;
     void *arena, *fb[2];
     cudaIpcMemHandle_t h_arena, h_fb[2];
     unsigned char reserved[GSR_GROUP_BLOB_BYTES - 264];
@@ -842,8 +869,8 @@ GSR_API int gsr_group_export(gsr_ctx *c, void *blob) {
     int rc = use_device(c->device);
     if (rc) return rc;
     if (!c->grp.arena) {
-        c->grp.table_entries = ((c->max_splats + 255ull) & ~255ull) + 256ull * GROUP_MAX;   // any world's 256-aligned slices fit
-        const size_t bytes = GROUP_FLAGS_BYTES + 2ull * sizeof(uint32_t) * c->grp.table_entries;
+        c->grp.rx_capacity = c->capacity;   // the receive segments of all sources together hold as many pairs as one sort input
+        const size_t bytes = arena_bytes(c->grp.rx_capacity, c->max_splats);
         cudaError_t e = cudaMalloc(&c->grp.arena, bytes);
         if (e != cudaSuccess) { set_last_error("cudaMalloc(group arena, %zu B) -> %s", bytes, cudaGetErrorString(e)); c->grp.arena = nullptr; return GSR_ERR_OOM; }
         GSR_CUDA_TRY(cudaMemset(c->grp.arena, 0, bytes));
@@ -852,7 +879,7 @@ GSR_API int gsr_group_export(gsr_ctx *c, void *blob) {
     memset(&b, 0, sizeof b);
     b.magic = GROUP_MAGIC; b.version = 1; b.pid = (uint64_t)getpid();
     b.device = c->device; b.width = c->width; b.height = c->height;
-    b.max_splats = c->max_splats; b.table_entries = c->grp.table_entries;
+    b.max_splats = c->max_splats; b.rx_capacity = c->grp.rx_capacity;
     b.arena = c->grp.arena; b.fb[0] = c->fb; b.fb[1] = c->fb2;
     // IPC handles are needed only by ranks living in other processes; a failure here surfaces there (zero handle)
     if (cudaIpcGetMemHandle(&b.h_arena, c->grp.arena) != cudaSuccess || cudaIpcGetMemHandle(&b.h_fb[0], c->fb) != cudaSuccess ||
@@ -875,7 +902,7 @@ GSR_API int gsr_group_attach(gsr_ctx *c, int32_t rank, int32_t world, const void
     const uint64_t slice = (((c->max_splats + (uint64_t)world - 1) / (uint64_t)world) + 255ull) & ~255ull;
     for (int r = 0; r < world; ++r) {
         if (B[r].magic != GROUP_MAGIC || B[r].version != 1) { set_last_error("gsr_group_attach: blob %d is not a gsr_group_export blob", r); return GSR_ERR_INVALID; }
-        if (B[r].max_splats != c->max_splats || B[r].width != c->width || B[r].height != c->height || slice * (uint64_t)world > B[r].table_entries) {
+        if (B[r].max_splats != c->max_splats || B[r].width != c->width || B[r].height != c->height || B[r].rx_capacity != c->grp.rx_capacity) {
             set_last_error("gsr_group_attach: rank %d was created with a different scene / frame size", r);
             return GSR_ERR_INVALID;
         }
@@ -914,13 +941,14 @@ GSR_API int gsr_group_attach(gsr_ctx *c, int32_t rank, int32_t world, const void
             }
         }
         c->grp.flags[r] = reinterpret_cast<GroupFlags *>(arena);
-        c->grp.table[0][r] = reinterpret_cast<uint32_t *>(arena + GROUP_FLAGS_BYTES);
-        c->grp.table[1][r] = c->grp.table[0][r] + B[r].table_entries;
+        c->grp.peer_arena[r] = arena;
         if (r == 0) { c->grp.root_fb[0] = fb[0]; c->grp.root_fb[1] = fb[1]; }
     }
     GSR_CUDA_TRY(cudaMemsetAsync(c->grp.arena, 0, GROUP_FLAGS_BYTES, c->stream));   // flags start at seq 0 (all ranks attach, then barrier)
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->grp.rank = rank; c->grp.world = world; c->grp.slice = slice; c->grp.seq = 0;
+    c->grp.seg_cap = (uint32_t)(c->grp.rx_capacity / (uint64_t)world);
+    c->grp.records_cur = nullptr;
     c->row_mod = world; c->row_rem = rank;   // cyclic tile rows: balanced by construction
     c->band_y0 = 0; c->band_y1 = c->tiles_y; c->band_set = false;
     c->copied_valid[0] = c->copied_valid[1] = false;
@@ -980,7 +1008,7 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
     const uint32_t t0 = (uint32_t)(c->band_y0 * c->tiles_x), t1 = (uint32_t)(c->band_y1 * c->tiles_x);
     if (tile_id < T && tile_id >= t0 && tile_id < t1 && (int)(tile_id / (uint32_t)c->tiles_x) % c->row_mod == c->row_rem) {
         CompositeArgs ca;
-        ca.records = c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
+        ca.records = (c->grp.world > 1 && c->grp.records_cur) ? c->grp.records_cur : c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
         ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
         ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1; ca.row_step = 1;
         ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
@@ -1092,7 +1120,7 @@ GSR_API int gsr_debug_copy(gsr_ctx *c, int which, void *dst, size_t bytes) {
     const void *src = nullptr;
     size_t avail = 0;
     switch (which) {
-        case GSR_BUF_RECORDS: src = c->records; avail = sizeof(float4) * 3ull * c->max_splats; break;
+        case GSR_BUF_RECORDS: src = (c->grp.world > 1 && c->grp.records_cur) ? c->grp.records_cur : c->records; avail = sizeof(float4) * 3ull * c->max_splats; break;
         case GSR_BUF_KEYS: src = c->keys; avail = sizeof(uint32_t) * c->capacity; break;
         case GSR_BUF_VALUES: src = c->vals; avail = sizeof(uint32_t) * c->capacity; break;
         case GSR_BUF_BOUNDS: src = c->bounds; avail = sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y; break;

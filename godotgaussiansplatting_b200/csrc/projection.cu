@@ -546,17 +546,6 @@ constexpr int SH_GROUPS = 4;
 constexpr int SH_SPLATS = SH_GROUPS * PROJ_THREADS;  // 1024 splats per CTA = one link of the chained scan
 constexpr size_t SH_SLAB_BYTES = sizeof(float4) * 3 * SH_SPLATS;  // planes 0..2 of the CTA's splats: [group][warp][plane][lane]
 
-// TABLE (experimental, a.extents != nullptr): the quick pass is a lookup in the frame's all-gathered row-extent table instead of
-// the cull + conservative test -- no plane is staged up front, the survivors' planes 0..2 are gathered in the dense pass.
-__device__ __forceinline__ bool extent_owned(uint32_t e, const ProjectionArgs &a) {   // does a row of [y0, y1) belong to this context?
-    int32_t y0 = (int32_t)(e & 0xFFFFu), y1 = (int32_t)(e >> 16);
-    if (y0 < a.band_y0) y0 = a.band_y0;
-    if (y1 > a.band_y1) y1 = a.band_y1;
-    if (y1 <= y0) return false;
-    return y0 + ((a.row_rem - y0 % a.row_mod) + a.row_mod) % a.row_mod < y1;
-}
-
-template <bool TABLE>
 __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(const __grid_constant__ ProjectionArgs a) {
 #ifndef GSR_CPU_EMU
     extern __shared__ __align__(128) unsigned char proj_smem[];
@@ -585,7 +574,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
     const uint32_t gx = (uint32_t)((a.u.dims[0] + TILE - 1) / TILE);
 
     // ---- TMA: planes 0..2 of the warp's four 32-splat slices (12 x 512 B onto the warp's mbarrier) ----
-    if (!TABLE && lane == 0) {
+    if (lane == 0) {
         mbar_expect_tx(&s_bar[warp], 12u * 512u);
 #pragma unroll
         for (int g = 0; g < SH_GROUPS; ++g)
@@ -594,7 +583,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
                 bulk_g2s(slab + ((g * PROJ_WARPS + warp) * 3u + k) * 32u, a.soa + (uint64_t)k * a.plane_stride + base_id + g * PROJ_THREADS + warp * 32u,
                          512u, &s_bar[warp]);
     }
-    if (!TABLE) mbar_wait(&s_bar[warp], 0);
+    mbar_wait(&s_bar[warp], 0);
 
     // ---- quick pass: cull + conservative row test, CTA-wide compaction of the survivors ----
 #pragma unroll
@@ -602,9 +591,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
         const uint32_t slot = g * PROJ_THREADS + tid;
         bool live = false;
         LaneOut q;
-        if (TABLE) {
-            if (base_id + slot < a.num_splats) live = extent_owned(__ldg(a.extents + base_id + slot), a);
-        } else
         if (base_id + slot < a.num_splats) live = project_lane<true>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), q);
         const uint32_t lmask = __ballot_sync(0xffffffffu, live);
         uint32_t wbase = 0;
@@ -620,9 +606,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
         const uint32_t slot = s_list[it];
         const uint32_t gid = base_id + slot;
         LaneOut o;
-        bool hit;
-        if (TABLE) hit = project_lane<false>(a, __ldg(a.soa + gid), __ldg(a.soa + a.plane_stride + gid), __ldg(a.soa + 2ull * a.plane_stride + gid), o);
-        else hit = project_lane<false>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), o);
+        const bool hit = project_lane<false>(a, slab_at(slot, 0), slab_at(slot, 1), slab_at(slot, 2), o);
         if (hit && o.n) {
             float col[3];
             sh_color<false>(a.soa + 3ull * a.plane_stride + gid, a.plane_stride, o.vx, o.vy, o.vz, col);
@@ -729,43 +713,245 @@ __global__ void __launch_bounds__(PROJ_THREADS, 3) projection_sharded_kernel(con
     }
 }
 
-// Group mode (gsr_group_attach): tile-row extent of the un-banded rect of splats [first, first + count) -- the exact rect of
-// gsplat_projection.glsl:144-148,191 (same project_lane), y0 | y1 << 16, 0 when the splat emits nothing -- stored into the
-// extent table of EVERY rank of the group: the all-gather of the cull is fused into the kernel that computes it, as 4-byte
-// peer stores over NVLink (a warp writes one 128-byte line per rank).  `a` must describe the FULL frame (band = all rows,
-// row_mod = 1, no reject): launch_extents() prepares that copy.  The CTA that finishes last publishes
-// seq << 32 | (last tile of the slice + 1) to meta[parity][rank] of every rank: data first, system fence, then the flag.
-__global__ void __launch_bounds__(PROJ_THREADS) extent_kernel(const __grid_constant__ ProjectionArgs a, uint32_t first, uint32_t count,
-                                                              const __grid_constant__ GroupPeers peers, int parity, uint32_t seq) {
-    __shared__ uint32_t s_is_last;
-    const uint32_t i = blockIdx.x * PROJ_THREADS + threadIdx.x;
-    const uint32_t id = first + i;
-    uint32_t e = 0u;
-    int32_t last = -1;
-    if (i < count && id < a.num_splats) {
-        LaneOut o;
-        if (project_lane<false>(a, __ldg(a.soa + id), __ldg(a.soa + a.plane_stride + id), __ldg(a.soa + 2ull * a.plane_stride + id), o) && o.n)
-            e = o.y0 | ((o.y0 + o.n / o.w) << 16);
-        last = o.last_tile;
+// ==============================================================================================================
+// Group mode (gsr_group_attach): the projection sharded by SPLATS.  Rank r of G runs the full-frame maths of projection_kernel for ITS
+// slice of the splats only (so the cull, the EWA, pow and the SH fetch happen once per splat in the whole group, not once per rank) and
+// sends every output to the rank that owns it: tile row y belongs to rank y % G, so a splat's (key, value) pairs of row y and its
+// 48-byte record go into rank (y % G)'s memory as plain stores through NVLink peer pointers -- the all-to-all of SURVEY 8e fused into the
+// kernel that produces the data.  Per destination the pairs must arrive in splat-id order (the stable sort keeps that order among
+// equal keys, and the reference's result depends on it): every destination has its own chained scan (G links per CTA, resolved together
+// by the closer warp), and source r writes into ITS receive segment of the destination, [r * seg_cap, (r + 1) * seg_cap).  The
+// destination later packs the G segments in source order = splat-id order.  When all CTAs are done the last one publishes
+// seq | count and seq | last tile to every destination's flag page (data first, system fence, then the flags).
+__device__ __forceinline__ unsigned long long lookback_exclusive_strided(volatile unsigned long long *status, uint32_t stride, uint32_t col, uint32_t bid,
+                                                                         unsigned long long total, uint32_t lane) {
+    if (bid == 0) return 0ull;
+    unsigned long long excl = 0ull;
+    int64_t start = (int64_t)bid - 1;
+    while (true) {
+        const int64_t t = start - (int64_t)lane;
+        unsigned long long v = (t >= 0) ? status[(uint64_t)t * stride + col] : LB_PREFIX;
+        while (__any_sync(0xffffffffu, (v >> 62) == 0ull)) {
+            if ((v >> 62) == 0ull) v = status[(uint64_t)t * stride + col];
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+        const uint32_t first = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        unsigned long long c = (lane <= first) ? (v & LB_VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        excl += c;
+        if (pmask) break;
+        start -= 32;
     }
-    if (i < count) {
-#pragma unroll 4
-        for (int r = 0; r < peers.world; ++r) peers.table[r][id] = e;
+    if (lane == 0) status[(uint64_t)bid * stride + col] = LB_PREFIX | ((excl + total) & LB_VAL);
+    return excl;
+}
+
+// rows of [y0, y1) that rank d of G owns: first such row and how many
+__device__ __forceinline__ void rows_of(uint32_t y0, uint32_t y1, uint32_t d, uint32_t G, uint32_t &first, uint32_t &count) {
+    first = y0 + ((d + G - y0 % G) % G);
+    count = first < y1 ? (y1 - 1u - first) / G + 1u : 0u;
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS, GSR_PROJ_MIN_BLOCKS) projection_scatter_kernel(const __grid_constant__ ProjectionArgs a,
+                                                                                               const __grid_constant__ ScatterPeers sp) {
+#ifndef GSR_CPU_EMU
+    extern __shared__ __align__(128) unsigned char proj_smem[];
+#else
+    __shared__ __align__(128) unsigned char proj_smem[PROJ_SMEM_BYTES];
+#endif
+    __shared__ uint32_t s_bid, s_is_last;
+    __shared__ __align__(8) uint64_t s_bar[PROJ_WARPS][2];
+    __shared__ uint32_t s_wtotal[PROJ_WARPS][GROUP_MAX];   // pairs of each warp for each destination
+    __shared__ uint32_t s_count, s_ready, s_nvis;
+    __shared__ int32_t s_last;
+    __shared__ unsigned long long s_cta_base[GROUP_MAX];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t G = (uint32_t)sp.world;
+    float4 *slab = reinterpret_cast<float4 *>(proj_smem + (size_t)warp * PROJ_SLAB_BYTES);  // [15][32]
+    GroupFlags *mine = sp.flags[sp.rank];
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_mbar_init();
     }
-    GroupFlags *mine = peers.flags[peers.rank];
-    const int32_t wl = __reduce_max_sync(0xffffffffu, last);
-    if ((threadIdx.x & 31u) == 0u && wl >= 0) atomicMax(&mine->ext_last, wl + 1);
-    __threadfence_system();   // this thread's table stores (and the atomicMax) are ordered before the ticket below
+    if (tid == 0) {
+        s_bid = atomicAdd(&a.frame->proj_ticket, 1u);
+        s_count = 0u; s_ready = 0u; s_nvis = 0u; s_last = -1;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) s_is_last = atomicAdd(&mine->ext_ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    const uint32_t bid = s_bid;                      // position of this CTA in the chained scans
+    const uint32_t li0 = (bid * PROJ_WARPS + warp) * 32u;   // index inside the slice
+    const uint32_t id0 = sp.first + li0, id = id0 + lane;
+    const bool warp_in = li0 < sp.count;             // the slice may end inside the CTA (planes are padded to 256 splats: staging stays in bounds)
+
+    if (warp_in && lane == 0) {
+        mbar_expect_tx(&s_bar[warp][0], 3u * 512u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][0]);
+    }
+    const uint32_t gx = (uint32_t)((a.u.dims[0] + TILE - 1) / TILE);
+
+    uint32_t n = 0, x0u = 0, y0u = 0, y1u = 0, wu = 0, depth = 0;
+    int32_t last_tile = -1;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    float splat_opacity = 0.0f, vx = 0.0f, vy = 0.0f, vz = 0.0f;
+    if (warp_in) {
+        mbar_wait(&s_bar[warp][0], 0);
+        if (li0 + lane < sp.count && id < a.num_splats) {
+            LaneOut o;
+            if (project_lane<false>(a, slab[lane], slab[32 + lane], slab[64 + lane], o) && o.n) {
+                n = o.n; x0u = o.x0; y0u = o.y0; wu = o.w; depth = o.depth; y1u = o.y0 + o.n / o.w;
+                r0 = o.r0; r1 = o.r1; splat_opacity = o.opacity; vx = o.vx; vy = o.vy; vz = o.vz;
+            }
+            last_tile = o.last_tile;
+        }
+    }
+
+    // ---- per-destination pair counts of the warp; the CTA's last warp through here (the closer) publishes the G scan links ----
+    for (uint32_t d = 0; d < G; ++d) {
+        uint32_t f, c;
+        rows_of(y0u, y1u, d, G, f, c);
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, n ? wu * c : 0u);
+        if (lane == 0) s_wtotal[warp][d] = tot;
+    }
+    const uint32_t emit_mask = __ballot_sync(0xffffffffu, n != 0u);
+    const uint32_t nvis = __popc(emit_mask);
+    const int32_t wl = __reduce_max_sync(0xffffffffu, last_tile);
+    bool closer = false;
+    if (lane == 0) {
+        if (nvis) atomicAdd(&s_nvis, nvis);
+        if (wl >= 0) atomicMax(&s_last, wl);
+        __threadfence_block();
+        closer = atomicAdd(&s_count, 1u) == PROJ_WARPS - 1;
+    }
+    closer = __shfl_sync(0xffffffffu, (int)closer, 0) != 0;
+    uint32_t cta_total = 0;   // closer: lane d holds the CTA's pair count for destination d
+    if (closer) {
+        __threadfence_block();
+        if (lane < G) {
+#pragma unroll
+            for (int w = 0; w < PROJ_WARPS; ++w) cta_total += ((volatile uint32_t *)&s_wtotal[w][0])[lane];
+            volatile unsigned long long *st = sp.lookback + (uint64_t)bid * G + lane;
+            *st = (bid == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)cta_total;
+        }
+    }
+
+    // ---- phase 2: SH planes -> colour -> record, stored into the record table of every rank that owns one of the splat's rows ----
+    const bool bulk = warp_in && nvis >= (uint32_t)a.sh_bulk_min;
+    if (bulk && lane == 0) {
+        mbar_expect_tx(&s_bar[warp][1], 12u * 512u);
+#pragma unroll
+        for (int k = 3; k < NUM_PLANES; ++k) bulk_g2s(slab + k * 32, a.soa + (uint64_t)k * a.plane_stride + id0, 512u, &s_bar[warp][1]);
+    }
+    if (closer) {
+        for (uint32_t d = 0; d < G; ++d) {
+            const uint32_t tot_d = __shfl_sync(0xffffffffu, cta_total, (int)d);
+            const unsigned long long base_d = lookback_exclusive_strided(sp.lookback, G, d, bid, (unsigned long long)tot_d, lane);
+            if (lane == 0) {
+                s_cta_base[d] = base_d;
+                if (bid == gridDim.x - 1) mine->seg_total[d] = base_d + tot_d;   // tickets are dense: this CTA closes every scan
+            }
+        }
+        if (lane == 0) {
+            __threadfence_block();
+            *(volatile uint32_t *)&s_ready = 1u;
+            const uint32_t nv = *(volatile uint32_t *)&s_nvis;
+            const int32_t lt = *(volatile int32_t *)&s_last;
+            if (nv) atomicAdd(&a.frame->visible, nv);
+            if (lt >= 0) atomicMax(&mine->scat_last, lt + 1);
+        }
+    }
+    if (bulk) mbar_wait(&s_bar[warp][1], 0);
+    if (n) {
+        float col[3];
+        if (bulk) sh_color<true>(slab + 3 * 32 + lane, 32, vx, vy, vz, col);
+        else sh_color<false>(a.soa + 3ull * a.plane_stride + id, a.plane_stride, vx, vy, vz, col);
+        const float4 r2 = make_float4(col[0], col[1], col[2], splat_opacity);
+        for (uint32_t d = 0; d < G; ++d) {
+            uint32_t f, c;
+            rows_of(y0u, y1u, d, G, f, c);
+            if (c) {
+                float4 *rec = sp.records[d] + (uint64_t)id * 3u;
+                rec[0] = r0; rec[1] = r1; rec[2] = r2;
+            }
+        }
+    }
+
+    if (lane == 0) {
+        while (*(volatile uint32_t *)&s_ready == 0u) __nanosleep(100);
+        __threadfence_block();
+    }
+    __syncwarp();
+
+    // ---- emit (:219-226), once per destination: slot base + off + j of destination d's segment holds tile j (row-major over the rows
+    //      d owns) of the splat's rect.  Same hybrid as projection_kernel: small rects by their own lane, big ones by the whole warp.
+    constexpr uint32_t EMIT_SMALL = 4;
+    for (uint32_t d = 0; d < G; ++d) {
+        uint32_t fy, cnt;
+        rows_of(y0u, y1u, d, G, fy, cnt);
+        const uint32_t nd = n ? wu * cnt : 0u;
+        if (!__any_sync(0xffffffffu, nd != 0u)) continue;
+        const uint32_t incl = warp_incl_scan_u32(nd, lane);
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = *(volatile unsigned long long *)&s_cta_base[d];
+            for (uint32_t w = 0; w < warp; ++w) base += ((volatile uint32_t *)&s_wtotal[w][0])[d];
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t *kd = sp.keys[d], *vd = sp.values[d];
+        const uint32_t my_off = incl - nd;
+        if (nd != 0u && nd <= EMIT_SMALL) {
+            uint32_t x = x0u, y = fy;
+            const uint32_t x1 = x0u + wu;
+#pragma unroll
+            for (uint32_t j = 0; j < EMIT_SMALL; ++j) {
+                if (j < nd) {
+                    const unsigned long long g = base + my_off + j;
+                    if (g < (unsigned long long)sp.seg_cap) {
+                        kd[g] = ((y * gx + x) << 16) | depth;
+                        vd[g] = id;
+                    }
+                    if (++x == x1) { x = x0u; y += G; }
+                }
+            }
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, nd > EMIT_SMALL);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1u;
+            const uint32_t sn = __shfl_sync(0xffffffffu, nd, src), soff = __shfl_sync(0xffffffffu, my_off, src);
+            const uint32_t sx0 = __shfl_sync(0xffffffffu, x0u, src), sy0 = __shfl_sync(0xffffffffu, fy, src);
+            const uint32_t sw = __shfl_sync(0xffffffffu, wu, src), sdepth = __shfl_sync(0xffffffffu, depth, src);
+            for (uint32_t j = lane; j < sn; j += 32u) {
+                const uint32_t ry = j / sw, rx = j - ry * sw;
+                const unsigned long long g = base + soff + j;
+                if (g < (unsigned long long)sp.seg_cap) {
+                    kd[g] = (((sy0 + ry * G) * gx + sx0 + rx) << 16) | sdepth;
+                    vd[g] = id0 + (uint32_t)src;
+                }
+            }
+        }
+    }
+
+    // ---- completion: when every CTA's pairs and records are on their way, tell every destination how many pairs it got from this
+    //      source and the largest tile this source touched (the frame-global Q10 bookkeeping travels with the data) ----
+    __threadfence_system();
     __syncthreads();
-    if (s_is_last && threadIdx.x < 32u) {
+    if (tid == 0) s_is_last = atomicAdd(&mine->scat_ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (s_is_last && tid < 32u) {
         __threadfence_system();
-        const int32_t lp1 = *(volatile int32_t *)&mine->ext_last;
-        const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)(uint32_t)(lp1 > 0 ? lp1 : 0);
-        if ((int)threadIdx.x < peers.world) *(volatile unsigned long long *)&peers.flags[threadIdx.x]->meta[parity][peers.rank] = word;
+        const int32_t lp1 = __shfl_sync(0xffffffffu, lane == 0 ? *(volatile int32_t *)&mine->scat_last : 0, 0);   // read once, before lane 0 resets it
+        if (lane < G) {
+            const unsigned long long cnt = *(volatile unsigned long long *)&mine->seg_total[lane];
+            volatile unsigned long long *m = &sp.flags[lane]->seg_meta[sp.parity][sp.rank][0];
+            m[1] = ((unsigned long long)sp.seq << 32) | (unsigned long long)(uint32_t)(lp1 > 0 ? lp1 : 0);
+            m[0] = ((unsigned long long)sp.seq << 32) | (cnt < 0xFFFFFFFFull ? cnt : 0xFFFFFFFFull);
+        }
         __syncwarp();
-        if (threadIdx.x == 0) { mine->ext_last = 0; mine->ext_ticket = 0u; __threadfence(); }   // ready for the next frame (stream order)
+        if (lane == 0) { mine->scat_last = 0; mine->scat_ticket = 0u; __threadfence(); }   // ready for the next frame (stream order)
     }
 }
 
@@ -780,20 +966,20 @@ int preload_projection_kernels() {
     cudaFuncAttributes fa;
     // dynamic shared memory opt-in is a per-device function attribute: set here, once per context creation, on the context's device
     GSR_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROJ_SMEM_BYTES));
-    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
-    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
+    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SLAB_BYTES));
+    GSR_CUDA_TRY(cudaFuncSetAttribute(projection_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROJ_SMEM_BYTES));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_kernel));
-    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel<false>));
-    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel<true>));
-    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, extent_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_sharded_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, projection_scatter_kernel));
     return GSR_OK;
 }
-int launch_extents(const ProjectionArgs &frame_args, uint32_t first, uint32_t count, const GroupPeers &peers, int parity, uint32_t seq, cudaStream_t stream) {
-    ProjectionArgs a = frame_args;   // the whole frame: no band, no row ownership, no reject
+uint32_t projection_scatter_blocks(uint32_t count) { return count ? (count + PROJ_THREADS - 1) / PROJ_THREADS : 1u; }   // an empty slice still publishes its flags
+
+int launch_projection_scatter(const ProjectionArgs &frame_args, const ScatterPeers &sp, cudaStream_t stream) {
+    ProjectionArgs a = frame_args;   // the whole frame: no band, no row ownership, no reject (ownership is decided per pair, by destination)
     a.band_y0 = 0; a.band_y1 = (a.u.dims[1] + TILE - 1) / TILE;
-    a.row_mod = 1; a.row_rem = 0; a.fast_reject = 0; a.fast_mode = 0; a.extents = nullptr;
-    const uint32_t blocks = count ? (count + PROJ_THREADS - 1) / PROJ_THREADS : 1u;   // an empty slice still publishes its flag
-    extent_kernel<<<blocks, PROJ_THREADS, 0, stream>>>(a, first, count, peers, parity, seq);
+    a.row_mod = 1; a.row_rem = 0; a.fast_reject = 0; a.fast_mode = 0; a.sh_bulk_min = 12;
+    projection_scatter_kernel<<<projection_scatter_blocks(sp.count), PROJ_THREADS, PROJ_SMEM_BYTES, stream>>>(a, sp);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;
 }
@@ -801,10 +987,9 @@ int launch_extents(const ProjectionArgs &frame_args, uint32_t first, uint32_t co
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream) {
     const uint32_t blocks = projection_num_blocks(a.num_splats);
     if (blocks == 0) return GSR_OK;
-    if (a.fast_reject || a.extents) {  // sharded variant: 1024 splats per CTA
+    if (a.fast_reject) {  // sharded variant: 1024 splats per CTA
         const uint32_t sblocks = (a.num_splats + SH_SPLATS - 1) / SH_SPLATS;
-        if (a.extents) projection_sharded_kernel<true><<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
-        else projection_sharded_kernel<false><<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
+        projection_sharded_kernel<<<sblocks, PROJ_THREADS, SH_SLAB_BYTES, stream>>>(a);
         GSR_CUDA_TRY(cudaGetLastError());
         return GSR_OK;
     }

@@ -255,7 +255,7 @@ GSR_API int gsr_debug_copy(gsr_ctx *ctx, int which, void *dst, size_t bytes);
 GSR_API int gsr_debug_enable_trace(gsr_ctx *ctx, uint32_t max_items);
 /* Scheduling of the compositor's persistent grid (results never depend on it): resident CTAs per SM (0 = as many as fit; default 2),
  * longest-chain-first ticket order (default on), and the sparse-frame rule of that order pass: with at most
- * sparse_tiles_per_sm * SMs occupied tiles only one CTA per SM works (default 3; 0 = never). */
+ * sparse_tiles_per_sm * SMs occupied tiles only one CTA per SM works (default 5; 0 = never). */
 GSR_API int gsr_debug_compositor_config(gsr_ctx *ctx, int32_t ctas_per_sm, int32_t longest_first, int32_t sparse_tiles_per_sm);
 /* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
 GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);

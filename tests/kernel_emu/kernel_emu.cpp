@@ -157,8 +157,7 @@ extern "C" int emu_sort_pairs(uint32_t *keys, uint32_t *values, uint32_t n, uint
 namespace { void run_blocks(unsigned blocks, unsigned threads, void (*body)(void *), void *arg); }
 namespace {
 void projection_body(void *p) { gsr::projection_kernel(*static_cast<const gsr::ProjectionArgs *>(p)); }
-void projection_sharded_body(void *p) { gsr::projection_sharded_kernel<false>(*static_cast<const gsr::ProjectionArgs *>(p)); }
-void projection_table_body(void *p) { gsr::projection_sharded_kernel<true>(*static_cast<const gsr::ProjectionArgs *>(p)); }
+void projection_sharded_body(void *p) { gsr::projection_sharded_kernel(*static_cast<const gsr::ProjectionArgs *>(p)); }
 }  // namespace
 
 // soa: 15 planes x plane_stride float4 (the library's SoA layout); vp: 32 floats; uniforms32: the 32-byte block.
@@ -196,26 +195,9 @@ extern "C" long long emu_projection(const void *soa, unsigned long long plane_st
         for (int i = 0; i < 3; ++i) { float row = 0.0f; for (int j = 0; j < 3; ++j) row += g[i][j] < 0.0f ? -g[i][j] : g[i][j]; nrm = row > nrm ? row : nrm; }
         pa.w_frob2 = nrm * 1.0001f;
     }
-    if (extents_out) {   // launch_extents(): the whole frame, no band / ownership / reject
-        gsr::ProjectionArgs fa = pa;
-        fa.band_y0 = 0; fa.band_y1 = (fa.u.dims[1] + gsr::TILE - 1) / gsr::TILE;
-        fa.row_mod = 1; fa.row_rem = 0; fa.fast_reject = 0; fa.fast_mode = 0; fa.extents = nullptr;
-        // group of one "rank": the peer-store loop writes the single table; the last block publishes seq << 32 | last tile + 1
-        static gsr::GroupFlags flags;
-        memset(&flags, 0, sizeof flags);
-        gsr::GroupPeers peers;
-        memset(&peers, 0, sizeof peers);
-        peers.world = 1; peers.rank = 0; peers.flags[0] = &flags; peers.table[0] = extents_out;
-        struct EL { gsr::ProjectionArgs a; unsigned first, count; gsr::GroupPeers peers; } el{fa, ext_first, ext_count, peers};
-        run_blocks(ext_count ? (ext_count + gsr::PROJ_THREADS - 1) / gsr::PROJ_THREADS : 1u, (unsigned)gsr::PROJ_THREADS,
-                   [](void *p) { EL *l = static_cast<EL *>(p); gsr::extent_kernel(l->a, l->first, l->count, l->peers, 1, 77u); }, &el);
-        if (flags.ext_ticket != 0u || flags.ext_last != 0 || (uint32_t)(flags.meta[1][0] >> 32) != 77u) return -1;   // protocol words reset / published
-        return (long long)(uint32_t)flags.meta[1][0];   // last tile of the slice + 1
-    }
-    pa.extents = extents;
     gsr::FrameState frame;
     memset(&frame, 0, sizeof frame);
-    const bool sharded_kernel = pa.fast_reject || pa.extents;
+    const bool sharded_kernel = pa.fast_reject != 0;
     const unsigned per_block = sharded_kernel ? (unsigned)gsr::SH_SPLATS : (unsigned)gsr::PROJ_THREADS;
     const unsigned blocks = (num_splats + per_block - 1) / per_block;
     unsigned long long *lookback = static_cast<unsigned long long *>(calloc(blocks ? blocks : 1, sizeof(unsigned long long)));
@@ -225,7 +207,7 @@ extern "C" long long emu_projection(const void *soa, unsigned long long plane_st
     cuda_emu::g_grid_dim = cuda_emu::dim{blocks, 1, 1};
     for (unsigned b = 0; b < blocks; ++b)
         glsl::run_workgroup(glsl::uvec3(b, 0, 0), glsl::uvec3((unsigned)gsr::PROJ_THREADS, 1, 1),
-                            pa.extents ? &projection_table_body : (pa.fast_reject ? &projection_sharded_body : &projection_body), &pa);
+                            pa.fast_reject ? &projection_sharded_body : &projection_body, &pa);
     cuda_emu::g_block_dim = cuda_emu::dim{128, 1, 1};
     cuda_emu::g_grid_dim = cuda_emu::dim{1, 1, 1};
     free(lookback);
@@ -233,6 +215,54 @@ extern "C" long long emu_projection(const void *soa, unsigned long long plane_st
     if (last_tile_out) *last_tile_out = frame.last_tile_plus1 - 1;
     if (overflow_out) *overflow_out = frame.overflow;
     return (long long)frame.dup_total;
+}
+
+// ---- projection_scatter_kernel (group mode): rank `rank` of `world` projects its slice [first, first + count) and scatters pairs and
+//      records into `world` destination buffers (here: plain host arrays standing in for the peers' arenas).  Returns 0 and fills
+//      counts[world] (pairs sent to each destination, as published in the flag words) and *last_plus1.
+extern "C" int emu_projection_scatter(const void *soa, unsigned long long plane_stride, unsigned num_splats, const float *vp, const void *uniforms32, int world,
+                                      int rank, unsigned first, unsigned count, unsigned seg_cap, void **dst_records, uint32_t **dst_keys, uint32_t **dst_values,
+                                      unsigned long long *counts, unsigned *last_plus1) {
+    if (world < 1 || world > gsr::GROUP_MAX) return 3;
+    gsr::ProjectionArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.soa = static_cast<const float4 *>(soa); pa.plane_stride = plane_stride; pa.num_splats = num_splats;
+    memcpy(pa.vp, vp, sizeof pa.vp);
+    memcpy(&pa.u, uniforms32, sizeof pa.u);
+    {
+        const float tfi0 = vp[16 + 0], tfi1 = vp[16 + 5];
+        const volatile float hw = (float)pa.u.dims[0] * 0.5f, hh = (float)pa.u.dims[1] * 0.5f;
+        const volatile float f0 = hw * tfi0, f1 = hh * tfi1;
+        const volatile float t0 = 1.0f / tfi0, t1 = 1.0f / tfi1;
+        const volatile float n0 = -t0, n1 = -t1;
+        pa.focal_base[0] = f0; pa.focal_base[1] = f1;
+        pa.lim_lo[0] = n0 * 1.3f; pa.lim_lo[1] = n1 * 1.3f;
+        pa.lim_hi[0] = t0 * 1.3f; pa.lim_hi[1] = t1 * 1.3f;
+    }
+    pa.band_y0 = 0; pa.band_y1 = (pa.u.dims[1] + gsr::TILE - 1) / gsr::TILE; pa.row_mod = 1; pa.row_rem = 0; pa.sh_bulk_min = 12;
+    gsr::FrameState frame;
+    memset(&frame, 0, sizeof frame);
+    pa.frame = &frame;
+    static gsr::GroupFlags flags[gsr::GROUP_MAX];
+    memset(flags, 0, sizeof flags);
+    gsr::ScatterPeers sp;
+    memset(&sp, 0, sizeof sp);
+    sp.world = world; sp.rank = rank; sp.parity = 1; sp.seq = 91u; sp.first = first; sp.count = count; sp.seg_cap = seg_cap;
+    for (int d = 0; d < world; ++d) { sp.records[d] = static_cast<float4 *>(dst_records[d]); sp.keys[d] = dst_keys[d]; sp.values[d] = dst_values[d]; sp.flags[d] = &flags[d]; }
+    const unsigned blocks = count ? (count + gsr::PROJ_THREADS - 1) / gsr::PROJ_THREADS : 1u;
+    sp.lookback = static_cast<unsigned long long *>(calloc((size_t)blocks * world, sizeof(unsigned long long)));
+    struct SL { gsr::ProjectionArgs a; gsr::ScatterPeers sp; } sl{pa, sp};
+    run_blocks(blocks, (unsigned)gsr::PROJ_THREADS, [](void *p) { SL *l = static_cast<SL *>(p); gsr::projection_scatter_kernel(l->a, l->sp); }, &sl);
+    free(sp.lookback);
+    int rc = 0;
+    for (int d = 0; d < world; ++d) {   // what the kernel's last block published to destination d
+        const unsigned long long w0 = flags[d].seg_meta[1][rank][0], w1 = flags[d].seg_meta[1][rank][1];
+        if ((uint32_t)(w0 >> 32) != 91u || (uint32_t)(w1 >> 32) != 91u) rc = 1;
+        counts[d] = (uint32_t)w0;
+        if (last_plus1) *last_plus1 = (uint32_t)w1;
+    }
+    if (flags[rank].scat_ticket != 0u || flags[rank].scat_last != 0) rc = 2;   // protocol words reset for the next frame
+    return rc;
 }
 
 // ---- csrc/ingest.cu ----

@@ -224,16 +224,27 @@ def emu_upload(splat60, chunk=None):
     return soa, stride
 
 
-def emu_extents(soa, stride, n, vp, ub, table, first, count):
-    """launch_extents (group mode): fills table[first:first+count] (y0 | y1 << 16 of the un-banded rect, 0 = emits nothing)."""
+def emu_scatter(soa, stride, n, vp, ub, G, rank, first, count, seg_cap):
+    """projection_scatter_kernel (group mode) of rank `rank`: its slice's pairs and records into G destination buffers."""
     vp = np.ascontiguousarray(vp, dtype=np.float32)
-    r = lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, 0, 0, 1, 0, 0, 0, None, None, None, 0, None, None, None,
-                             None, table.ctypes.data, first, count)
-    assert r >= 0, "extent kernel: flag protocol words not published / reset"
-    return int(r)   # last tile of the slice + 1 (what the kernel publishes next to the sequence number)
+    recs = [np.zeros(n, dtype=orc.RECORD_DTYPE) for _ in range(G)]
+    keys = [np.full(seg_cap, 0xDEADBEEF, dtype=np.uint32) for _ in range(G)]
+    vals = [np.full(seg_cap, 0xDEADBEEF, dtype=np.uint32) for _ in range(G)]
+    PP = C.c_void_p * G
+    counts = (C.c_ulonglong * G)()
+    last = C.c_uint(0)
+    L = lib()
+    L.emu_projection_scatter.restype = C.c_int
+    L.emu_projection_scatter.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.emu_projection_scatter(soa.ctypes.data, stride, n, vp.ctypes.data, ub, G, rank, first, count, seg_cap,
+                                  PP(*[r.ctypes.data for r in recs]), PP(*[k.ctypes.data for k in keys]), PP(*[v.ctypes.data for v in vals]),
+                                  counts, C.byref(last))
+    assert rc == 0, {1: "flag words not published", 2: "protocol words not reset"}.get(rc, rc)
+    return recs, keys, vals, [int(c) for c in counts], int(last.value)
 
 
-def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, fast_reject=0, sh_bulk_min=0, cap=None, extents=None):
+def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, fast_reject=0, sh_bulk_min=0, cap=None):
     gy = (h + 15) // 16
     y0, y1 = (0, gy) if band is None else band
     cap = cap or 10 * n
@@ -244,7 +255,7 @@ def emu_project(soa, stride, n, vp, ub, w, h, band=None, row_mod=1, row_rem=0, f
     vp = np.ascontiguousarray(vp, dtype=np.float32)
     m = lib().emu_projection(soa.ctypes.data, stride, n, vp.ctypes.data, ub, y0, y1, row_mod, row_rem, fast_reject, sh_bulk_min, rec.ctypes.data,
                              keys.ctypes.data, vals.ctypes.data, cap, C.byref(vis), C.byref(last), C.byref(ovf),
-                             None if extents is None else extents.ctypes.data, None, 0, 0)
+                             None, None, 0, 0)
     return dict(m=int(m), keys=keys[:min(m, cap)], values=vals[:min(m, cap)], records=rec, visible=int(vis.value), last_tile=int(last.value),
                 overflow=bool(ovf.value))
 
@@ -366,42 +377,44 @@ def test_whole_pipeline_through_the_emulated_kernels():
 
 
 @pytest.mark.parametrize("G", [2, 3, 8])
-def test_extent_table_mode_splits_the_cull_across_ranks(G):
-    """Group mode (gsr_group_*): every rank computes the tile-row extents of its slice of the splats, the slices are all-gathered,
-    and every rank then projects only the splats whose rows it owns -- emitting exactly what the replicated cull emits."""
+def test_scatter_projection_shards_the_splats_and_routes_pairs_to_row_owners(G):
+    """Group mode (gsr_group_*, projection_scatter_kernel): every rank projects ITS slice of the splats and stores each pair / record
+    into the buffers of the rank that owns the tile row (row % G).  Concatenating, per destination, the segments of the sources in
+    rank order must give exactly the single-GPU emission restricted to the destination's rows -- same keys, same splat-id order --
+    and the destination's record table must hold the oracle's records of every splat that touches its rows."""
     n, w, h = 12000, 320, 240
     gx, gy = (w + 15) // 16, (h + 15) // 16
     splat60, vp, ub = make_scene(n, 8, w, h, scale_boost=1.0)
     u = orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8))
     soa, stride = emu_upload(splat60)
     full = orc.project(splat60, vp, u)
-    # "all-gather": rank r fills its 256-aligned slice of the one table
+    rows = (full.keys >> 16).astype(np.int64) // gx
     slice_len = ((n + G - 1) // G + 255) // 256 * 256
-    table = np.full(G * slice_len, 0xDEADBEEF, dtype=np.uint32)
-    lasts = [emu_extents(soa, stride, n, vp, ub, table, r * slice_len, slice_len) for r in range(G)]
-    assert max(lasts) == full.last_tile + 1   # the frame-global last occupied tile travels with the slices (exact Q10 bookkeeping)
-    # the table is the exact rect: rows [y0, y1) of every visible splat, 0 otherwise
-    tiles = full.keys >> 16
-    row = (tiles // gx).astype(np.int64)
-    y0 = np.full(n, 1 << 30, dtype=np.int64)
-    y1 = np.zeros(n, dtype=np.int64)
-    np.minimum.at(y0, full.values, row)
-    np.maximum.at(y1, full.values, row + 1)
-    vis = y1 > 0
-    np.testing.assert_array_equal(table[:n][vis], (y0[vis] | (y1[vis] << 16)).astype(np.uint32))
-    assert not table[:n][~vis].any() and not table[n:].any()
-    rows = row
-    seen = 0
-    for rem in range(G):
-        got = emu_project(soa, stride, n, vp, ub, w, h, row_mod=G, row_rem=rem, extents=table)
-        own = rows % G == rem
-        np.testing.assert_array_equal(got["keys"], full.keys[own])
-        np.testing.assert_array_equal(got["values"], full.values[own])
+    seg_cap = 10 * n // G
+    got_keys = [[] for _ in range(G)]
+    got_vals = [[] for _ in range(G)]
+    got_recs = [np.zeros(n, dtype=orc.RECORD_DTYPE) for _ in range(G)]
+    lasts = []
+    for r in range(G):
+        first = min(r * slice_len, n)
+        count = max(0, min(slice_len, n - first))
+        recs, keys, vals, counts, last = emu_scatter(soa, stride, n, vp, ub, G, r, first, count, seg_cap)
+        lasts.append(last)
+        in_slice = (full.values >= first) & (full.values < first + count)
+        for d in range(G):
+            assert counts[d] == int((in_slice & (rows % G == d)).sum())           # the count published to destination d
+            assert counts[d] <= seg_cap and np.all(keys[d][counts[d]:] == 0xDEADBEEF)  # nothing beyond the segment's fill
+            got_keys[d].append(keys[d][:counts[d]]); got_vals[d].append(vals[d][:counts[d]])
+            ids = np.unique(vals[d][:counts[d]])
+            got_recs[d][ids] = recs[d][ids]
+    assert max(lasts) == full.last_tile + 1   # the frame-global last occupied tile travels with the segments (exact Q10 bookkeeping)
+    for d in range(G):
+        own = rows % G == d
+        np.testing.assert_array_equal(np.concatenate(got_keys[d]), full.keys[own])
+        np.testing.assert_array_equal(np.concatenate(got_vals[d]), full.values[own])
         ids = np.unique(full.values[own])
         for f in orc.RECORD_DTYPE.names:
-            np.testing.assert_array_equal(bits(got["records"][f][ids]), bits(full.records[f][ids]), err_msg=f"record field {f}")
-        seen += got["m"]
-    assert seen == full.duplicates
+            np.testing.assert_array_equal(bits(got_recs[d][f][ids]), bits(full.records[f][ids]), err_msg=f"record field {f}")
 
 
 @pytest.mark.parametrize("fmt", [0, 1, 2, 3, 0x100, 0x101, 0x102, 0x103])
