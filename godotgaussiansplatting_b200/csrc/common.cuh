@@ -161,7 +161,7 @@ int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
 // multi-GPU shard group (group.cu, gsr_group_attach): flag words + extent tables in every rank's arena
 // ---------------------------------------------------------------------------------------------
 constexpr int GROUP_MAX = 16;                                   // ranks per group (one NVSwitch domain)
-#define GSR_GROUP_TIMEOUT_NS 10000000000ull                     // every device-side wait gives up after 10 s
+#define GSR_GROUP_TIMEOUT_NS 2000000000ull                      // every device-side wait gives up after 2 s
 struct GroupFlags {                                             // offset 0 of a rank's arena; written by the peers over NVLink
     // [frame parity][source rank][0] = seq << 32 | pairs the source sent to THIS rank's receive segment,
     //                            [1] = seq << 32 | (largest tile id touched by the source's splats + 1)

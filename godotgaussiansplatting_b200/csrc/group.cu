@@ -12,7 +12,11 @@ namespace gsr {
 
 namespace {
 
+#ifndef GSR_CPU_EMU
 __device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#else
+inline unsigned long long now_ns() { return 0ull; }
+#endif
 
 // Destination side of the scatter projection.  Lane r < world waits until source r's two flag words of this parity carry `seq`
 // (the source stored its pairs and records first, then a system fence, then the flags).  Then: exclusive prefix of the received
@@ -40,9 +44,9 @@ __global__ void __launch_bounds__(32) group_wait_segments_kernel(GroupFlags *fla
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane <= world) flags->seg_prefix[lane] = lane == world ? __shfl_sync(0xffffffffu, incl, world - 1) : incl - kept;
+    const uint32_t m = __shfl_sync(0xffffffffu, incl, world - 1);   // (warp collectives stay outside divergent code)
+    if (lane <= world) flags->seg_prefix[lane] = lane == world ? m : incl - kept;
     const unsigned long long total = (unsigned long long)__reduce_add_sync(0xffffffffu, count > 0x7FFFFFFFu ? 0x7FFFFFFFu : count);  // 16 x 2^31 fits
-    const uint32_t m = __shfl_sync(0xffffffffu, incl, world - 1);
     const uint32_t any_over = __any_sync(0xffffffffu, count > seg_cap) ? 1u : 0u;
     const uint32_t g = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) {

@@ -7,7 +7,7 @@ nvidia-smi topo -m > $out/topo.txt 2>&1
 run() { # name, args...
   name=$1; shift
   NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N "$@" > $out/bench_$name.json 2> $out/bench_$name.err
-  echo "$name rc=$? $(python -c "import json,sys; d=json.load(open('$out/bench_$name.json')); print('fps',round(d['fps'],1),'e2e_fps',round(d['e2e']['fps'],1),'stages',{k:round(v,3) for k,v in d['stage_ms'].items()},'parity',d['parity'].get('rgba_bit_identical'))" 2>&1 | tail -1)"
+  echo "$name rc=$? $(python -c "import json,sys; d=json.load(open('$out/bench_$name.json')); print('fps',round(d['fps'],1),'e2e_fps',round(d['e2e']['fps'],1),'stages',{k:round(v,3) for k,v in d['stage_ms'].items()},'e2e_stages',{k:round(v,3) for k,v in d['e2e'].get('stage_ms',{}).items()},'host_ms',{k:round(v,3) for k,v in d['e2e'].get('host_enqueue_ms_per_step',{}).items()},'parity',d['parity'].get('rgba_bit_identical'))" 2>&1 | tail -1)"
 }
 run c3_group_rows --steps 60 --warmup 10 --mgpu group --present rows --no-radix
 run c3_group_root --steps 60 --warmup 10 --mgpu group --present root --no-radix

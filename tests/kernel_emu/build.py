@@ -18,6 +18,7 @@ DEPS = [os.path.join(HERE, f) for f in ("kernel_emu.cpp", "cuda_shim.h", "build.
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "projection.cu"),
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "ingest.cu"),
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "present.cu"),
+    os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "group.cu"),
     os.path.join(ROOT, "godotgaussiansplatting_b200", "csrc", "common.cuh"),
 ]
 

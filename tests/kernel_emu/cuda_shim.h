@@ -86,6 +86,7 @@ template <class T> inline void __stcg(T *p, T v) { *p = v; }
 
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicExch(unsigned *p, unsigned v) { unsigned o = *p; *p = v; return o; }
 inline int atomicMax(int *p, int v) { int o = *p; *p = o < v ? v : o; return o; }
 
 inline float __fadd_rn(float a, float b) { return a + b; }

@@ -15,6 +15,7 @@ namespace gsr { void set_last_error(const char *, ...) {} }
 #include "../../godotgaussiansplatting_b200/csrc/projection.cu"
 #include "../../godotgaussiansplatting_b200/csrc/ingest.cu"
 #include "../../godotgaussiansplatting_b200/csrc/present.cu"
+#include "../../godotgaussiansplatting_b200/csrc/group.cu"
 
 namespace {
 struct Launch { const gsr::CompositeArgs *args; int variant; };
@@ -263,6 +264,25 @@ extern "C" int emu_projection_scatter(const void *soa, unsigned long long plane_
     }
     if (flags[rank].scat_ticket != 0u || flags[rank].scat_last != 0) rc = 2;   // protocol words reset for the next frame
     return rc;
+}
+
+// ---- csrc/group.cu, destination side of the scatter projection: wait for the sources' flag words, publish prefix / M / overflow / last
+//      tile, pack the receive segments.  counts_in[world] / last_in[world] are what the sources "published" (seq already matching).
+extern "C" int emu_group_receive(int world, unsigned seg_cap, unsigned capacity, const unsigned *counts_in, const unsigned *last_in, const uint32_t *rx_keys,
+                                 const uint32_t *rx_vals, uint32_t *keys, uint32_t *vals, unsigned long long *dup_total, unsigned *dup_sorted, unsigned *overflow,
+                                 int *last_plus1, unsigned *prefix_out) {
+    static gsr::GroupFlags flags;
+    memset(&flags, 0, sizeof flags);
+    for (int r = 0; r < world; ++r) { flags.seg_meta[1][r][0] = (77ull << 32) | counts_in[r]; flags.seg_meta[1][r][1] = (77ull << 32) | last_in[r]; }
+    gsr::FrameState frame;
+    memset(&frame, 0, sizeof frame);
+    struct WL { gsr::GroupFlags *f; int world; unsigned seg_cap, cap; gsr::FrameState *fr; } wl{&flags, world, seg_cap, capacity, &frame};
+    run_blocks(1, 32, [](void *p) { WL *l = static_cast<WL *>(p); gsr::group_wait_segments_kernel(l->f, 1, l->world, 77u, l->seg_cap, l->cap, l->fr, 1000ull); }, &wl);
+    struct GL { const gsr::GroupFlags *f; int world; unsigned seg_cap; const uint32_t *rk, *rv; uint32_t *k, *v; } gl{&flags, world, seg_cap, rx_keys, rx_vals, keys, vals};
+    run_blocks(3, 256, [](void *p) { GL *l = static_cast<GL *>(p); gsr::gather_segments_kernel(l->f, l->world, l->seg_cap, l->rk, l->rv, l->k, l->v); }, &gl);
+    *dup_total = frame.dup_total; *dup_sorted = frame.dup_sorted; *overflow = frame.overflow; *last_plus1 = frame.last_tile_plus1;
+    for (int r = 0; r <= world; ++r) prefix_out[r] = flags.seg_prefix[r];
+    return flags.error ? 1 : 0;
 }
 
 // ---- csrc/ingest.cu ----

@@ -459,3 +459,36 @@ def test_compositor_ticket_order_does_not_change_pixels():
             emu_composite(SPEC, fr.records, fr.values, fr.bounds, w, h, heat, tile_begin=rem * gx, row_step=3, num_tiles=rows * gx, out=out2,
                           hint=h3, longest_first=True)
     np.testing.assert_array_equal(bits(out2), bits(fr.rgba))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8, 16])
+def test_group_receive_kernels_pack_the_segments_in_source_order(world):
+    """csrc/group.cu, destination side of the scatter projection: group_wait_segments_kernel (prefix of the clamped segment lengths, M,
+    overflow, frame-global last tile) and gather_segments_kernel (segments packed in source order) -- incl. an empty and an
+    over-full segment.  Running them here also proves their warp collectives sit outside divergent code (the emulator's collectives
+    are real rendezvous: a shuffle that only some lanes reach never returns)."""
+    rng = np.random.default_rng(world)
+    seg_cap, capacity = 1000, 100000
+    counts = rng.integers(0, seg_cap + 1, size=world).astype(np.uint32)
+    counts[0] = 0
+    if world > 2:
+        counts[2] = seg_cap + 57          # the source sent more than its segment holds: kept = seg_cap, overflow flagged
+    lasts = rng.integers(0, 500, size=world).astype(np.uint32)
+    rx_k = rng.integers(0, 1 << 32, size=world * seg_cap, dtype=np.uint64).astype(np.uint32)
+    rx_v = rng.integers(0, 1 << 32, size=world * seg_cap, dtype=np.uint64).astype(np.uint32)
+    keys = np.zeros(capacity, dtype=np.uint32); vals = np.zeros(capacity, dtype=np.uint32)
+    total, m, ovf, last = C.c_ulonglong(0), C.c_uint(0), C.c_uint(0), C.c_int(0)
+    prefix = np.zeros(world + 1, dtype=np.uint32)
+    L = lib()
+    L.emu_group_receive.restype = C.c_int
+    L.emu_group_receive.argtypes = [C.c_int, C.c_uint, C.c_uint] + [C.c_void_p] * 6 + [C.c_void_p] * 5
+    rc = L.emu_group_receive(world, seg_cap, capacity, counts.ctypes.data, lasts.ctypes.data, rx_k.ctypes.data, rx_v.ctypes.data, keys.ctypes.data, vals.ctypes.data,
+                             C.byref(total), C.byref(m), C.byref(ovf), C.byref(last), prefix.ctypes.data)
+    assert rc == 0
+    kept = np.minimum(counts, seg_cap)
+    np.testing.assert_array_equal(prefix, np.concatenate([[0], np.cumsum(kept)]))
+    assert total.value == int(counts.sum()) and m.value == int(kept.sum()) and ovf.value == int((counts > seg_cap).any()) and last.value == int(lasts.max())
+    want_k = np.concatenate([rx_k[r * seg_cap: r * seg_cap + kept[r]] for r in range(world)])
+    want_v = np.concatenate([rx_v[r * seg_cap: r * seg_cap + kept[r]] for r in range(world)])
+    np.testing.assert_array_equal(keys[:m.value], want_k)
+    np.testing.assert_array_equal(vals[:m.value], want_v)
