@@ -263,6 +263,7 @@ int preload_group_kernels();
 int preload_projection_kernels();
 int preload_sort_kernels();
 int preload_ranges_kernels();
+int launch_frame_clear(FrameState *frame, unsigned long long *links, uint32_t n_links, uint2 *bounds, uint32_t n_bounds, cudaStream_t stream);
 int preload_ingest_kernels();
 int preload_present_kernels();
 int preload_composite_kernels();

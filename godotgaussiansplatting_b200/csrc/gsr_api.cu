@@ -47,6 +47,9 @@ struct gsr_ctx {
     uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
     uint32_t *comp_order = nullptr, *comp_hint = nullptr;   // longest-chain-first ticket order of the compositor + last frame's consumed chunks
     int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1, comp_sparse_per_sm = 5;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
+#ifdef GSR_GROUP_PROBE
+    cudaEvent_t probe_ev[GSR_HISTORY_FRAMES][2] = {};   // ubench builds only: after the scatter kernel, after the segment wait
+#endif
     uint64_t comp_hint_key = 0;   // ownership (band, rows) the hints were recorded under: a change invalidates them
     FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
     ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
@@ -505,9 +508,22 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     const uint32_t slot = (uint32_t)(c->frame_counter % GSR_HISTORY_FRAMES);
     c->frame = c->ring + slot;
     cudaEvent_t *ev = c->ev + 5 * slot;
-    GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * projection_num_blocks((uint32_t)c->max_splats), s));
-    GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
+    {   // one clear kernel: the frame's counters, the scan links this frame's projection uses, the tile bounds
+        uint32_t links = projection_num_blocks((uint32_t)c->max_splats);
+        if (gf) {
+            const uint64_t first = (uint64_t)c->grp.rank * c->grp.slice;
+            const uint64_t count = first < c->max_splats ? ((c->max_splats - first) < c->grp.slice ? (c->max_splats - first) : c->grp.slice) : 0;
+            links = projection_scatter_blocks((uint32_t)count) * (uint32_t)c->grp.world;
+        }
+#ifdef GSR_FRAME_CLEAR_MEMSET
+        GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
+        GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * links, s));
+        GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
+#else
+        if ((rc = launch_frame_clear(c->frame, c->lookback, links, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), s))) return rc;
+        launches += 1;
+#endif
+    }
     GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
 
     ProjectionArgs pa;
@@ -552,10 +568,16 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
             sp.flags[d] = c->grp.flags[d];
         }
         sp.lookback = c->lookback;
-        GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * (size_t)projection_scatter_blocks(sp.count) * G, s));
         if ((rc = launch_projection_scatter(pa, sp, s))) return rc;
+#ifdef GSR_GROUP_PROBE
+        for (int k = 0; k < 2; ++k) if (!c->probe_ev[slot][k]) cudaEventCreate(&c->probe_ev[slot][k]);
+        cudaEventRecord(c->probe_ev[slot][0], s);
+#endif
         char *mine = c->grp.peer_arena[c->grp.rank];
         if ((rc = launch_group_wait_segments(c->grp.flags[c->grp.rank], gf->parity, G, gf->seq, c->grp.seg_cap, (uint32_t)c->capacity, c->frame, s))) return rc;
+#ifdef GSR_GROUP_PROBE
+        cudaEventRecord(c->probe_ev[slot][1], s);
+#endif
         if ((rc = launch_gather_segments(c->grp.flags[c->grp.rank], G, c->grp.seg_cap,
                                          reinterpret_cast<const uint32_t *>(mine + arena_rx_keys_off(c->grp.rx_capacity, gf->parity)),
                                          reinterpret_cast<const uint32_t *>(mine + arena_rx_vals_off(c->grp.rx_capacity, gf->parity)), c->keys, c->vals,
@@ -1096,6 +1118,25 @@ GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t
     c->comp_ctas_per_sm = ctas_per_sm ? ctas_per_sm : c->comp_max_ctas; c->comp_order_mode = longest_first != 0; c->comp_sparse_per_sm = sparse_tiles_per_sm;
     return GSR_OK;
 }
+
+#ifdef GSR_GROUP_PROBE
+// ubench builds only: mean (scatter kernel, segment wait, gather) ms over the frames of the history ring (call after gsr_sync)
+GSR_API int gsr_debug_group_probe(gsr_ctx *c, float out[3]) {
+    if (!c || !out) return GSR_ERR_INVALID;
+    double acc[3] = {0, 0, 0}; int n = 0;
+    for (uint32_t slot = 0; slot < GSR_HISTORY_FRAMES; ++slot) {
+        if (!c->probe_ev[slot][0] || !c->probe_ev[slot][1]) continue;
+        cudaEvent_t *ev = c->ev + 5 * slot;
+        float a, b, d;
+        if (cudaEventElapsedTime(&a, ev[0], c->probe_ev[slot][0]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cudaEventElapsedTime(&b, c->probe_ev[slot][0], c->probe_ev[slot][1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cudaEventElapsedTime(&d, c->probe_ev[slot][1], ev[1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        acc[0] += a; acc[1] += b; acc[2] += d; ++n;
+    }
+    for (int k = 0; k < 3; ++k) out[k] = n ? (float)(acc[k] / n) : 0.f;
+    return GSR_OK;
+}
+#endif
 
 GSR_API int gsr_debug_enable_trace(gsr_ctx *c, uint32_t max_items) {
     if (!c) return GSR_ERR_INVALID;

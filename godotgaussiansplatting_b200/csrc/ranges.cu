@@ -122,15 +122,39 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2 *__restric
     if (hint) for (int32_t k = (int32_t)tid; k < num_tiles; k += 1024) hint[k] &= 0x7FFFFFFFu;   // consumed: the compositor sets bit 31 again
 }
 
+// Start of a frame (rasterizer.gd:127-128): this frame's counters, the projection's scan links and the tile bounds back to zero.
+// One kernel instead of three cudaMemsetAsync: fewer stream operations per frame, and nothing on the render stream that the
+// driver may hand to a copy engine (where it would queue behind a frame read-back in flight).
+__global__ void __launch_bounds__(256) frame_clear_kernel(unsigned long long *frame_words, uint32_t n_frame, unsigned long long *links, uint32_t n_links,
+                                                            unsigned long long *bounds, uint32_t n_bounds) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 < n_frame) frame_words[i0] = 0ull;
+    for (uint32_t i = i0; i < n_links; i += stride) links[i] = 0ull;
+    for (uint32_t i = i0; i < n_bounds; i += stride) bounds[i] = 0ull;
+}
+
 }  // namespace
 
 #ifndef GSR_CPU_EMU  // tests/kernel_emu compiles the kernels above for the CPU; the launchers are CUDA only
+int launch_frame_clear(FrameState *frame, unsigned long long *links, uint32_t n_links, uint2 *bounds, uint32_t n_bounds, cudaStream_t stream) {
+    static_assert(sizeof(FrameState) % 8 == 0 && sizeof(uint2) == 8, "cleared as 64-bit words");
+    const uint32_t most = n_links > n_bounds ? n_links : n_bounds;
+    uint32_t grid = (most + 255u) / 256u;
+    grid = grid < 1u ? 1u : (grid > 296u ? 296u : grid);
+    frame_clear_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<unsigned long long *>(frame), (uint32_t)(sizeof(FrameState) / 8), links, n_links,
+                                                 reinterpret_cast<unsigned long long *>(bounds), n_bounds);
+    GSR_CUDA_TRY(cudaGetLastError());
+    return GSR_OK;
+}
+
 // Force-load this file's kernels (CUDA loads modules lazily; see gsr_create).
 int preload_ranges_kernels() {
     cudaFuncAttributes fa;
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_ranges_kernel));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, band_fixup_kernel));
     GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, tile_order_kernel));
+    GSR_CUDA_TRY(cudaFuncGetAttributes(&fa, frame_clear_kernel));
     return GSR_OK;
 }
 
