@@ -47,12 +47,12 @@ def parse_args():
     ap.add_argument("--splats", type=int, default=int(os.environ.get("GSR_BENCH_SPLATS", "0")), help="debug: override N (marks the line reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-radix", action="store_true")
-    ap.add_argument("--present", default=os.environ.get("GSR_BENCH_PRESENT", "root"), choices=["root", "rows"],
+    ap.add_argument("--present", default="rows", choices=["root", "rows"],
                     help="group mode, e2e: 'root' = the frame is assembled on rank 0's device and read back over its PCIe link; 'rows' = every rank "
                          "reads its own tile rows back into one shared page-locked host frame (a PCIe link per GPU)")
-    ap.add_argument("--mgpu", default=os.environ.get("GSR_BENCH_MGPU", "peer"), choices=["group", "peer", "nccl"],
-                    help="N>1: 'group' = NCCL-free shard group (cull split across the ranks, extents exchanged and rows composited over "
-                         "NVLink peer memory, device-side flags); 'peer' = replicated cull, compositor stores bands into the root's frame over "
+    ap.add_argument("--mgpu", default="group", choices=["group", "peer", "nccl"],
+                    help="N>1: 'group' (default) = NCCL-free shard group (projection sharded by splats, every rank scatters its pairs and records "
+                         "into the row owners' memory over NVLink peer pointers, device-side flags); 'peer' = round-1 path: replicated cull, compositor stores bands into the root's frame over "
                          "NVLink peer memory + 4-byte NCCL sync; 'nccl' = NCCL gather of the band framebuffers")
     return ap.parse_args()
 
@@ -103,11 +103,11 @@ def make_config(args, wl):
         par = f"tile-row bands x{args.gpus} + NCCL framebuffer gather"
     else:
         par = (f"cyclic tile rows x{args.gpus} (row % {args.gpus} == rank), " +
-               ("cull split across the ranks, row extents exchanged with peer stores, device-side flags (no NCCL on the frame path)" if args.mgpu == "group"
+               ("projection sharded by splats, pairs + records scattered to the row owners over NVLink peer stores, device-side flags (no NCCL on the frame path)" if args.mgpu == "group"
                 else "replicated cull with early reject, 4-byte NCCL all-reduce per frame") +
                ", compositor stores into the root frame over NVLink peer memory")
     if args.gpus > 1 and args.mgpu == "group" and args.present == "rows":
-        par += "; e2e: every rank reads its own rows back into one shared page-locked host frame"
+        par += "; e2e: every rank reads its own rows back into one shared page-locked host frame (device-resident leg: frame assembled in rank 0's HBM)"
     return {"workload": f"{args.workload}: {wl['desc']}", "splats": wl["n"], "width": wl["w"], "height": wl["h"], "sh_degree": 3,
             "parallelism": par, "reduced": bool(args.splats),
             "l2": "inputs larger than L2 (SoA splats %.0f MB + records + pairs per frame >> 126 MB)" % (240 * wl["n"] / 1e6)}
@@ -407,7 +407,7 @@ def main():
     peer = world > 1 and args.mgpu == "peer"
     sync_flag = torch.zeros(1, dtype=torch.int32, device="cuda") if world > 1 else None
     if group:
-        # NCCL-free frame path: every rank exports its arena (flag page + extent tables) and frames, the blobs are all-gathered
+        # NCCL-free frame path: every rank exports its arena (flag page + receive segments + record tables) and frames, the blobs are all-gathered
         # ONCE here, and from then on the ranks talk through NVLink peer memory only (include/gsr.h gsr_group_*)
         from godotgaussiansplatting_b200 import _lib as _gl
         mine = torch.frombuffer(bytearray(rast.group_export()), dtype=torch.uint8).cuda()
@@ -467,7 +467,7 @@ def main():
         if world == 1:
             rast.render_raw(vp, ub, 0.0, pinned2[i & 1].data_ptr() if e2e else None, asynchronous=True, rgb_only=rgb)
         elif group:
-            rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # extents + rows travel over NVLink; flags order the ranks on the devices
+            rast.render_raw(vp, ub, 0.0, None, asynchronous=True)  # pairs, records and rows travel over NVLink; flags order the ranks on the devices
             if e2e and shared2 is not None and not rgb:
                 rast.readback_rows_async(shared2[i & 1].data_ptr())   # every rank: its own rows, its own PCIe link
             elif e2e and rank == 0:
@@ -543,6 +543,8 @@ def main():
     peak, peak_src = measured_peak_gbs()
     band_frac = (band[1] - band[0]) / tiles_y
     bytes_proj = 16 * N + 224 * V + 36 * V + 8 * M
+    if group:   # this rank's slice of the splats (V = its visible ones); records to one owner at least; pairs stored once (M: received ~ emitted) + packed (16 M)
+        bytes_proj = 16 * N / world + 224 * V + 48 * V + 8 * M + 16 * M
     bytes_sort = 68 * M
     bytes_ranges = 4 * M + 8 * T * band_frac
     bytes_comp = 40 * Cc + 16 * P * band_frac + 8 * T * band_frac
@@ -552,8 +554,11 @@ def main():
 
     dominant = max(("Projection", "Sort", "Render"), key=lambda k: stage[k])
     dom_bytes = {"Projection": bytes_proj, "Sort": bytes_sort, "Render": bytes_comp}[dominant]
+    proj_name = "projection_scatter_kernel + segment wait + gather_segments_kernel" if group else "projection_kernel"
     traffic, traffic_src = profiled_traffic({"Projection": "projection_kernel", "Sort": "onesweep_kernel", "Render": "composite_kernel"}[dominant])
-    roofline = {"kernel": {"Projection": "projection_kernel", "Sort": "sort_hist_kernel + 4x onesweep_kernel", "Render": "composite_kernel"}[dominant],
+    if group and dominant == "Projection":
+        traffic, traffic_src = None, "no single-GPU ncu capture of the scatter projection (its stores go to peer memory)"
+    roofline = {"kernel": {"Projection": proj_name, "Sort": "sort_hist_kernel + 4x onesweep_kernel", "Render": "composite_kernel"}[dominant],
                 "bound": "hbm", "achieved": gbs(dom_bytes, stage[dominant]), "peak": peak, "unit": "GB/s",
                 "frac": gbs(dom_bytes, stage[dominant]) / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": ("the compositor is FP32-issue/FMA-pipe bound, not HBM bound (ncu: FMA pipe ~55-70 % of active cycles, DRAM 4 %); its HBM "
