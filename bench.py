@@ -54,6 +54,8 @@ def parse_args():
                     help="N>1: 'group' (default) = NCCL-free shard group (projection sharded by splats, every rank scatters its pairs and records "
                          "into the row owners' memory over NVLink peer pointers, device-side flags); 'peer' = round-1 path: replicated cull, compositor stores bands into the root's frame over "
                          "NVLink peer memory + 4-byte NCCL sync; 'nccl' = NCCL gather of the band framebuffers")
+    ap.add_argument("--overlap", type=int, default=-1, choices=[-1, 0, 1],
+                    help="front/back overlap of consecutive frames (gsr_debug_pipeline): -1 = the library's default (on in a shard group)")
     return ap.parse_args()
 
 
@@ -378,7 +380,7 @@ def main():
         dist.barrier()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     # one dedicated (non-default) stream carries libgsr's kernels, the NCCL gather and the timing events
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream(priority=-1)   # the render stream outranks libgsr's front stream (next frame's projection): freed SM slots go to the back part first
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
 
@@ -394,6 +396,8 @@ def main():
     rast = GaussianSplattingRasterizer(stub, (W, H), RenderTexture(), default_camera(aspect=W / H), device=local_rank)
     rast.init_gpu(load=False)
     rast.set_stream(stream.cuda_stream)
+    if args.overlap >= 0:
+        rast.debug_pipeline(args.overlap)
     keep_host = rank == 0 and not args.no_cpu_baseline   # N > 1: rank 0 keeps the scene for the one-frame parity check of the assembled frame
     host_chunks = []
     t_gen = time.perf_counter()
@@ -649,7 +653,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": fps,
             "config": make_config(args, wl),
-            "run_info": {"duplicates_M": M, "visible_V": V, "staged_C": Cc, "scene_build_s": t_gen},
+            "run_info": {"duplicates_M": M, "visible_V": V, "staged_C": Cc, "scene_build_s": t_gen,
+                         "frame_overlap": ("on" if (args.overlap == 1 or (args.overlap < 0 and group)) else "off") +
+                                          ": projection of frame f+1 beside the compositor of frame f (gsr_debug_pipeline; stage_ms are per-stage GPU times, their sum exceeds the frame period when on)"},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),
                     "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * 16,
                     "stage_ms": {nm: float(np.mean([r.stage_ms[i] for r in hist_e2e])) for i, nm in enumerate(names)},

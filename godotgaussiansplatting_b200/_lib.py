@@ -21,7 +21,7 @@ EXPORTS = [
     "gsr_create", "gsr_destroy", "gsr_set_stream", "gsr_upload_splats_aos", "gsr_upload_ply_raw", "gsr_resize", "gsr_set_band", "gsr_set_row_interleave", "gsr_band_sync_word", "gsr_band_fixup", "gsr_render",
     "gsr_render_async", "gsr_render_async_rgb", "gsr_render_async_fmt", "gsr_output_bytes", "gsr_present_device", "gsr_readback_async", "gsr_peer_export_framebuffers", "gsr_peer_import_framebuffers",
     "gsr_stream_join", "gsr_group_export", "gsr_group_attach", "gsr_group_detach", "gsr_group_set_present", "gsr_readback_rows_async", "gsr_sync", "gsr_framebuffer_device_ptr", "gsr_set_framebuffer_external", "gsr_pick",
-    "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_compositor_config", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
+    "gsr_get_stats", "gsr_get_frame_history", "gsr_debug_copy", "gsr_debug_enable_trace", "gsr_debug_compositor_config", "gsr_debug_pipeline", "gsr_debug_keep_unsorted", "gsr_sorter_create", "gsr_sorter_destroy",
     "gsr_sorter_sort_device", "gsr_sort_pairs_host", "gsr_sorter_last_ms", "gsr_error_string", "gsr_last_error",
     "gsr_device_count", "gsr_version",
 ]
@@ -47,7 +47,7 @@ GSR_GROUP_BLOB_BYTES = 320
 
 class GsrFrameRecord(C.Structure):
     _fields_ = [("frame_index", C.c_uint64), ("duplicates", C.c_uint64), ("visible", C.c_uint64), ("staged", C.c_uint64),
-                ("overflow", C.c_uint32), ("reserved", C.c_uint32), ("stage_ms", C.c_float * 5), ("reserved2", C.c_float)]
+                ("overflow", C.c_uint32), ("reserved", C.c_uint32), ("stage_ms", C.c_float * 5), ("front_ms", C.c_float)]
 
 
 class GsrError(RuntimeError):
@@ -106,6 +106,7 @@ def lib():
         L.gsr_debug_keep_unsorted.argtypes = [vp, C.c_int]
         L.gsr_debug_enable_trace.argtypes = [vp, u32]
         L.gsr_debug_compositor_config.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+        L.gsr_debug_pipeline.argtypes = [vp, C.c_int32]
         L.gsr_sorter_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp)]
         L.gsr_sorter_destroy.argtypes = [vp]
         L.gsr_sorter_sort_device.argtypes = [vp, vp, vp, C.c_uint64, vp]

@@ -158,14 +158,18 @@ struct ProjectionArgs {
 int launch_projection(const ProjectionArgs &a, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
-// multi-GPU shard group (group.cu, gsr_group_attach): flag words + extent tables in every rank's arena
+// multi-GPU shard group (group.cu, gsr_group_attach): flag words + receive segments + record tables in every rank's arena
 // ---------------------------------------------------------------------------------------------
 constexpr int GROUP_MAX = 16;                                   // ranks per group (one NVSwitch domain)
+// Receive segments and record tables exist three times (frame seq % 3): a source's scatter projection of frame f+1 runs while the
+// destinations still composite frame f (front / back overlap, gsr_api.cu), and frame f-1's consumers are only known to be done
+// through the chain  scatter(f+1) after own ranges(f) after all sources' scatter(f) after their ranges(f-1) after their compositor(f-2).
+constexpr int GROUP_PHASES = 3;
 #define GSR_GROUP_TIMEOUT_NS 2000000000ull                      // every device-side wait gives up after 2 s
 struct GroupFlags {                                             // offset 0 of a rank's arena; written by the peers over NVLink
-    // [frame parity][source rank][0] = seq << 32 | pairs the source sent to THIS rank's receive segment,
-    //                            [1] = seq << 32 | (largest tile id touched by the source's splats + 1)
-    unsigned long long seg_meta[2][GROUP_MAX][2];
+    // [frame phase = seq % 3][source rank][0] = seq << 32 | pairs the source sent to THIS rank's receive segment,
+    //                                     [1] = seq << 32 | (largest tile id touched by the source's splats + 1)
+    unsigned long long seg_meta[GROUP_PHASES][GROUP_MAX][2];
     uint32_t done[GROUP_MAX];               // presenting rank: done[r] = seq of the newest frame whose rows from rank r have landed
     uint32_t released;                      // set by the presenting rank: frames with seq <= released no longer need their slot
     uint32_t error;                         // local: a wait timed out (1 = segments of a peer, 2 = done / released)
@@ -174,14 +178,14 @@ struct GroupFlags {                                             // offset 0 of a
     unsigned long long seg_total[GROUP_MAX];  // local: pairs this rank sent to each destination this frame (scan total)
     uint32_t seg_prefix[GROUP_MAX + 1];     // local: exclusive prefix of the received (clamped) segment lengths, [world] = M of this rank
 };
-constexpr size_t GROUP_FLAGS_BYTES = 4096;                      // the two extent tables follow the flag page
+constexpr size_t GROUP_FLAGS_BYTES = 4096;                      // the receive segments and record tables follow the flag page
 static_assert(sizeof(GroupFlags) <= GROUP_FLAGS_BYTES, "flag page");
 struct GroupPeers {                                             // the same pointers on every rank, indexed by rank
     GroupFlags *flags[GROUP_MAX];
     int world, rank;
 };
 // What the scatter projection of one rank needs to know about the group: every destination's record table and receive segment
-// (peer pointers) of the current frame parity, and this rank's slice of the splats.
+// (peer pointers) of the current frame phase (seq % 3; called parity below), and this rank's slice of the splats.
 struct ScatterPeers {
     int world, rank, parity;
     uint32_t seq;

@@ -29,15 +29,26 @@ void set_last_error(const char *fmt, ...) {
 
 using namespace gsr;
 
+constexpr int EV_PER_FRAME = 7;
+
 struct gsr_ctx {
     int device = 0;
     uint32_t flags = 0;
     uint64_t max_splats = 0, capacity = 0, plane_stride = 0, num_splats = 0;
+    uint64_t cap_stride = 0;     // capacity rounded up to 1024 pairs: distance between the three pair buffers (keeps each 16-byte aligned)
     cudaStream_t stream = nullptr, own_stream = nullptr;
     float4 *soa = nullptr;       // 15 planes x plane_stride
-    float4 *records = nullptr;   // 3 float4 per splat id
-    uint32_t *keys = nullptr;    // 2 * capacity (ping-pong halves, rasterizer.gd:88)
-    uint32_t *vals = nullptr;    // 2 * capacity
+    float4 *records = nullptr;   // 3 float4 per splat id; two tables (consecutive frames alternate: front / back overlap)
+    float4 *records2 = nullptr;
+    uint32_t *keys = nullptr;    // 3 * capacity: sort input of even frames | of odd frames | ping-pong partner (rasterizer.gd:88 has two halves)
+    uint32_t *vals = nullptr;    // 3 * capacity
+    uint32_t *keys_cur = nullptr, *vals_cur = nullptr;   // sorted pairs of the most recent frame
+    float4 *records_cur = nullptr;                       // record table the most recent frame composited from
+    // front / back overlap: the projection of frame f+1 (front: HBM-bound) runs on its own stream beside the compositor of frame f
+    // (back: FMA-pipe / chain bound) when the host enqueues frames back to back (gsr_render_async).  gsr_debug_pipeline(ctx, 0) = serial.
+    cudaStream_t front_stream = nullptr;
+    cudaEvent_t front_gate = nullptr;    // recorded after the tile ranges of the most recent frame (nullptr: nothing to wait for)
+    int overlap = -1;                    // -1 = automatic: on for a context attached to a shard group, off otherwise (measured: DESIGN.md section 6)
     SortWorkspace sort;
     FrameState *ring = nullptr;  // GSR_HISTORY_FRAMES slots; slot = frame_counter % GSR_HISTORY_FRAMES
     FrameState *frame = nullptr; // slot of the most recent frame
@@ -47,9 +58,6 @@ struct gsr_ctx {
     uint2 *bounds = nullptr;     // followed in the same allocation by the compositor queue (one memset per frame)
     uint32_t *comp_order = nullptr, *comp_hint = nullptr;   // longest-chain-first ticket order of the compositor + last frame's consumed chunks
     int comp_ctas_per_sm = 2, comp_order_mode = 1, comp_max_ctas = 1, comp_sparse_per_sm = 5;   // scheduling of the compositor's persistent grid (gsr_debug_compositor_config)
-#ifdef GSR_GROUP_PROBE
-    cudaEvent_t probe_ev[GSR_HISTORY_FRAMES][2] = {};   // ubench builds only: after the scatter kernel, after the segment wait
-#endif
     uint64_t comp_hint_key = 0;   // ownership (band, rows) the hints were recorded under: a change invalidates them
     FrameState *pick_frame = nullptr;  // queue counters of the single-tile pick launch
     ulonglong4 *trace = nullptr;       // GSR_BUF_COMPOSITOR_TRACE (debug; allocated by gsr_debug_enable_trace)
@@ -90,9 +98,8 @@ struct gsr_ctx {
         uint32_t seq = 0;                 // frames rendered by the group so far (lockstep on all ranks)
         uint64_t slice = 0;               // splats per rank (256-aligned)
         uint32_t seg_cap = 0;             // pairs one source may send to one destination per frame
-        float4 *records_cur = nullptr;    // record table (of this rank's arena) the most recent frame composited from
     } grp;
-    cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][5]
+    cudaEvent_t *ev = nullptr;   // [GSR_HISTORY_FRAMES][EV_PER_FRAME]: front start, front end | back start, received, sorted, ranges, rendered
     // dynamic duplicate capacity (replaces the reference's static 10 x N, rasterizer.gd:79 "FIXME: This should not be a static
     // value!"): every frame's M travels to a pinned host mirror without a host sync; the capacity grows ahead of need
     FrameState *host_ring = nullptr;       // pinned mirror of `ring`
@@ -140,6 +147,7 @@ int check_device(int device) {
 }
 
 void group_detach(gsr_ctx *c) {
+    if (c->front_stream) cudaStreamSynchronize(c->front_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (int i = 0; i < c->grp.n_opened; ++i) cudaIpcCloseMemHandle(c->grp.opened[i]);
@@ -155,7 +163,8 @@ void free_ctx(gsr_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->soa); cudaFree(c->records); cudaFree(c->keys); cudaFree(c->vals);
+    if (c->front_stream) { cudaStreamSynchronize(c->front_stream); cudaStreamDestroy(c->front_stream); }
+    cudaFree(c->soa); cudaFree(c->records); cudaFree(c->records2); cudaFree(c->keys); cudaFree(c->vals);
     sort_workspace_destroy(c->sort);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->peer_opened) { cudaIpcCloseMemHandle(c->peer_fb[0]); cudaIpcCloseMemHandle(c->peer_fb[1]); }
@@ -168,7 +177,7 @@ void free_ctx(gsr_ctx *c) {
     cudaFree(c->grp.arena);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); cudaFree(c->trace); cudaFree(c->trace_count);
     if (c->ev) {
-        for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        for (int i = 0; i < GSR_HISTORY_FRAMES * EV_PER_FRAME; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         delete[] c->ev;
     }
     if (c->ev_stat) {
@@ -234,10 +243,20 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
         }                                                                                          \
     } while (0)
 
-    cudaError_t se = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    cudaError_t se;
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        se = cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, greatest);
+    }
     if (se != cudaSuccess) { set_last_error("cudaStreamCreate -> %s", cudaGetErrorString(se)); free_ctx(c); return GSR_ERR_CUDA; }
     c->stream = c->own_stream;
     se = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (se == cudaSuccess) {   // the front stream yields to the render stream wherever the host gave that one a higher priority
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        se = cudaStreamCreateWithPriority(&c->front_stream, cudaStreamNonBlocking, least);
+    }
     for (int i = 0; i < 2 && se == cudaSuccess; ++i) {
         se = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
         if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
@@ -245,8 +264,11 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     if (se != cudaSuccess) { set_last_error("copy stream/events -> %s", cudaGetErrorString(se)); free_ctx(c); return GSR_ERR_CUDA; }
     TRY_ALLOC(c->soa, sizeof(float4) * NUM_PLANES * c->plane_stride);
     TRY_ALLOC(c->records, sizeof(float4) * 3ull * c->max_splats);
-    TRY_ALLOC(c->keys, sizeof(uint32_t) * 2ull * c->capacity);
-    TRY_ALLOC(c->vals, sizeof(uint32_t) * 2ull * c->capacity);
+    TRY_ALLOC(c->records2, sizeof(float4) * 3ull * c->max_splats);
+    c->cap_stride = (c->capacity + 1023ull) & ~1023ull;
+    TRY_ALLOC(c->keys, sizeof(uint32_t) * 3ull * c->cap_stride);
+    TRY_ALLOC(c->vals, sizeof(uint32_t) * 3ull * c->cap_stride);
+    c->keys_cur = c->keys; c->vals_cur = c->vals; c->records_cur = c->records;
     c->lookback_blocks = projection_num_blocks((uint32_t)c->max_splats);  // one scan link per CTA
     TRY_ALLOC(c->ring, sizeof(FrameState) * GSR_HISTORY_FRAMES);
     TRY_ALLOC(c->lookback, sizeof(unsigned long long) * ((size_t)c->lookback_blocks + 2u * GROUP_MAX * GROUP_MAX));  // scatter mode: (N/G/256 + 1) x G links
@@ -258,9 +280,9 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
 #undef TRY_ALLOC
     rc = sort_workspace_create(c->sort, c->capacity, /*need_alt_buffers=*/false);
     if (rc) { free_ctx(c); return rc; }
-    c->ev = new (std::nothrow) cudaEvent_t[GSR_HISTORY_FRAMES * 5]();
+    c->ev = new (std::nothrow) cudaEvent_t[GSR_HISTORY_FRAMES * EV_PER_FRAME]();
     if (!c->ev) { free_ctx(c); return GSR_ERR_OOM; }
-    for (int i = 0; i < GSR_HISTORY_FRAMES * 5; ++i) {
+    for (int i = 0; i < GSR_HISTORY_FRAMES * EV_PER_FRAME; ++i) {
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { set_last_error("cudaEventCreate failed"); free_ctx(c); return GSR_ERR_CUDA; }
     }
     c->ev_stat = new (std::nothrow) cudaEvent_t[GSR_HISTORY_FRAMES]();
@@ -274,6 +296,7 @@ GSR_API int gsr_create(const gsr_config *cfg, gsr_ctx **out) {
     memset(c->host_ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES);
     cudaMemsetAsync(c->soa, 0, sizeof(float4) * NUM_PLANES * c->plane_stride, c->stream);
     cudaMemsetAsync(c->records, 0, sizeof(float4) * 3ull * c->max_splats, c->stream);
+    cudaMemsetAsync(c->records2, 0, sizeof(float4) * 3ull * c->max_splats, c->stream);
     cudaMemsetAsync(c->pick, 0, sizeof(float4), c->stream);
     cudaMemsetAsync(c->sync_word, 0, sizeof(int32_t), c->stream);
     cudaMemsetAsync(c->ring, 0, sizeof(FrameState) * GSR_HISTORY_FRAMES, c->stream);
@@ -296,9 +319,10 @@ GSR_API int gsr_set_stream(gsr_ctx *c, void *cuda_stream) {
     if (!c) return GSR_ERR_INVALID;
     int rc = use_device(c->device);
     if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->front_stream));
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
-    c->ev_valid = false;
+    c->ev_valid = false; c->front_gate = nullptr;
     return GSR_OK;
 }
 
@@ -307,6 +331,7 @@ GSR_API int gsr_upload_splats_aos(gsr_ctx *c, const float *splat60, uint64_t fir
     if (count > c->max_splats || first > c->max_splats - count) { set_last_error("upload range [%llu,%llu) exceeds max_splats %llu", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)c->max_splats); return GSR_ERR_INVALID; }
     int rc = use_device(c->device);
     if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->front_stream));   // a projection in flight reads the planes this call rewrites
     uint64_t done = 0;
     while (done < count) {
         const uint64_t m = (count - done) < c->staging_splats ? (count - done) : c->staging_splats;
@@ -328,6 +353,7 @@ GSR_API int gsr_upload_ply_raw(gsr_ctx *c, const float *ply, uint32_t nprops, ui
     const uint64_t staging_floats = c->staging_splats * 60ull;  // the AoS staging buffer, reused for raw vertices
     const uint64_t per = staging_floats / nprops;
     if (per == 0) { set_last_error("gsr_upload_ply_raw: staging buffer too small"); return GSR_ERR_INVALID; }
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->front_stream));   // a projection in flight reads the planes this call rewrites
     uint64_t done = 0;
     while (done < count) {
         const uint64_t m = (count - done) < per ? (count - done) : per;
@@ -349,7 +375,9 @@ GSR_API int gsr_resize(gsr_ctx *c, int32_t width, int32_t height) {
     }
     int rc = use_device(c->device);
     if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->front_stream));
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->front_gate = nullptr;
     c->width = c->height = c->tiles_x = c->tiles_y = 0;  // a failure below leaves the context in the "before gsr_resize" state
     cudaFree(c->bounds); c->bounds = nullptr;
     cudaFree(c->comp_order); c->comp_order = nullptr;
@@ -440,15 +468,19 @@ static void frame_constants(const float *view_proj, const Uniforms &u, Projectio
 static int grow_capacity(gsr_ctx *c, uint64_t want) {
     if (want > c->capacity_max) want = c->capacity_max;
     if (want <= c->capacity) return GSR_OK;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->front_stream));
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     GSR_CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
-    cudaFree(c->keys); cudaFree(c->vals); c->keys = c->vals = nullptr;
+    c->front_gate = nullptr;
+    cudaFree(c->keys); cudaFree(c->vals); c->keys = c->vals = c->keys_cur = c->vals_cur = nullptr;
     sort_workspace_destroy(c->sort);
     const bool unsorted = c->unsorted_keys != nullptr;
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals); c->unsorted_keys = c->unsorted_vals = nullptr;
     c->capacity = want;
-    GSR_CUDA_TRY(cudaMalloc((void **)&c->keys, sizeof(uint32_t) * 2ull * c->capacity));
-    GSR_CUDA_TRY(cudaMalloc((void **)&c->vals, sizeof(uint32_t) * 2ull * c->capacity));
+    c->cap_stride = (c->capacity + 1023ull) & ~1023ull;
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->keys, sizeof(uint32_t) * 3ull * c->cap_stride));
+    GSR_CUDA_TRY(cudaMalloc((void **)&c->vals, sizeof(uint32_t) * 3ull * c->cap_stride));
+    c->keys_cur = c->keys; c->vals_cur = c->vals;
     if (unsorted) {
         GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_keys, sizeof(uint32_t) * c->capacity));
         GSR_CUDA_TRY(cudaMalloc((void **)&c->unsorted_vals, sizeof(uint32_t) * c->capacity));
@@ -474,11 +506,27 @@ static int track_capacity(gsr_ctx *c) {
 
 struct GroupFrame { uint32_t seq; int parity; int rows_local; };
 
+// GPU time of one frame's stages from its events: 'Projection' = front part (clear + projection kernel, on the front stream when frames
+// overlap) + receive (group mode: segment wait + gather); total = the sum of the stages = GPU time attributable to the frame (with
+// overlap the frame PERIOD is shorter than that: the front part runs beside the previous frame's compositor).
+static int stage_times(gsr_ctx *c, uint32_t slot, float out[5], float *front_ms) {
+    cudaEvent_t *ev = c->ev + EV_PER_FRAME * slot;
+    float front = 0.f, recv = 0.f;
+    GSR_CUDA_TRY(cudaEventElapsedTime(&front, ev[0], ev[1]));
+    GSR_CUDA_TRY(cudaEventElapsedTime(&recv, ev[2], ev[3]));
+    out[0] = front + recv;
+    for (int i = 1; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&out[i], ev[2 + i], ev[3 + i]));
+    out[4] = out[0] + out[1] + out[2] + out[3];
+    if (front_ms) *front_ms = front;
+    return GSR_OK;
+}
+
 // arena layout (identical on every rank of a group: same max_splats, same rx_capacity)
+// (`parity` = frame phase seq % GROUP_PHASES)
 static size_t arena_rx_keys_off(uint64_t cap, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * (size_t)parity; }
-static size_t arena_rx_vals_off(uint64_t cap, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * (size_t)(2 + parity); }
-static size_t arena_records_off(uint64_t cap, uint64_t max_splats, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * 4 + sizeof(float4) * 3ull * max_splats * (size_t)parity; }
-static size_t arena_bytes(uint64_t cap, uint64_t max_splats) { return arena_records_off(cap, max_splats, 2); }
+static size_t arena_rx_vals_off(uint64_t cap, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * (size_t)(GROUP_PHASES + parity); }
+static size_t arena_records_off(uint64_t cap, uint64_t max_splats, int parity) { return GROUP_FLAGS_BYTES + sizeof(uint32_t) * cap * 2 * GROUP_PHASES + sizeof(float4) * 3ull * max_splats * (size_t)parity; }
+static size_t arena_bytes(uint64_t cap, uint64_t max_splats) { return arena_records_off(cap, max_splats, GROUP_PHASES); }
 
 static GroupPeers group_peers(const gsr_ctx *c, int parity) {
     (void)parity;
@@ -503,28 +551,39 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     if (rc) return rc;
     if ((rc = track_capacity(c))) return rc;
     cudaStream_t s = c->stream;
+    // Front / back overlap.  The front part of a frame (clear + projection: HBM-bound) needs nothing from the frame before it, the back
+    // part (sort, ranges, compositor) nothing from the frame after it.  With overlap on, the front part runs on its own stream and
+    // is released when the PREVIOUS frame's tile ranges are done: it then shares the GPU with that frame's compositor (FMA-pipe /
+    // chain bound, 1-2 small CTAs per SM), which leaves the memory system idle.  Consecutive frames alternate between two sort
+    // inputs and two record tables; the back part waits for its own front part.  A host that renders one frame at a time
+    // (gsr_render) sees the same kernels in the same order.
+    const bool overlap = (c->overlap < 0 ? gf != nullptr : c->overlap != 0) && c->front_stream != nullptr;
+    cudaStream_t fs = overlap ? c->front_stream : s;
     int launches = 0;
-    // rasterizer.gd:127-128: clear M (this frame's history slot) + look-back words, clear tile bounds
     const uint32_t slot = (uint32_t)(c->frame_counter % GSR_HISTORY_FRAMES);
     c->frame = c->ring + slot;
-    cudaEvent_t *ev = c->ev + 5 * slot;
-    {   // one clear kernel: the frame's counters, the scan links this frame's projection uses, the tile bounds
+    cudaEvent_t *ev = c->ev + EV_PER_FRAME * slot;
+    const int half = (int)(c->frame_counter & 1u);
+    uint32_t *keys_in = c->keys + (size_t)half * c->cap_stride, *vals_in = c->vals + (size_t)half * c->cap_stride;
+    uint32_t *keys_alt = c->keys + 2ull * c->cap_stride, *vals_alt = c->vals + 2ull * c->cap_stride;
+    float4 *records = half ? c->records2 : c->records;
+    const uint32_t n_tiles = (uint32_t)(c->tiles_x * c->tiles_y);
+
+    // ---- front: rasterizer.gd:127-128 (clear M = this frame's history slot + the scan links), then the projection ----
+    if (overlap && c->front_gate) GSR_CUDA_TRY(cudaStreamWaitEvent(fs, c->front_gate, 0));
+    {
         uint32_t links = projection_num_blocks((uint32_t)c->max_splats);
         if (gf) {
             const uint64_t first = (uint64_t)c->grp.rank * c->grp.slice;
             const uint64_t count = first < c->max_splats ? ((c->max_splats - first) < c->grp.slice ? (c->max_splats - first) : c->grp.slice) : 0;
             links = projection_scatter_blocks((uint32_t)count) * (uint32_t)c->grp.world;
         }
-#ifdef GSR_FRAME_CLEAR_MEMSET
-        GSR_CUDA_TRY(cudaMemsetAsync(c->frame, 0, sizeof(FrameState), s));
-        GSR_CUDA_TRY(cudaMemsetAsync(c->lookback, 0, sizeof(unsigned long long) * links, s));
-        GSR_CUDA_TRY(cudaMemsetAsync(c->bounds, 0, sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y, s));
-#else
-        if ((rc = launch_frame_clear(c->frame, c->lookback, links, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), s))) return rc;
+        // serial: one kernel clears the tile bounds as well; overlapped: the bounds belong to the back part (the previous frame's
+        // compositor may still read them)
+        if ((rc = launch_frame_clear(c->frame, c->lookback, links, overlap ? nullptr : c->bounds, overlap ? 0u : n_tiles, fs))) return rc;
         launches += 1;
-#endif
     }
-    GSR_CUDA_TRY(cudaEventRecord(ev[0], s));  // 'Start'
+    GSR_CUDA_TRY(cudaEventRecord(ev[0], fs));  // 'Start'
 
     ProjectionArgs pa;
     // the reference dispatches over splat_buffer.length() = point_cloud.size every frame (rasterizer.gd:83,134), i.e. also over the
@@ -533,7 +592,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     memcpy(pa.vp, view_proj, sizeof pa.vp);
     pa.u = u;
     frame_constants(view_proj, u, pa);
-    const bool fast = c->row_mod > 1 && !gf;   // group mode is exact: the frame-global last tile travels with the extents
+    const bool fast = c->row_mod > 1 && !gf;   // group mode is exact: the frame-global last tile travels with the pairs
     pa.band_y0 = c->band_y0; pa.band_y1 = c->band_y1;
     pa.row_mod = c->row_mod; pa.row_rem = c->row_rem;
     // Conservative early reject + compaction of the survivors over 1024-splat CTAs (projection_sharded_kernel): exact, and
@@ -545,13 +604,12 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     // full frame: 12 of 32 lanes (below that, per-lane 128-bit gathers move fewer bytes); sharded: few lanes of a warp land in
     // this rank's rows and the latency-bound gather path was measured slower than fetching the whole 6 KB slice (0.60 vs 0.46 ms)
     pa.sh_bulk_min = (fast || c->row_mod > 1) ? 1 : 12;
-    pa.records = c->records; pa.keys = c->keys; pa.values = c->vals; pa.capacity = (uint32_t)c->capacity;
+    pa.records = records; pa.keys = keys_in; pa.values = vals_in; pa.capacity = (uint32_t)c->capacity;
     pa.lookback = c->lookback; pa.frame = c->frame;
-    float4 *records = c->records;
     if (gf) {
         // group mode: the projection is sharded by SPLATS.  This rank projects its slice and stores every pair and record into the
-        // memory of the rank that owns it (peer stores over NVLink); then it waits for the other sources' flags and packs what it
-        // received -- its own rows' pairs of ALL splats, in splat-id order -- into the sort input.
+        // memory of the rank that owns it (peer stores over NVLink); the back part then waits for the other sources' flags and packs
+        // what it received -- its own rows' pairs of ALL splats, in splat-id order -- into the sort input.
         const int G = c->grp.world;
         ScatterPeers sp;
         memset(&sp, 0, sizeof sp);
@@ -568,43 +626,50 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
             sp.flags[d] = c->grp.flags[d];
         }
         sp.lookback = c->lookback;
-        if ((rc = launch_projection_scatter(pa, sp, s))) return rc;
-#ifdef GSR_GROUP_PROBE
-        for (int k = 0; k < 2; ++k) if (!c->probe_ev[slot][k]) cudaEventCreate(&c->probe_ev[slot][k]);
-        cudaEventRecord(c->probe_ev[slot][0], s);
-#endif
-        char *mine = c->grp.peer_arena[c->grp.rank];
-        if ((rc = launch_group_wait_segments(c->grp.flags[c->grp.rank], gf->parity, G, gf->seq, c->grp.seg_cap, (uint32_t)c->capacity, c->frame, s))) return rc;
-#ifdef GSR_GROUP_PROBE
-        cudaEventRecord(c->probe_ev[slot][1], s);
-#endif
-        if ((rc = launch_gather_segments(c->grp.flags[c->grp.rank], G, c->grp.seg_cap,
-                                         reinterpret_cast<const uint32_t *>(mine + arena_rx_keys_off(c->grp.rx_capacity, gf->parity)),
-                                         reinterpret_cast<const uint32_t *>(mine + arena_rx_vals_off(c->grp.rx_capacity, gf->parity)), c->keys, c->vals,
-                                         c->sm_count * 8, s))) return rc;
-        records = reinterpret_cast<float4 *>(mine + arena_records_off(c->grp.rx_capacity, c->max_splats, gf->parity));
-        c->grp.records_cur = records;
-        launches += 3;
+        if ((rc = launch_projection_scatter(pa, sp, fs))) return rc;
+        launches += 1;
     } else {
-        if ((rc = launch_projection(pa, s))) return rc;
+        if ((rc = launch_projection(pa, fs))) return rc;
         launches += pa.num_splats ? 1 : 0;
     }
-    GSR_CUDA_TRY(cudaEventRecord(ev[1], s));  // 'Projection'
+    GSR_CUDA_TRY(cudaEventRecord(ev[1], fs));  // end of the front part
+
+    // ---- back ----
+    if (overlap) {
+        GSR_CUDA_TRY(cudaStreamWaitEvent(s, ev[1], 0));
+        if ((rc = launch_frame_clear(nullptr, nullptr, 0u, c->bounds, n_tiles, s))) return rc;
+        launches += 1;
+    }
+    GSR_CUDA_TRY(cudaEventRecord(ev[2], s));
+    if (gf) {
+        const int G = c->grp.world;
+        char *mine = c->grp.peer_arena[c->grp.rank];
+        if ((rc = launch_group_wait_segments(c->grp.flags[c->grp.rank], gf->parity, G, gf->seq, c->grp.seg_cap, (uint32_t)c->capacity, c->frame, s))) return rc;
+        if ((rc = launch_gather_segments(c->grp.flags[c->grp.rank], G, c->grp.seg_cap,
+                                         reinterpret_cast<const uint32_t *>(mine + arena_rx_keys_off(c->grp.rx_capacity, gf->parity)),
+                                         reinterpret_cast<const uint32_t *>(mine + arena_rx_vals_off(c->grp.rx_capacity, gf->parity)), keys_in, vals_in,
+                                         c->sm_count * 8, s))) return rc;
+        records = reinterpret_cast<float4 *>(mine + arena_records_off(c->grp.rx_capacity, c->max_splats, gf->parity));
+        launches += 2;
+    }
+    c->keys_cur = keys_in; c->vals_cur = vals_in; c->records_cur = records;
+    GSR_CUDA_TRY(cudaEventRecord(ev[3], s));  // 'Projection' = front + receive
 
     if (c->keep_unsorted) {
-        GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_keys, c->keys, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
-        GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_vals, c->vals, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
+        GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_keys, keys_in, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
+        GSR_CUDA_TRY(cudaMemcpyAsync(c->unsorted_vals, vals_in, sizeof(uint32_t) * c->capacity, cudaMemcpyDeviceToDevice, s));
     }
     const uint32_t *m_ptr = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(c->frame) + offsetof(FrameState, dup_sorted));
-    if ((rc = sort_pairs_device(c->sort, c->keys, c->vals, m_ptr, c->keys + c->capacity, c->vals + c->capacity, s, &launches))) return rc;
-    GSR_CUDA_TRY(cudaEventRecord(ev[2], s));  // 'Sort'
+    if ((rc = sort_pairs_device(c->sort, keys_in, vals_in, m_ptr, keys_alt, vals_alt, s, &launches))) return rc;
+    GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Sort'
 
     const int sharded = fast ? 2 : ((!(c->band_y0 == 0 && c->band_y1 == c->tiles_y) || c->row_mod > 1) ? 1 : 0);
     if (fast) GSR_CUDA_TRY(cudaMemsetAsync(c->sync_word, 0, sizeof(int32_t), s));
     const int quirks = (c->flags & GSR_FLAG_FIXED_RANGES) ? 0 : 1;
-    if ((rc = launch_tile_ranges(c->keys, c->frame, c->bounds, (uint32_t)(c->tiles_x * c->tiles_y), quirks, sharded, fast ? c->sync_word : nullptr, c->sm_count * 8, s))) return rc;
+    if ((rc = launch_tile_ranges(keys_in, c->frame, c->bounds, n_tiles, quirks, sharded, fast ? c->sync_word : nullptr, c->sm_count * 8, s))) return rc;
     launches += 1;
-    GSR_CUDA_TRY(cudaEventRecord(ev[3], s));  // 'Boundaries'
+    GSR_CUDA_TRY(cudaEventRecord(ev[5], s));  // 'Boundaries'
+    c->front_gate = ev[5];   // the next frame's front part may start here, beside this frame's compositor
 
     CompositeArgs ca;
     float4 *out_fb = c->fb_ext ? c->fb_ext : (target ? target : c->fb);
@@ -614,7 +679,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
         if (c->copied_valid[i] && owned == out_fb) GSR_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_copied[i], 0));
     }
     c->fb_last = out_fb;
-    ca.records = records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = out_fb;
+    ca.records = records; ca.values = vals_in; ca.bounds = c->bounds; ca.out = out_fb;
     ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
     {   // owned tile rows: band rows with row % row_mod == row_rem
         int first = c->band_y0 + ((c->row_rem - c->band_y0 % c->row_mod) + c->row_mod) % c->row_mod;
@@ -652,7 +717,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
         if ((rc = launch_group_signal_done(group_peers(c, gf->parity), 0, c->grp.rank, gf->seq, s))) return rc;
         launches += 1;
     }
-    GSR_CUDA_TRY(cudaEventRecord(ev[4], s));  // 'Render'
+    GSR_CUDA_TRY(cudaEventRecord(ev[6], s));  // 'Render'
     // this frame's counters (M, overflow, C) to the pinned mirror: what track_capacity() reads without ever syncing
     // (a 16-byte-store kernel into mapped pinned memory, NOT a cudaMemcpyAsync: a D2H copy on the render stream would queue behind the
     // frame read-back on the copy engine and serialise the two streams)
@@ -714,13 +779,12 @@ static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uni
         int rc = use_device(c->device);
         if (rc) return rc;
         GroupFrame gf;
-        gf.seq = c->grp.seq + 1u; gf.parity = (int)(gf.seq & 1u);
+        gf.seq = c->grp.seq + 1u; gf.parity = (int)(gf.seq % (uint32_t)GROUP_PHASES);
         const int slot = (int)((gf.seq - 1u) & 1u);
         gf.rows_local = c->grp.present_rows;
         float4 *target = c->grp.root_fb[slot];
         if (gf.rows_local) {   // every rank presents its own rows (host consumer, one PCIe link per GPU): only its own read-back gates the slot
-            target = slot ? c->fb2 : c->fb;
-            if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+            target = slot ? c->fb2 : c->fb;   // (render_enqueue orders the compositor after the slot's read-back)
         } else if (c->grp.rank == 0) {
             if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
             if (gf.seq >= 3u && (rc = launch_group_release(group_peers(c, gf.parity), c->grp.world, gf.seq - 2u, c->stream))) return rc;
@@ -753,8 +817,7 @@ static int render_async_impl(gsr_ctx *c, const float *view_proj, const void *uni
     int rc = use_device(c->device);
     if (rc) return rc;
     const int slot = (int)(c->async_counter & 1u);
-    float4 *target = slot ? c->fb2 : c->fb;
-    if (c->copied_valid[slot]) GSR_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+    float4 *target = slot ? c->fb2 : c->fb;   // (render_enqueue orders the compositor after the slot's read-back; sort and ranges need not wait)
     if ((rc = render_enqueue(c, view_proj, uniforms32, heatmap_factor, target))) return rc;
     if ((rc = readback_enqueue(c, target, slot, pinned_host, format))) return rc;
     c->async_counter += 1;
@@ -891,7 +954,7 @@ GSR_API int gsr_group_export(gsr_ctx *c, void *blob) {
     int rc = use_device(c->device);
     if (rc) return rc;
     if (!c->grp.arena) {
-        c->grp.rx_capacity = c->capacity;   // the receive segments of all sources together hold as many pairs as one sort input
+        c->grp.rx_capacity = (c->capacity + 1023ull) & ~1023ull;   // the receive segments of all sources together hold as many pairs as one sort input
         const size_t bytes = arena_bytes(c->grp.rx_capacity, c->max_splats);
         cudaError_t e = cudaMalloc(&c->grp.arena, bytes);
         if (e != cudaSuccess) { set_last_error("cudaMalloc(group arena, %zu B) -> %s", bytes, cudaGetErrorString(e)); c->grp.arena = nullptr; return GSR_ERR_OOM; }
@@ -969,8 +1032,7 @@ GSR_API int gsr_group_attach(gsr_ctx *c, int32_t rank, int32_t world, const void
     GSR_CUDA_TRY(cudaMemsetAsync(c->grp.arena, 0, GROUP_FLAGS_BYTES, c->stream));   // flags start at seq 0 (all ranks attach, then barrier)
     GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->grp.rank = rank; c->grp.world = world; c->grp.slice = slice; c->grp.seq = 0;
-    c->grp.seg_cap = (uint32_t)(c->grp.rx_capacity / (uint64_t)world);
-    c->grp.records_cur = nullptr;
+    c->grp.seg_cap = (uint32_t)(c->grp.rx_capacity / (uint64_t)world) & ~3u;   // segments start 16-byte aligned
     c->row_mod = world; c->row_rem = rank;   // cyclic tile rows: balanced by construction
     c->band_y0 = 0; c->band_y1 = c->tiles_y; c->band_set = false;
     c->copied_valid[0] = c->copied_valid[1] = false;
@@ -1030,7 +1092,7 @@ GSR_API int gsr_pick(gsr_ctx *c, uint32_t tile_id, float heatmap_factor, float o
     const uint32_t t0 = (uint32_t)(c->band_y0 * c->tiles_x), t1 = (uint32_t)(c->band_y1 * c->tiles_x);
     if (tile_id < T && tile_id >= t0 && tile_id < t1 && (int)(tile_id / (uint32_t)c->tiles_x) % c->row_mod == c->row_rem) {
         CompositeArgs ca;
-        ca.records = (c->grp.world > 1 && c->grp.records_cur) ? c->grp.records_cur : c->records; ca.values = c->vals; ca.bounds = c->bounds; ca.out = framebuffer(c);
+        ca.records = c->records_cur; ca.values = c->vals_cur; ca.bounds = c->bounds; ca.out = framebuffer(c);
         ca.width = c->width; ca.height = c->height; ca.tiles_x = c->tiles_x;
         ca.tile_begin = (int32_t)tile_id; ca.num_tiles = 1; ca.row_step = 1;
         ca.heatmap_factor = heatmap_factor; ca.target_tile_id = tile_id; ca.pick = c->pick;
@@ -1068,9 +1130,7 @@ GSR_API int gsr_get_stats(gsr_ctx *c, gsr_stats *out) {
     out->kernel_launches = c->last_launches;
     out->staged = fs.staged;
     if (c->ev_valid && c->frame_counter > 0) {
-        cudaEvent_t *ev = c->ev + 5 * ((c->frame_counter - 1) % GSR_HISTORY_FRAMES);
-        for (int i = 0; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[i], ev[i], ev[i + 1]));
-        GSR_CUDA_TRY(cudaEventElapsedTime(&out->stage_ms[4], ev[0], ev[4]));
+        if ((rc = stage_times(c, (uint32_t)((c->frame_counter - 1) % GSR_HISTORY_FRAMES), out->stage_ms, nullptr))) return rc;
     }
     return GSR_OK;
 }
@@ -1093,9 +1153,7 @@ GSR_API int gsr_get_frame_history(gsr_ctx *c, uint32_t max_frames, gsr_frame_rec
         gsr_frame_record &r = out[k];
         memset(&r, 0, sizeof r);
         r.frame_index = fi; r.duplicates = fs.dup_total; r.visible = fs.visible; r.staged = fs.staged; r.overflow = fs.overflow;
-        cudaEvent_t *ev = c->ev + 5 * slot;
-        for (int i = 0; i < 4; ++i) GSR_CUDA_TRY(cudaEventElapsedTime(&r.stage_ms[i], ev[i], ev[i + 1]));
-        GSR_CUDA_TRY(cudaEventElapsedTime(&r.stage_ms[4], ev[0], ev[4]));
+        if ((rc = stage_times(c, slot, r.stage_ms, &r.front_ms))) return rc;
     }
     *n_out = (uint32_t)n;
     return GSR_OK;
@@ -1119,24 +1177,15 @@ GSR_API int gsr_debug_compositor_config(gsr_ctx *c, int32_t ctas_per_sm, int32_t
     return GSR_OK;
 }
 
-#ifdef GSR_GROUP_PROBE
-// ubench builds only: mean (scatter kernel, segment wait, gather) ms over the frames of the history ring (call after gsr_sync)
-GSR_API int gsr_debug_group_probe(gsr_ctx *c, float out[3]) {
-    if (!c || !out) return GSR_ERR_INVALID;
-    double acc[3] = {0, 0, 0}; int n = 0;
-    for (uint32_t slot = 0; slot < GSR_HISTORY_FRAMES; ++slot) {
-        if (!c->probe_ev[slot][0] || !c->probe_ev[slot][1]) continue;
-        cudaEvent_t *ev = c->ev + 5 * slot;
-        float a, b, d;
-        if (cudaEventElapsedTime(&a, ev[0], c->probe_ev[slot][0]) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (cudaEventElapsedTime(&b, c->probe_ev[slot][0], c->probe_ev[slot][1]) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (cudaEventElapsedTime(&d, c->probe_ev[slot][1], ev[1]) != cudaSuccess) { cudaGetLastError(); continue; }
-        acc[0] += a; acc[1] += b; acc[2] += d; ++n;
-    }
-    for (int k = 0; k < 3; ++k) out[k] = n ? (float)(acc[k] / n) : 0.f;
+GSR_API int gsr_debug_pipeline(gsr_ctx *c, int32_t overlap) {
+    if (!c) return GSR_ERR_INVALID;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->front_stream));
+    GSR_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->overlap = overlap < 0 ? -1 : (overlap != 0); c->front_gate = nullptr;
     return GSR_OK;
 }
-#endif
 
 GSR_API int gsr_debug_enable_trace(gsr_ctx *c, uint32_t max_items) {
     if (!c) return GSR_ERR_INVALID;
@@ -1161,9 +1210,9 @@ GSR_API int gsr_debug_copy(gsr_ctx *c, int which, void *dst, size_t bytes) {
     const void *src = nullptr;
     size_t avail = 0;
     switch (which) {
-        case GSR_BUF_RECORDS: src = (c->grp.world > 1 && c->grp.records_cur) ? c->grp.records_cur : c->records; avail = sizeof(float4) * 3ull * c->max_splats; break;
-        case GSR_BUF_KEYS: src = c->keys; avail = sizeof(uint32_t) * c->capacity; break;
-        case GSR_BUF_VALUES: src = c->vals; avail = sizeof(uint32_t) * c->capacity; break;
+        case GSR_BUF_RECORDS: src = c->records_cur; avail = sizeof(float4) * 3ull * c->max_splats; break;
+        case GSR_BUF_KEYS: src = c->keys_cur; avail = sizeof(uint32_t) * c->capacity; break;
+        case GSR_BUF_VALUES: src = c->vals_cur; avail = sizeof(uint32_t) * c->capacity; break;
         case GSR_BUF_BOUNDS: src = c->bounds; avail = sizeof(uint2) * (size_t)c->tiles_x * c->tiles_y; break;
         case GSR_BUF_KEYS_UNSORTED: src = c->unsorted_keys; avail = c->unsorted_keys ? sizeof(uint32_t) * c->capacity : 0; break;
         case GSR_BUF_VALUES_UNSORTED: src = c->unsorted_vals; avail = c->unsorted_vals ? sizeof(uint32_t) * c->capacity : 0; break;

@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2 *__restric
 }
 
 // Start of a frame (rasterizer.gd:127-128): this frame's counters, the projection's scan links and the tile bounds back to zero.
-// One kernel instead of three cudaMemsetAsync: fewer stream operations per frame, and nothing on the render stream that the
-// driver may hand to a copy engine (where it would queue behind a frame read-back in flight).
+// One kernel instead of three cudaMemsetAsync (fewer stream operations per frame); any of the three parts may be absent
+// (overlapped frames clear the bounds at the start of the back part: gsr_api.cu).
 __global__ void __launch_bounds__(256) frame_clear_kernel(unsigned long long *frame_words, uint32_t n_frame, unsigned long long *links, uint32_t n_links,
                                                             unsigned long long *bounds, uint32_t n_bounds) {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -142,7 +142,7 @@ int launch_frame_clear(FrameState *frame, unsigned long long *links, uint32_t n_
     const uint32_t most = n_links > n_bounds ? n_links : n_bounds;
     uint32_t grid = (most + 255u) / 256u;
     grid = grid < 1u ? 1u : (grid > 296u ? 296u : grid);
-    frame_clear_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<unsigned long long *>(frame), (uint32_t)(sizeof(FrameState) / 8), links, n_links,
+    frame_clear_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<unsigned long long *>(frame), frame ? (uint32_t)(sizeof(FrameState) / 8) : 0u, links, n_links,
                                                  reinterpret_cast<unsigned long long *>(bounds), n_bounds);
     GSR_CUDA_TRY(cudaGetLastError());
     return GSR_OK;

@@ -166,6 +166,10 @@ class GaussianSplattingRasterizer:
         else:
             _lib.check(L.gsr_render_async_fmt(self._ctx, vpp, uniforms32, float(heatmap), hp, int(fmt)), "gsr_render_async_fmt")
 
+    def debug_pipeline(self, overlap: int) -> None:
+        """gsr_debug_pipeline: 1 / 0 = front/back overlap of consecutive frames on / off, -1 = automatic (include/gsr.h)."""
+        _lib.check(_lib.lib().gsr_debug_pipeline(self._ctx, int(overlap)), "gsr_debug_pipeline")
+
     def set_stream(self, cuda_stream: int) -> None:
         _lib.check(_lib.lib().gsr_set_stream(self._ctx, C.c_void_p(cuda_stream)), "gsr_set_stream")
 

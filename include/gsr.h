@@ -102,8 +102,9 @@ typedef struct gsr_frame_record {
     uint64_t staged;      /* C */
     uint32_t overflow;
     uint32_t reserved;
-    float stage_ms[5];    /* Projection, Sort, Boundaries, Render, total -- CUDA events on the render stream */
-    float reserved2;
+    float stage_ms[5];    /* Projection, Sort, Boundaries, Render, total (= their sum) -- GPU time between CUDA events around every stage */
+    float front_ms;       /* the part of Projection that ran on the front stream (clear + projection kernel): overlapped with the previous
+                             frame's compositor when frames are enqueued back to back, so the frame period is shorter than `total` */
 } gsr_frame_record;
 
 /* ---- lifecycle: replaces _init/init_gpu/cleanup_gpu (rasterizer.gd:59-120) and RenderingContext
@@ -257,6 +258,12 @@ GSR_API int gsr_debug_enable_trace(gsr_ctx *ctx, uint32_t max_items);
  * longest-chain-first ticket order (default on), and the sparse-frame rule of that order pass: with at most
  * sparse_tiles_per_sm * SMs occupied tiles only one CTA per SM works (default 5; 0 = never). */
 GSR_API int gsr_debug_compositor_config(gsr_ctx *ctx, int32_t ctas_per_sm, int32_t longest_first, int32_t sparse_tiles_per_sm);
+/* Front / back overlap of consecutive frames (results never depend on it): 1 = a frame's clear + projection run on a second
+ * stream, released when the previous frame's tile ranges are done, i.e. beside that frame's compositor; 0 = every kernel of a
+ * frame on the render stream, frames strictly one after the other; -1 (default) = automatic: on for a context attached to a shard
+ * group (the scatter projection hides behind the compositor and the ranks' skew), off for a single GPU (measured: no gain, the two
+ * kernels compete for the same issue slots). */
+GSR_API int gsr_debug_pipeline(gsr_ctx *ctx, int32_t overlap);
 /* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
 GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);
 

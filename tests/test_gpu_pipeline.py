@@ -287,6 +287,42 @@ def test_pipelined_readback_matches_sync_render():
         np.testing.assert_array_equal(bits(a), bits(b))
 
 
+def test_overlapped_frames_equal_serial_frames():
+    """Front / back overlap (gsr_debug_pipeline): frame f+1's projection runs beside frame f's compositor on a second stream, consecutive
+    frames alternate between two sort inputs and two record tables.  Back-to-back frames through pinned host memory, an upload in
+    the middle of the sequence (it must not overtake a projection in flight), a pick after the last frame: bit-identical to the
+    serial pipeline, and the first and last frame equal the oracle's."""
+    import ctypes as C
+    import torch
+    n, w, h = 150000, 1280, 720
+    cams = [make_scene(n, 23, w, h, frame=f) for f in range(0, 96, 6)]
+    splat60 = cams[0][0]
+    late = make_scene(n, 24, w, h, frame=0)[0][: n // 3]   # replaces the first third of the splats half-way through
+    results = {}
+    for overlap in (0, 1):
+        with Ctx(n, w, h) as c:
+            _lib.check(c.L.gsr_debug_pipeline(c.h, overlap), "pipeline")
+            c.upload(splat60)
+            hosts = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in cams]
+            for i, (_, vp, ub) in enumerate(cams):
+                if i == len(cams) // 2:
+                    c.upload(late)
+                c.render_async(vp, ub, host_ptr=hosts[i].data_ptr())
+            _lib.check(c.L.gsr_stream_join(c.h), "join")
+            c.sync()
+            picked = c.pick(c.stats().last_tile // 2)
+            results[overlap] = ([t.numpy().copy() for t in hosts], picked, c.taps())
+    for a, b in zip(results[0][0], results[1][0]):
+        np.testing.assert_array_equal(bits(a), bits(b))
+    np.testing.assert_array_equal(bits(results[0][1]), bits(results[1][1]))
+    np.testing.assert_array_equal(results[0][2]["keys"], results[1][2]["keys"])
+    np.testing.assert_array_equal(results[0][2]["values"], results[1][2]["values"])
+    for idx, scene in ((0, splat60), (len(cams) - 1, np.concatenate([late, splat60[n // 3:]]))):
+        _, vp, ub = cams[idx]
+        ref = orc.frame(scene, vp, orc.uniforms_from_bytes(np.frombuffer(ub, dtype=np.uint8)), cap=1000 * n)
+        np.testing.assert_array_equal(bits(results[1][0][idx]), bits(ref.rgba))
+
+
 def test_golden_demo_subset_on_gpu():
     """Real data: 8216 splats of the reference's demo.ply (tests/golden/demo_subset.npz: oracle outputs + the reference shaders' own outputs)."""
     import os
