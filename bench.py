@@ -55,7 +55,7 @@ def parse_args():
                          "into the row owners' memory over NVLink peer pointers, device-side flags); 'peer' = round-1 path: replicated cull, compositor stores bands into the root's frame over "
                          "NVLink peer memory + 4-byte NCCL sync; 'nccl' = NCCL gather of the band framebuffers")
     ap.add_argument("--overlap", type=int, default=-1, choices=[-1, 0, 1],
-                    help="front/back overlap of consecutive frames (gsr_debug_pipeline): -1 = the library's default (on in a shard group)")
+                    help="front/back overlap of consecutive frames (gsr_debug_pipeline): -1 = the library's default (off)")
     return ap.parse_args()
 
 
@@ -654,7 +654,7 @@ def main():
             "fps": fps,
             "config": make_config(args, wl),
             "run_info": {"duplicates_M": M, "visible_V": V, "staged_C": Cc, "scene_build_s": t_gen,
-                         "frame_overlap": ("on" if (args.overlap == 1 or (args.overlap < 0 and group)) else "off") +
+                         "frame_overlap": ("on" if args.overlap == 1 else "off") +
                                           ": projection of frame f+1 beside the compositor of frame f (gsr_debug_pipeline; stage_ms are per-stage GPU times, their sum exceeds the frame period when on)"},
             "e2e": {"value": e2e_value, "unit": "Msplats/s", "ms_per_step": e2e_ms / args.steps, "fps": 1000.0 / (e2e_ms / args.steps),
                     "h2d_bytes_per_step": 160, "d2h_bytes_per_step": P * 16,

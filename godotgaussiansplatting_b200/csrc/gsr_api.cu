@@ -48,7 +48,7 @@ struct gsr_ctx {
     // (back: FMA-pipe / chain bound) when the host enqueues frames back to back (gsr_render_async).  gsr_debug_pipeline(ctx, 0) = serial.
     cudaStream_t front_stream = nullptr;
     cudaEvent_t front_gate = nullptr;    // recorded after the tile ranges of the most recent frame (nullptr: nothing to wait for)
-    int overlap = -1;                    // -1 = automatic: on for a context attached to a shard group, off otherwise (measured: DESIGN.md section 6)
+    int overlap = -1;                    // -1 = default = off (measured: DESIGN.md section 6; on helps c3 on 4 GPUs by 10 %, not one GPU, and hurt c4's read-back leg)
     SortWorkspace sort;
     FrameState *ring = nullptr;  // GSR_HISTORY_FRAMES slots; slot = frame_counter % GSR_HISTORY_FRAMES
     FrameState *frame = nullptr; // slot of the most recent frame
@@ -557,7 +557,7 @@ static int render_enqueue(gsr_ctx *c, const float *view_proj, const void *unifor
     // chain bound, 1-2 small CTAs per SM), which leaves the memory system idle.  Consecutive frames alternate between two sort
     // inputs and two record tables; the back part waits for its own front part.  A host that renders one frame at a time
     // (gsr_render) sees the same kernels in the same order.
-    const bool overlap = (c->overlap < 0 ? gf != nullptr : c->overlap != 0) && c->front_stream != nullptr;
+    const bool overlap = c->overlap > 0 && c->front_stream != nullptr;
     cudaStream_t fs = overlap ? c->front_stream : s;
     int launches = 0;
     const uint32_t slot = (uint32_t)(c->frame_counter % GSR_HISTORY_FRAMES);

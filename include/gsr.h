@@ -259,10 +259,10 @@ GSR_API int gsr_debug_enable_trace(gsr_ctx *ctx, uint32_t max_items);
  * sparse_tiles_per_sm * SMs occupied tiles only one CTA per SM works (default 5; 0 = never). */
 GSR_API int gsr_debug_compositor_config(gsr_ctx *ctx, int32_t ctas_per_sm, int32_t longest_first, int32_t sparse_tiles_per_sm);
 /* Front / back overlap of consecutive frames (results never depend on it): 1 = a frame's clear + projection run on a second
- * stream, released when the previous frame's tile ranges are done, i.e. beside that frame's compositor; 0 = every kernel of a
- * frame on the render stream, frames strictly one after the other; -1 (default) = automatic: on for a context attached to a shard
- * group (the scatter projection hides behind the compositor and the ranks' skew), off for a single GPU (measured: no gain, the two
- * kernels compete for the same issue slots). */
+ * stream, released when the previous frame's tile ranges are done, i.e. beside that frame's compositor; 0 or -1 (default) = every
+ * kernel of a frame on the render stream, frames strictly one after the other.  Measured on B200: one GPU,
+ * c3: neutral (the two kernels compete for the same issue slots); shard group of 4, c3: +10 % device-resident and end to end;
+ * shard group of 4, c4: +10 % device-resident but -35 % with the rows-local read-back -- hence off by default. */
 GSR_API int gsr_debug_pipeline(gsr_ctx *ctx, int32_t overlap);
 /* Keep an unsorted copy of the emitted pairs each frame (costs 8*M bytes of traffic; off by default). */
 GSR_API int gsr_debug_keep_unsorted(gsr_ctx *ctx, int enable);

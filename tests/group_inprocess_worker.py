@@ -26,6 +26,7 @@ def main():
     G = int(sys.argv[1])
     n, w, h = (int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (30000, 640, 360)
     boost = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
+    overlap = int(sys.argv[6]) if len(sys.argv) > 6 else -1    # gsr_debug_pipeline: front/back overlap of consecutive frames
     gx = (w + 15) // 16
     frames = [make_scene(n, 41, w, h, frame=f, scale_boost=boost) for f in (0, 45, 90, 135, 180, 225)]
     splat60 = frames[0][0]
@@ -36,6 +37,7 @@ def main():
         blobs = b"".join(c.group_export() for c in ctxs)
         for r, c in enumerate(ctxs):
             c.group_attach(r, G, blobs)
+            _lib.check(c.L.gsr_debug_pipeline(c.h, overlap), "gsr_debug_pipeline")
         hosts = [pinned((h, w, 4)) for _ in frames]
         for k, (_, vp, ub) in enumerate(frames):
             for c in ctxs:                      # every rank enqueues the frame; nothing blocks on the host
