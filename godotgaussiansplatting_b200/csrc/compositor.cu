@@ -48,6 +48,15 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f3
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// a*b + c with TWO roundings per lane, for the uncontracted evaluation.  ptxas (12.9, sm_100a) contracts a mul.rn.f32x2 whose only use
+// is an add.rn.f32x2 into one FFMA2 -- in spite of the .rn qualifiers and of -fmad=false (cuobjdump: 44 FFMA2 where the PTX has 24
+// fma.rn.f32x2; tests/test_gpu_pipeline.py::test_uncontracted_blend_flag_... caught it on silicon).  It honours the scalar .rn pair.
+__device__ __forceinline__ u64 mul_add2_unfused(u64 a, u64 b, u64 c) {
+    float al, ah, bl, bh, cl, ch;
+    asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(al), "=f"(ah) : "l"(a));
+    upk(b, bl, bh); upk(c, cl, ch);
+    return pk(__fadd_rn(__fmul_rn(al, bl), cl), __fadd_rn(__fmul_rn(ah, bh), ch));
+}
 #else  // tests/kernel_emu: the kernels of this file compiled for the CPU (test infrastructure; libgsr never defines GSR_CPU_EMU).
        // A packed op is two independent IEEE binary32 operations -- exactly what the PTX f32x2 instructions are.
 inline u64 pk(float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (u64)a | ((u64)b << 32); }
@@ -56,6 +65,7 @@ inline u64 fma2(u64 a, u64 b, u64 c) { float al, ah, bl, bh, cl, ch; upk(a, al, 
 inline u64 mul2(u64 a, u64 b) { float al, ah, bl, bh; upk(a, al, ah); upk(b, bl, bh); return pk(al * bl, ah * bh); }
 inline u64 add2(u64 a, u64 b) { float al, ah, bl, bh; upk(a, al, ah); upk(b, bl, bh); return pk(al + bl, ah + bh); }
 inline u64 sub2(u64 a, u64 b) { float al, ah, bl, bh; upk(a, al, ah); upk(b, bl, bh); return pk(al - bl, ah - bh); }
+inline u64 mul_add2_unfused(u64 a, u64 b, u64 c) { return add2(mul2(a, b), c); }
 #endif
 __device__ __forceinline__ u64 bc(float x) { return pk(x, x); }
 
@@ -124,16 +134,15 @@ __device__ __forceinline__ void phase_a(const float4 A[GU], const float4 B[GU], 
 #pragma unroll
     for (int u = 0; u < GU; ++u) pw2[u] = mul2(bc(A[u].z), ox2[u]);
 #pragma unroll
-    for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], ox2[u]);
-#pragma unroll
     for (int u = 0; u < GU; ++u) {
         const float czoy = A[u].w * oy[u];
-        pw2[u] = CONTRACT ? fma2(bc(czoy), bc(oy[u]), pw2[u]) : add2(pw2[u], bc(czoy * oy[u]));
+        if (CONTRACT) pw2[u] = fma2(bc(czoy), bc(oy[u]), mul2(pw2[u], ox2[u]));
+        else pw2[u] = mul_add2_unfused(pw2[u], ox2[u], bc(__fmul_rn(czoy, oy[u])));   // (the second product must not fuse with the sum either)
     }
 #pragma unroll
     for (int u = 0; u < GU; ++u) e2[u] = mul2(bc(B[u].x), ox2[u]);
 #pragma unroll
-    for (int u = 0; u < GU; ++u) pw2[u] = CONTRACT ? fma2(e2[u], bc(oy[u]), pw2[u]) : add2(pw2[u], mul2(e2[u], bc(oy[u])));
+    for (int u = 0; u < GU; ++u) pw2[u] = CONTRACT ? fma2(e2[u], bc(oy[u]), pw2[u]) : mul_add2_unfused(e2[u], bc(oy[u]), pw2[u]);
     // exp(power): det_exp(), two lanes at a time
 #pragma unroll
     for (int u = 0; u < GU; ++u) pw2[u] = mul2(pw2[u], K.L2E2);
@@ -197,9 +206,9 @@ __device__ __forceinline__ void phase_b(const float4 B[GU], const float *s_c, in
             cg2 = fma2(mul2(bc(B[u].w), m2), t2, cg2);
             cb2 = fma2(mul2(bc(cbl), m2), t2, cb2);
         } else {
-            cr2 = add2(cr2, mul2(mul2(bc(B[u].z), m2), t2));
-            cg2 = add2(cg2, mul2(mul2(bc(B[u].w), m2), t2));
-            cb2 = add2(cb2, mul2(mul2(bc(cbl), m2), t2));
+            cr2 = mul_add2_unfused(mul2(bc(B[u].z), m2), t2, cr2);
+            cg2 = mul_add2_unfused(mul2(bc(B[u].w), m2), t2, cg2);
+            cb2 = mul_add2_unfused(mul2(bc(cbl), m2), t2, cb2);
         }
         t0 = a0 ? pl : t0;
         t1 = a1 ? ph : t1;

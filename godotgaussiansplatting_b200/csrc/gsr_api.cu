@@ -435,7 +435,7 @@ GSR_API int gsr_set_band(gsr_ctx *c, int32_t row_begin, int32_t row_end) {
     return GSR_OK;
 }
 
-// Per-frame constants of the projection (shared by gsr_render and the experimental gsr_shard_extents_compute).
+// Per-frame constants of the projection: project_covariance's focal / limit terms and the norm bound of the conservative reject.
 static void frame_constants(const float *view_proj, const Uniforms &u, ProjectionArgs &pa) {
     {   // per-frame constants of project_covariance, same IEEE binary32 operations as gsplat_projection.glsl:127-133
         const float tfi0 = view_proj[16 + 0], tfi1 = view_proj[16 + 5];
@@ -1067,7 +1067,7 @@ GSR_API int gsr_sync(gsr_ctx *c) {
         GSR_CUDA_TRY(cudaMemcpy(&err, &c->grp.flags[c->grp.rank]->error, sizeof err, cudaMemcpyDeviceToHost));
         if (err) {
             cudaMemset(&c->grp.flags[c->grp.rank]->error, 0, sizeof err);
-            set_last_error("group: a device-side wait timed out (%s)", err == 1 ? "extent slices of a peer" : "done / released flag");
+            set_last_error("group: a device-side wait timed out (%s)", err == 1 ? "segments of a peer" : "done / released flag");
             return GSR_ERR_STATE;
         }
     }

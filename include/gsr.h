@@ -205,15 +205,17 @@ GSR_API int gsr_stream_join(gsr_ctx *ctx);
 
 /* ---- Multi-GPU shard group (no reference counterpart -- the reference is single-device).  One context per GPU,
  *      in one process (a thread per GPU) or in one process per GPU.  The frame path of an attached group uses neither the
- *      host nor NCCL: per frame every rank (1) culls ITS slice of the splats and stores their tile-row extents into every rank's
- *      table with peer stores over NVLink/NVSwitch, (2) runs the projection maths only for the splats whose tile rows it owns
- *      (cyclic rows: row % world == rank), sorts and scans its own pairs, (3) composites its rows straight into the presenting
- *      rank's (rank 0) frame; sequence-numbered flag words written with system-scope stores order all of it on the devices.
+ *      host nor NCCL: per frame every rank (1) projects ITS slice of the splats (cull, EWA, SH: once per splat in the whole group) and
+ *      stores every (key, value) pair and every 48-byte record into the memory of the rank that owns the pair's tile row
+ *      (cyclic rows: row % world == rank) with peer stores over NVLink/NVSwitch, in splat-id order per destination, (2) packs,
+ *      sorts and scans the pairs it received, (3) composites its rows straight into the presenting rank's (rank 0) frame, or
+ *      keeps them (gsr_group_set_present); sequence-numbered flag words behind one system-scope fence per kernel order all of
+ *      it on the devices.
  *      Results are bit-identical to the single-GPU frame (same rects, same emission order, exact Q10 bookkeeping).
  *        every rank:  gsr_resize; gsr_group_export(ctx, blob)            -> exchange the blobs (any transport)
  *                     gsr_group_attach(ctx, rank, world, all_blobs)       -> barrier once (any transport)
  *        per frame:   gsr_render_async(ctx, vp, uniforms, heat, NULL) on every rank (same frame order everywhere);
- *                     rank 0: gsr_readback_async(ctx, pinned, rgb_only) and/or gsr_framebuffer_device_ptr
+ *                     rank 0: gsr_readback_async(ctx, pinned, format) and/or gsr_present_device / gsr_framebuffer_device_ptr
  *      gsr_resize detaches (export / attach again).  A lost peer makes the bounded device-side waits expire: gsr_sync then
  *      returns GSR_ERR_STATE instead of the GPU hanging. ---- */
 #define GSR_GROUP_BLOB_BYTES 320

@@ -1,5 +1,5 @@
 """Worker of tests/test_gpu_group.py: a shard group of G contexts living in ONE process on ONE GPU (each on its own stream) --
-the same device-side protocol as one context per GPU (extent slices exchanged with "peer" stores, flag words, rows composited
+the same device-side protocol as one context per GPU (pairs and records scattered with "peer" stores, flag words, rows composited
 into rank 0's frames), exercised without a multi-GPU box.  Rank 0's frames must equal the oracle's bit for bit and every rank's
 sorted pairs must be exactly the single-GPU pairs of the tile rows it owns.
 CUDA_DEVICE_MAX_CONNECTIONS is raised by the caller: 2 streams per context must not share a hardware queue, or a spinning

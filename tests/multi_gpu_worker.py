@@ -83,7 +83,7 @@ def main():
             assert np.array_equal(got.view(np.uint32), ref.rgba.view(np.uint32)), "gathered frame differs"
             print("NCCL_GATHER_OK", flush=True)
     dist.barrier()
-    # ---- (c) shard group: NCCL-free frame path (extent slices + rows over NVLink peer memory, device-side flags) ----
+    # ---- (c) shard group: NCCL-free frame path (pairs, records and rows over NVLink peer memory, device-side flags) ----
     gx = (w + 15) // 16
     with Ctx(n, w, h, device=local) as c:
         _lib.check(L.gsr_set_stream(c.h, C.c_void_p(stream.cuda_stream)), "stream")

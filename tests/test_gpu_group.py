@@ -1,5 +1,5 @@
 """Shard-group protocol (include/gsr.h gsr_group_*; csrc/group.cu) on ONE GPU: G contexts in one process, each on its own
-stream, run the full NCCL-free multi-GPU frame path -- extent slices with "peer" stores, flag words, rows composited into
+stream, run the full NCCL-free multi-GPU frame path -- scatter projection with "peer" stores, flag words, rows composited into
 rank 0's frames, pipelined read-back with slot release -- and must reproduce the oracle bit for bit.  The multi-process /
 multi-GPU version of the same check is tests/test_gpu_multi.py."""
 import os
