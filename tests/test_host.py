@@ -158,6 +158,30 @@ def test_bench_reference_arm_contract():
     assert "unavailable" in ref or (ref["kind"] == "reference" and ref["keys_and_ranges_identical_to_port"])
 
 
+def test_bench_config_is_a_function_of_the_command_line_only():
+    """Both bench arms must print the SAME `config` for the same workload and GPU count (the driver compares them), and the default
+    multi-GPU path is the shard group with the rows-local read-back."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    old = sys.argv
+    try:
+        cfgs = {}
+        for impl in ("gsr", "reference"):
+            for n in (1, 2, 8):
+                sys.argv = ["bench.py", "--impl", impl, "--gpus", str(n)]
+                args = bench.parse_args()
+                assert args.mgpu == "group" and args.present == "rows" and args.overlap == -1
+                cfgs[impl, n] = bench.make_config(args, dict(bench.WORKLOADS[args.workload]))
+    finally:
+        sys.argv = old
+    for n in (1, 2, 8):
+        assert cfgs["gsr", n] == cfgs["reference", n]
+    assert cfgs["gsr", 1]["parallelism"] == "single GPU" and cfgs["gsr", 1]["workload"].startswith("c3")
+    assert "scattered to the row owners" in cfgs["gsr", 8]["parallelism"] and "x8" in cfgs["gsr", 8]["parallelism"]
+
+
 def test_free_look_camera_orbits_like_util_camera_gd():
     """Scope row f4: FreeLookCamera restates util/camera.gd's orbit (set_focused_position :144-149, ORBIT mouse motion :52-60, the
     t = 1 steady state of _update_movement :127-141): the camera stays on a sphere about the focused position, always looks at it,
